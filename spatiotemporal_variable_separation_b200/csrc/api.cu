@@ -1,0 +1,75 @@
+// C-ABI plumbing: error text, launch accounting, and the convolution dispatch (tcgen05 path for the
+// eligible bf16 layers, CUDA-core gather-GEMM for everything else).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vs {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return 1;
+}
+
+int launched(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = 148;   // B200
+        }
+    }
+    return n;
+}
+
+int conv_forward_simt(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
+                      double* stats, cudaStream_t stream);
+int conv_wgrad_simt(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream);
+
+static int check_geom(const vs_conv_geom* g) {
+    VS_REQUIRE(g != nullptr, "null geometry");
+    VS_REQUIRE(g->dtype == VS_F32 || g->dtype == VS_BF16, "unsupported dtype %d", g->dtype);
+    VS_REQUIRE(g->N >= 1 && g->H >= 1 && g->W >= 1 && g->C >= 1 && g->K >= 1 && g->R >= 1 && g->S >= 1 && g->stride >= 1 && g->pad >= 0,
+               "bad convolution geometry");
+    VS_REQUIRE(g->P == (g->H + 2 * g->pad - g->R) / g->stride + 1 && g->Q == (g->W + 2 * g->pad - g->S) / g->stride + 1,
+               "P/Q inconsistent with H/W, filter, stride and pad");
+    VS_REQUIRE(g->groups >= 1 && g->N % g->groups == 0, "N=%d not divisible by groups=%d", g->N, g->groups);
+    return 0;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_abi_version(void) { return 1; }
+extern "C" const char* vs_last_error(void) { return g_last_error.c_str(); }
+extern "C" int64_t vs_launch_count(void) { return g_launches.load(); }
+
+extern "C" int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* in, const void* wp, const float* bias,
+                               void* out, double* stats, void* stream) {
+    if (int rc = check_geom(g)) return rc;
+    VS_REQUIRE(mode == VS_CONV_DIRECT || mode == VS_CONV_TRANSPOSED, "bad mode %d", mode);
+    VS_REQUIRE(stats == nullptr || g->act == VS_ACT_NONE, "statistics are taken of the pre-activation: act must be NONE");
+    return conv_forward_simt(g, mode, in, wp, bias, out, stats, as_stream(stream));
+}
+
+extern "C" int vs_conv_wgrad(const vs_conv_geom* g, const void* small_, const void* big, float* dw, void* stream) {
+    if (int rc = check_geom(g)) return rc;
+    return conv_wgrad_simt(g, small_, big, dw, as_stream(stream));
+}

@@ -1,0 +1,240 @@
+// Grouped training-mode BatchNorm + activation, NHWC.  HBM-bound streaming kernels.
+// Replaces aten::native_batch_norm(_backward) + the in-place activation of
+// /root/reference/var_sep/networks/conv.py:56-59 (nn.BatchNorm2d: eps 1e-5, momentum 0.1, affine).
+//
+// "Grouped": rows [g*rpg, (g+1)*rpg) belong to reference call g; statistics are per (g, channel),
+// so one launch over G batched decoder time steps equals G sequential reference calls.
+#include "common.cuh"
+
+namespace vs {
+
+// one thread per channel; sequential EMA over groups reproduces the order of the reference calls
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int G, int C, double count, float eps,
+                                   float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ rmean, float* __restrict__ rvar, long long* nbt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt != nullptr) *nbt += G;
+    if (c >= C) return;
+    float rm = rmean ? rmean[c] : 0.f, rv = rvar ? rvar[c] : 0.f;
+    for (int g = 0; g < G; ++g) {
+        const double s1 = stats[((long long)g * C + c) * 2], s2 = stats[((long long)g * C + c) * 2 + 1];
+        const double mu = s1 / count;
+        double var = s2 / count - mu * mu;          // biased variance, fp64: no cancellation issue at these sizes
+        if (var < 0.0) var = 0.0;
+        mean[g * C + c] = (float)mu;
+        invstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+        const float unbiased = (float)(count > 1.0 ? var * count / (count - 1.0) : var);
+        rm = (1.f - momentum) * rm + momentum * (float)mu;
+        rv = (1.f - momentum) * rv + momentum * unbiased;
+    }
+    if (rmean) rmean[c] = rm;
+    if (rvar) rvar[c] = rv;
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar, int C, float eps,
+                                     float* __restrict__ mean, float* __restrict__ invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = rmean[c];
+    invstd[c] = 1.f / sqrtf(rvar[c] + eps);
+}
+
+// out = act(gamma*(y-mean)*invstd + beta); 4 channels per thread when C % 4 == 0
+template <typename T, bool VEC>
+__global__ void bn_act_fwd_kernel(const T* __restrict__ y, T* __restrict__ out, long long rows, int C, long long rpg,
+                                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, int act) {
+    const int W = VEC ? 4 : 1;
+    const long long total = rows * C / W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * W;
+        const long long row = e / C;
+        const int c = (int)(e - row * C);
+        const int g = (int)(row / rpg);
+        if (VEC) {
+            const float4 v = ld4<T>(y + e);
+            const float4 mu = *reinterpret_cast<const float4*>(mean + g * C + c);
+            const float4 is = *reinterpret_cast<const float4*>(invstd + g * C + c);
+            const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+            const float4 be = *reinterpret_cast<const float4*>(beta + c);
+            float4 o;
+            o.x = act_fwd(ga.x * ((v.x - mu.x) * is.x) + be.x, act);
+            o.y = act_fwd(ga.y * ((v.y - mu.y) * is.y) + be.y, act);
+            o.z = act_fwd(ga.z * ((v.z - mu.z) * is.z) + be.z, act);
+            o.w = act_fwd(ga.w * ((v.w - mu.w) * is.w) + be.w, act);
+            st4<T>(out + e, o);
+        } else {
+            const float xh = (ld<T>(y + e) - mean[g * C + c]) * invstd[g * C + c];
+            st<T>(out + e, act_fwd(gamma[c] * xh + beta[c], act));
+        }
+    }
+}
+
+// sums[g][c] += { sum dz, sum dz*xhat };  block = 32 channels x 8 row lanes, grid.y = G * chunks
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y, int C, long long rpg,
+                                     int chunks, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                     double* __restrict__ sums) {
+    __shared__ float r1[8][33], r2[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int g = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
+    const long long per = (rpg + chunks - 1) / chunks;
+    const long long r0 = (long long)g * rpg + (long long)chunk * per;
+    long long r_end = r0 + per;
+    if (r_end > (long long)(g + 1) * rpg) r_end = (long long)(g + 1) * rpg;
+    float s1 = 0.f, s2 = 0.f;
+    if (c < C) {
+        const float mu = mean[g * C + c], is = invstd[g * C + c], ga = gamma[c], be = beta[c];
+        for (long long r = r0 + threadIdx.y; r < r_end; r += 8) {
+            const float xh = (ld<T>(y + r * C + c) - mu) * is;
+            const float dz = ld<T>(dout + r * C + c) * act_grad_from_in(ga * xh + be, act);
+            s1 += dz;
+            s2 += dz * xh;
+        }
+    }
+    r1[threadIdx.y][threadIdx.x] = s1;
+    r2[threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t1 += (double)r1[k][threadIdx.x]; t2 += (double)r2[k][threadIdx.x]; }
+        atomicAdd(&sums[((long long)g * C + c) * 2], t1);
+        atomicAdd(&sums[((long long)g * C + c) * 2 + 1], t2);
+    }
+}
+
+template <typename T, bool VEC>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ y, T* __restrict__ dy,
+                                    long long rows, int C, long long rpg, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, int act, const double* __restrict__ sums,
+                                    int train) {
+    const int W = VEC ? 4 : 1;
+    const long long total = rows * C / W;
+    const float inv_count = 1.f / (float)rpg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * W;
+        const long long row = e / C;
+        const int c0 = (int)(e - row * C);
+        const int g = (int)(row / rpg);
+        float yv[4], dv[4], o[4];
+        if (VEC) {
+            const float4 a = ld4<T>(y + e), b = ld4<T>(dout + e);
+            yv[0] = a.x; yv[1] = a.y; yv[2] = a.z; yv[3] = a.w;
+            dv[0] = b.x; dv[1] = b.y; dv[2] = b.z; dv[3] = b.w;
+        } else {
+            yv[0] = ld<T>(y + e); dv[0] = ld<T>(dout + e);
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const int c = c0 + k;
+            const float is = invstd[g * C + c], ga = gamma[c];
+            const float xh = (yv[k] - mean[g * C + c]) * is;
+            const float dz = dv[k] * act_grad_from_in(ga * xh + beta[c], act);
+            if (train) {
+                const float m1 = (float)sums[((long long)g * C + c) * 2] * inv_count;
+                const float m2 = (float)sums[((long long)g * C + c) * 2 + 1] * inv_count;
+                o[k] = ga * is * (dz - m1 - xh * m2);
+            } else {
+                o[k] = ga * is * dz;
+            }
+        }
+        if (VEC) st4<T>(dy + e, make_float4(o[0], o[1], o[2], o[3]));
+        else st<T>(dy + e, o[0]);
+    }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int G, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int g = 0; g < G; ++g) { s1 += sums[((long long)g * C + c) * 2]; s2 += sums[((long long)g * C + c) * 2 + 1]; }
+    if (dbeta) dbeta[c] += (float)s1;
+    if (dgamma) dgamma[c] += (float)s2;
+}
+
+static int ew_blocks(long long work) {
+    long long b = cdiv(work, 256);
+    const long long cap = 8LL * num_sms();
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_bn_finalize(const double* stats, int32_t G, int32_t C, int64_t count, float eps, float momentum,
+                              float* mean, float* invstd, float* running_mean, float* running_var,
+                              int64_t* num_batches_tracked, void* stream) {
+    VS_REQUIRE(G >= 1 && C >= 1 && count >= 1, "bn_finalize: bad sizes");
+    bn_finalize_kernel<<<(int)cdiv(C, 128), 128, 0, as_stream(stream)>>>(
+        stats, G, C, (double)count, eps, momentum, mean, invstd, running_mean, running_var,
+        reinterpret_cast<long long*>(num_batches_tracked));
+    return launched("bn_finalize_kernel");
+}
+
+extern "C" int vs_bn_eval_stats(const float* running_mean, const float* running_var, int32_t C, float eps, float* mean,
+                                float* invstd, void* stream) {
+    bn_eval_stats_kernel<<<(int)cdiv(C, 128), 128, 0, as_stream(stream)>>>(running_mean, running_var, C, eps, mean, invstd);
+    return launched("bn_eval_stats_kernel");
+}
+
+extern "C" int vs_bn_act_forward(const void* y, void* out, int32_t dtype, int64_t rows, int32_t C, int32_t G,
+                                 const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                 int32_t act, void* stream) {
+    VS_REQUIRE(G >= 1 && rows % G == 0, "bn_act_forward: rows %lld not divisible by groups %d", (long long)rows, G);
+    if (rows == 0) return 0;
+    const long long rpg = rows / G;
+    const bool vec = (C % 4) == 0;
+    const int blocks = ew_blocks(rows * C / (vec ? 4 : 1));
+    VS_DISPATCH_DTYPE(dtype, T, {
+        if (vec) bn_act_fwd_kernel<T, true><<<blocks, 256, 0, as_stream(stream)>>>((const T*)y, (T*)out, rows, C, rpg, mean, invstd, gamma, beta, act);
+        else bn_act_fwd_kernel<T, false><<<blocks, 256, 0, as_stream(stream)>>>((const T*)y, (T*)out, rows, C, rpg, mean, invstd, gamma, beta, act);
+    });
+    return launched("bn_act_fwd_kernel");
+}
+
+extern "C" int vs_bn_act_backward_reduce(const void* dout, const void* y, int32_t dtype, int64_t rows, int32_t C,
+                                         int32_t G, const float* mean, const float* invstd, const float* gamma,
+                                         const float* beta, int32_t act, double* sums, void* stream) {
+    VS_REQUIRE(G >= 1 && rows % G == 0, "bn_act_backward_reduce: rows not divisible by groups");
+    if (rows == 0) return 0;
+    const long long rpg = rows / G;
+    const int cx = (int)cdiv(C, 32);
+    long long chunks = cdiv(4LL * num_sms(), (long long)cx * G);
+    if (chunks > cdiv(rpg, 64)) chunks = cdiv(rpg, 64);
+    if (chunks < 1) chunks = 1;
+    VS_REQUIRE((long long)G * chunks <= 65535, "bn reduce grid too large");
+    dim3 grid(cx, (unsigned)(G * chunks)), block(32, 8);
+    VS_DISPATCH_DTYPE(dtype, T, (bn_bwd_reduce_kernel<T><<<grid, block, 0, as_stream(stream)>>>(
+        (const T*)dout, (const T*)y, C, rpg, (int)chunks, mean, invstd, gamma, beta, act, sums)));
+    return launched("bn_bwd_reduce_kernel");
+}
+
+extern "C" int vs_bn_act_backward_apply(const void* dout, const void* y, void* dy, int32_t dtype, int64_t rows,
+                                        int32_t C, int32_t G, const float* mean, const float* invstd,
+                                        const float* gamma, const float* beta, int32_t act, const double* sums,
+                                        int32_t train, float* dgamma, float* dbeta, void* stream) {
+    VS_REQUIRE(G >= 1 && rows % G == 0, "bn_act_backward_apply: rows not divisible by groups");
+    if (rows == 0) return 0;
+    const long long rpg = rows / G;
+    const bool vec = (C % 4) == 0;
+    const int blocks = ew_blocks(rows * C / (vec ? 4 : 1));
+    VS_DISPATCH_DTYPE(dtype, T, {
+        if (vec) bn_bwd_apply_kernel<T, true><<<blocks, 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, rows, C, rpg, mean, invstd, gamma, beta, act, sums, train);
+        else bn_bwd_apply_kernel<T, false><<<blocks, 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, rows, C, rpg, mean, invstd, gamma, beta, act, sums, train);
+    });
+    int rc = launched("bn_bwd_apply_kernel");
+    if (rc) return rc;
+    if (dgamma != nullptr || dbeta != nullptr) {
+        bn_param_grad_kernel<<<(int)cdiv(C, 128), 128, 0, as_stream(stream)>>>(sums, G, C, dgamma, dbeta);
+        rc = launched("bn_param_grad_kernel");
+    }
+    return rc;
+}

@@ -1,0 +1,369 @@
+// Generic fp32-accumulate gather-GEMM convolution (CUDA cores).  This is the exact-arithmetic path
+// (fp32 storage: parity mode) and the fallback geometry coverage for the bf16 mode; the tensor-core
+// path for the hot layers lives in conv_tc.cu and is selected by vs_conv_forward/vs_conv_wgrad.
+//
+// Replaces aten::convolution / convolution_backward / addmm issued by
+// /root/reference/var_sep/networks/conv.py:41-60 (make_conv_block) and mlp.py:40.
+#include "common.cuh"
+
+namespace vs {
+
+struct GatherArgs {
+    int N, IH, IW, IC;   // tensor that is read through the filter window
+    int OH, OW, OC;      // tensor that is produced
+    int R, S, stride, pad;
+    int transposed;      // 0: ih = oh*stride - pad + r ; 1: ih = (oh + pad - r)/stride when divisible
+    int groups, act;
+    int n_per_group;     // samples per BatchNorm group
+};
+
+constexpr int BM = 64, BN = 64, BK = 16, LDS = BM + 4;
+
+// out[m][oc] = act(bias[oc] + sum_{tap,c} in[src(m,tap)][c] * wp[oc][tap][c])
+// grid: (row tiles, oc tiles, stride*stride output-parity classes when transposed)
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) gather_gemm_kernel(GatherArgs a, const T* __restrict__ in,
+                                                          const T* __restrict__ wp, const float* __restrict__ bias,
+                                                          T* __restrict__ out, double* __restrict__ stats) {
+    __shared__ __align__(16) float smem[2 * BK * LDS];
+    float(*As)[LDS] = reinterpret_cast<float(*)[LDS]>(smem);
+    float(*Bs)[LDS] = reinterpret_cast<float(*)[LDS]>(smem + BK * LDS);
+
+    const int tid = threadIdx.x;
+    const int ost = a.transposed ? a.stride : 1;          // output sub-sampling of this class
+    const int ca = blockIdx.z / ost, cb = blockIdx.z % ost;  // parity class (transposed only)
+    const int OHc = (a.OH - ca + ost - 1) / ost, OWc = (a.OW - cb + ost - 1) / ost;
+    const long long Mc = (long long)a.N * OHc * OWc;
+    const long long m0 = (long long)blockIdx.x * BM;
+    if (m0 >= Mc) return;
+    const int n0 = blockIdx.y * BN;
+
+    // ---- loader role: one row (pixel) and 4 consecutive k per thread
+    const int lr = tid >> 2, cq = (tid & 3) * 4;
+    const long long lm = m0 + lr;
+    const bool lrow_ok = lm < Mc;
+    int ln = 0, loh = 0, low = 0;
+    if (lrow_ok) {
+        ln = (int)(lm / ((long long)OHc * OWc));
+        int rem = (int)(lm - (long long)ln * OHc * OWc);
+        loh = (rem / OWc) * ost + ca;
+        low = (rem % OWc) * ost + cb;
+    }
+    const int woc = n0 + lr;   // weight row loaded by this thread
+    const bool wrow_ok = woc < a.OC;
+    const long long wrow = (long long)woc * a.R * a.S * a.IC;
+
+    // ---- compute role
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    int r_begin = 0, r_step = 1, s_begin = 0, s_step = 1;
+    if (a.transposed) {
+        r_begin = (ca + a.pad) % a.stride; r_step = a.stride;
+        s_begin = (cb + a.pad) % a.stride; s_step = a.stride;
+    }
+    for (int r = r_begin; r < a.R; r += r_step) {
+        int ih; bool rok;
+        if (a.transposed) { int t = loh + a.pad - r; ih = t / a.stride; rok = t >= 0 && ih < a.IH; }
+        else { ih = loh * a.stride - a.pad + r; rok = ih >= 0 && ih < a.IH; }
+        for (int s = s_begin; s < a.S; s += s_step) {
+            int iw; bool sok;
+            if (a.transposed) { int t = low + a.pad - s; iw = t / a.stride; sok = t >= 0 && iw < a.IW; }
+            else { iw = low * a.stride - a.pad + s; sok = iw >= 0 && iw < a.IW; }
+            const bool pix_ok = lrow_ok && rok && sok;
+            const T* src = in + (((long long)ln * a.IH + ih) * a.IW + iw) * a.IC;
+            const T* wsrc = wp + wrow + (long long)(r * a.S + s) * a.IC;
+            for (int c0 = 0; c0 < a.IC; c0 += BK) {
+                const int c = c0 + cq;
+                float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+                if (VEC) {
+                    if (pix_ok && c < a.IC) av = ld4<T>(src + c);
+                    if (wrow_ok && c < a.IC) bv = ld4<T>(wsrc + c);
+                } else {
+                    if (pix_ok) {
+                        if (c + 0 < a.IC) av.x = ld<T>(src + c + 0);
+                        if (c + 1 < a.IC) av.y = ld<T>(src + c + 1);
+                        if (c + 2 < a.IC) av.z = ld<T>(src + c + 2);
+                        if (c + 3 < a.IC) av.w = ld<T>(src + c + 3);
+                    }
+                    if (wrow_ok) {
+                        if (c + 0 < a.IC) bv.x = ld<T>(wsrc + c + 0);
+                        if (c + 1 < a.IC) bv.y = ld<T>(wsrc + c + 1);
+                        if (c + 2 < a.IC) bv.z = ld<T>(wsrc + c + 2);
+                        if (c + 3 < a.IC) bv.w = ld<T>(wsrc + c + 3);
+                    }
+                }
+                __syncthreads();   // previous slab fully consumed
+                As[cq + 0][lr] = av.x; As[cq + 1][lr] = av.y; As[cq + 2][lr] = av.z; As[cq + 3][lr] = av.w;
+                Bs[cq + 0][lr] = bv.x; Bs[cq + 1][lr] = bv.y; Bs[cq + 2][lr] = bv.z; Bs[cq + 3][lr] = bv.w;
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < BK; ++k) {
+                    const float4 x = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                    const float4 w = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                    const float xs[4] = {x.x, x.y, x.z, x.w}, ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xs[i], ws[j], acc[i][j]);
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: bias, statistics of the pre-activation, activation, store
+    float bj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int oc = n0 + tx * 4 + j;
+        bj[j] = (bias != nullptr && oc < a.OC) ? bias[oc] : 0.f;
+    }
+    int rg[4];   // BatchNorm group of each of this thread's rows (-1: row out of range)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        rg[i] = -1;
+        if (m >= Mc) continue;
+        const int n = (int)(m / ((long long)OHc * OWc));
+        const int rem = (int)(m - (long long)n * OHc * OWc);
+        const int oh = (rem / OWc) * ost + ca, ow = (rem % OWc) * ost + cb;
+        rg[i] = n / a.n_per_group;
+        T* dst = out + (((long long)n * a.OH + oh) * a.OW + ow) * a.OC + n0 + tx * 4;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j] += bj[j]; v[j] = act_fwd(acc[i][j], a.act); }
+        if (VEC && (a.OC & 3) == 0 && n0 + tx * 4 + 3 < a.OC) {
+            st4<T>(dst, make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n0 + tx * 4 + j < a.OC) st<T>(dst + j, v[j]);
+        }
+    }
+    if (stats == nullptr) return;
+
+    const long long m_last = (m0 + BM - 1 < Mc ? m0 + BM - 1 : Mc - 1);
+    const int g_first = (int)(m0 / ((long long)OHc * OWc)) / a.n_per_group;
+    const int g_last = (int)(m_last / ((long long)OHc * OWc)) / a.n_per_group;
+    if (g_first == g_last) {
+        // whole tile in one group: reduce the 16 row-slices through shared memory, 1 atomic per column
+        float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (rg[i] >= 0)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s1[j] += acc[i][j]; s2[j] += acc[i][j] * acc[i][j]; }
+        __syncthreads();
+        float* red = smem;   // [16][64][2]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            red[(ty * 64 + tx * 4 + j) * 2 + 0] = s1[j];
+            red[(ty * 64 + tx * 4 + j) * 2 + 1] = s2[j];
+        }
+        __syncthreads();
+        if (tid < 128) {
+            const int col = tid >> 1, which = tid & 1;
+            double t = 0.0;
+#pragma unroll
+            for (int y = 0; y < 16; ++y) t += (double)red[(y * 64 + col) * 2 + which];
+            if (n0 + col < a.OC) atomicAdd(&stats[((long long)g_first * a.OC + n0 + col) * 2 + which], t);
+        }
+    } else {
+        // tile straddles groups (tiny batches): per-thread atomics
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (rg[i] >= 0)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + tx * 4 + j < a.OC) {
+                        double* p = &stats[((long long)rg[i] * a.OC + n0 + tx * 4 + j) * 2];
+                        atomicAdd(p, (double)acc[i][j]);
+                        atomicAdd(p + 1, (double)acc[i][j] * (double)acc[i][j]);
+                    }
+    }
+}
+
+// dw[k][c][tap] += sum_m small[m][k] * big[src(m, tap)][c]        (direct-form gather, fp32 atomics)
+// grid: (k tiles, taps * c tiles, splits over m)
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) wgrad_kernel(vs_conv_geom g, const T* __restrict__ small_,
+                                                    const T* __restrict__ big, float* __restrict__ dw,
+                                                    int c_tiles, long long rows_per_split) {
+    __shared__ __align__(16) float smem[2 * BK * LDS];
+    float(*Ds)[LDS] = reinterpret_cast<float(*)[LDS]>(smem);             // [m][k]
+    float(*Gs)[LDS] = reinterpret_cast<float(*)[LDS]>(smem + BK * LDS);  // [m][c]
+    const int tid = threadIdx.x;
+    const int k0 = blockIdx.x * BN;
+    const int tap = blockIdx.y / c_tiles, c0 = (blockIdx.y % c_tiles) * BN;
+    const int r = tap / g.S, s = tap % g.S;
+    const long long M = (long long)g.N * g.P * g.Q;
+    const long long m_begin = (long long)blockIdx.z * rows_per_split;
+    const long long m_end = m_begin + rows_per_split < M ? m_begin + rows_per_split : M;
+
+    const int lrow = tid >> 4, lcol = (tid & 15) * 4;   // loader: 16 rows x 64 columns, 4 per thread
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (long long mb = m_begin; mb < m_end; mb += BK) {
+        const long long m = mb + lrow;
+        float4 dv = make_float4(0.f, 0.f, 0.f, 0.f), gv = dv;
+        if (m < m_end) {
+            const T* dp = small_ + m * g.K + k0 + lcol;
+            const int n = (int)(m / ((long long)g.P * g.Q));
+            const int rem = (int)(m - (long long)n * g.P * g.Q);
+            const int ih = (rem / g.Q) * g.stride - g.pad + r, iw = (rem % g.Q) * g.stride - g.pad + s;
+            const bool ok = ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+            const T* gp = big + (((long long)n * g.H + ih) * g.W + iw) * g.C + c0 + lcol;
+            if (VEC) {
+                if (k0 + lcol < g.K) dv = ld4<T>(dp);
+                if (ok && c0 + lcol < g.C) gv = ld4<T>(gp);
+            } else {
+                if (k0 + lcol + 0 < g.K) dv.x = ld<T>(dp + 0);
+                if (k0 + lcol + 1 < g.K) dv.y = ld<T>(dp + 1);
+                if (k0 + lcol + 2 < g.K) dv.z = ld<T>(dp + 2);
+                if (k0 + lcol + 3 < g.K) dv.w = ld<T>(dp + 3);
+                if (ok) {
+                    if (c0 + lcol + 0 < g.C) gv.x = ld<T>(gp + 0);
+                    if (c0 + lcol + 1 < g.C) gv.y = ld<T>(gp + 1);
+                    if (c0 + lcol + 2 < g.C) gv.z = ld<T>(gp + 2);
+                    if (c0 + lcol + 3 < g.C) gv.w = ld<T>(gp + 3);
+                }
+            }
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&Ds[lrow][lcol]) = dv;
+        *reinterpret_cast<float4*>(&Gs[lrow][lcol]) = gv;
+        __syncthreads();
+#pragma unroll
+        for (int mm = 0; mm < BK; ++mm) {
+            const float4 x = *reinterpret_cast<const float4*>(&Ds[mm][ty * 4]);
+            const float4 w = *reinterpret_cast<const float4*>(&Gs[mm][tx * 4]);
+            const float xs[4] = {x.x, x.y, x.z, x.w}, ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xs[i], ws[j], acc[i][j]);
+        }
+    }
+    const int RS = g.R * g.S;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty * 4 + i;
+        if (k >= g.K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + tx * 4 + j;
+            if (c < g.C) atomicAdd(&dw[((long long)k * g.C + c) * RS + tap], acc[i][j]);
+        }
+    }
+}
+
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int K, int C, int RS, int swap) {
+    const long long total = (long long)K * C * RS;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        // i indexes the OUTPUT (coalesced writes): [A][RS][B]
+        const int B = swap ? K : C;
+        const int b = (int)(i % B);
+        const int tap = (int)((i / B) % RS);
+        const int a = (int)(i / ((long long)B * RS));
+        const int k = swap ? b : a, c = swap ? a : b;
+        st<T>(out + i, w[((long long)k * C + c) * RS + tap]);
+    }
+}
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ a, long long rows, int C, float* __restrict__ db,
+                              long long rows_per_block) {
+    // block = 32 columns x 8 row lanes
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float s = 0.f;
+    if (c < C)
+        for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += ld<T>(a + r * C + c);
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+        atomicAdd(&db[c], t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+int conv_forward_simt(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
+                      double* stats, cudaStream_t stream) {
+    GatherArgs a;
+    a.N = g->N; a.R = g->R; a.S = g->S; a.stride = g->stride; a.pad = g->pad;
+    a.groups = g->groups; a.act = g->act; a.transposed = mode == VS_CONV_TRANSPOSED;
+    if (mode == VS_CONV_DIRECT) { a.IH = g->H; a.IW = g->W; a.IC = g->C; a.OH = g->P; a.OW = g->Q; a.OC = g->K; }
+    else { a.IH = g->P; a.IW = g->Q; a.IC = g->K; a.OH = g->H; a.OW = g->W; a.OC = g->C; }
+    a.n_per_group = g->N / g->groups;
+    const int st = a.transposed ? a.stride : 1;
+    const long long Mc0 = (long long)a.N * cdiv(a.OH, st) * cdiv(a.OW, st);
+    dim3 grid((unsigned)cdiv(Mc0, BM), (unsigned)cdiv(a.OC, BN), (unsigned)(st * st));
+    const bool vec = (a.IC % 4) == 0;
+    VS_DISPATCH_DTYPE(g->dtype, T, {
+        if (vec) gather_gemm_kernel<T, true><<<grid, 256, 0, stream>>>(a, (const T*)in, (const T*)wp, bias, (T*)out, stats);
+        else gather_gemm_kernel<T, false><<<grid, 256, 0, stream>>>(a, (const T*)in, (const T*)wp, bias, (T*)out, stats);
+    });
+    return launched("gather_gemm_kernel");
+}
+
+int conv_wgrad_simt(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream) {
+    const int c_tiles = (int)cdiv(g->C, BN), k_tiles = (int)cdiv(g->K, BN);
+    const long long M = (long long)g->N * g->P * g->Q;
+    const long long base = (long long)k_tiles * c_tiles * g->R * g->S;
+    long long splits = cdiv(4LL * num_sms(), base);
+    const long long max_splits = cdiv(M, 256);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    long long rps = cdiv(cdiv(M, splits), BK) * BK;
+    splits = cdiv(M, rps);
+    VS_REQUIRE((long long)c_tiles * g->R * g->S <= 65535 && splits <= 65535, "wgrad grid too large");
+    dim3 grid((unsigned)k_tiles, (unsigned)(c_tiles * g->R * g->S), (unsigned)splits);
+    const bool vec = (g->C % 4) == 0 && (g->K % 4) == 0;
+    VS_DISPATCH_DTYPE(g->dtype, T, {
+        if (vec) wgrad_kernel<T, true><<<grid, 256, 0, stream>>>(*g, (const T*)small_, (const T*)big, dw, c_tiles, rps);
+        else wgrad_kernel<T, false><<<grid, 256, 0, stream>>>(*g, (const T*)small_, (const T*)big, dw, c_tiles, rps);
+    });
+    return launched("wgrad_kernel");
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_pack_weight(const float* w, void* out, int32_t dtype, int32_t K, int32_t C, int32_t RS,
+                              int32_t swap, void* stream) {
+    const long long total = (long long)K * C * RS;
+    if (total == 0) return 0;
+    const int blocks = (int)(cdiv(total, 256) < 4096 ? cdiv(total, 256) : 4096);
+    VS_DISPATCH_DTYPE(dtype, T, (pack_weight_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(w, (T*)out, K, C, RS, swap)));
+    return launched("pack_weight_kernel");
+}
+
+extern "C" int vs_colsum(const void* a, int32_t dtype, int64_t rows, int32_t C, float* db, void* stream) {
+    if (rows == 0 || C == 0) return 0;
+    const int cx = (int)cdiv(C, 32);
+    long long by = cdiv(2LL * num_sms(), cx);
+    if (by > cdiv(rows, 64)) by = cdiv(rows, 64);
+    if (by < 1) by = 1;
+    if (by > 65535) by = 65535;
+    const long long rpb = cdiv(rows, by);
+    dim3 grid(cx, (unsigned)cdiv(rows, rpb)), block(32, 8);
+    VS_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)a, rows, C, db, rpb)));
+    return launched("colsum_kernel");
+}

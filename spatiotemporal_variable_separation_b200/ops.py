@@ -1,0 +1,527 @@
+"""Host-side operators: thin autograd wrappers around the C ABI.
+
+Every arithmetic operation of the hot path is a kernel of libvarsep_sm100a.so;
+torch.autograd only wires the backward calls together and PyTorch tensors are
+used as device-memory handles.  Internal activations are NHWC tensors
+``[N, H, W, C]`` of the compute dtype (fp32 = parity mode, bf16 = tensor-core mode).
+"""
+from collections import namedtuple
+
+import torch
+
+from . import _lib as L
+from ._lib import ptr
+
+_compute_dtype = torch.float32
+
+
+def set_compute_dtype(dtype):
+    """torch.float32 (bit-for-bit fp32 accumulation, parity mode) or torch.bfloat16 (tcgen05 path)."""
+    global _compute_dtype
+    assert dtype in (torch.float32, torch.bfloat16)
+    _compute_dtype = dtype
+
+
+def compute_dtype():
+    return _compute_dtype
+
+
+# ------------------------------------------------------------------------------------------------
+# packed-weight cache.  Kernels read weights as [OC][taps][IC] in the compute dtype; the fp32
+# torch parameter stays the master copy.  Entries live on the parameter object and are invalidated by
+# the tensor version counter or by ``invalidate_packed()`` (called after the fused Adam step, which
+# writes through raw pointers and therefore does not bump version counters).
+# ------------------------------------------------------------------------------------------------
+_pack_epoch = 0
+
+
+def invalidate_packed():
+    global _pack_epoch
+    _pack_epoch += 1
+
+
+def packed_weight(w, K, C, RS, swap, dtype):
+    """Packed copy of parameter ``w``; cached on the parameter object itself (so the cache dies with
+    the module and can never alias another tensor that later reuses the same address)."""
+    cache = w.__dict__.setdefault('_vs_pack', {})
+    key = (K, C, RS, bool(swap), dtype)
+    tag = (w._version, w.data_ptr(), _pack_epoch)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    out = hit[1] if hit is not None else torch.empty(K * C * RS, device=w.device, dtype=dtype)
+    L.call('vs_pack_weight', ptr(w), ptr(out), L.dtype_code(out), K, C, RS, int(swap), L.stream())
+    cache[key] = (tag, out)
+    return out
+
+
+ConvCfg = namedtuple('ConvCfg', 'kind K C R S stride pad act groups training has_bn eps momentum flags')
+
+
+def _geom(cfg, dtype, N, H, W, P, Q, act, groups):
+    return L.Geom(L.VS_F32 if dtype == torch.float32 else L.VS_BF16, N, H, W, cfg.C, P, Q, cfg.K, cfg.R, cfg.S,
+                  cfg.stride, cfg.pad, groups, act, cfg.flags)
+
+
+class ConvBlockFn(torch.autograd.Function):
+    """conv/convT/linear -> [BatchNorm (grouped batch stats or running stats)] -> activation.
+
+    Replaces one ``make_conv_block`` Sequential (conv.py:41-60) or one Linear (+ReLU of the next
+    MLP block, mlp.py:24-41).  Geometry terms: see include/varsep.h (big[N,H,W,C] <-> small[N,P,Q,K]).
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, rmean, rvar, nbt, cfg):
+        L.require_cuda(x, weight)
+        x = x.contiguous()
+        N = x.shape[0]
+        if cfg.kind == 'conv':
+            H, W = x.shape[1], x.shape[2]
+            assert x.shape[3] == cfg.C, (x.shape, cfg)
+            P = (H + 2 * cfg.pad - cfg.R) // cfg.stride + 1
+            Q = (W + 2 * cfg.pad - cfg.S) // cfg.stride + 1
+            out_shape, OC, mode = (N, P, Q, cfg.K), cfg.K, L.DIRECT
+        else:
+            P, Q = x.shape[1], x.shape[2]
+            assert x.shape[3] == cfg.K, (x.shape, cfg)
+            H = (P - 1) * cfg.stride - 2 * cfg.pad + cfg.R
+            W = (Q - 1) * cfg.stride - 2 * cfg.pad + cfg.S
+            out_shape, OC, mode = (N, H, W, cfg.C), cfg.C, L.TRANSPOSED
+        dt = x.dtype
+        act = L.ACT[cfg.act]
+        wp = packed_weight(weight, cfg.K, cfg.C, cfg.R * cfg.S, mode == L.TRANSPOSED, dt)
+        y = torch.empty(out_shape, device=x.device, dtype=dt)
+        rows = y.numel() // OC
+        ctx.cfg, ctx.dims, ctx.mode = cfg, (N, H, W, P, Q, OC), mode
+        if cfg.has_bn:
+            G = cfg.groups if cfg.training else 1
+            mean = torch.empty(G * OC, device=x.device, dtype=torch.float32)
+            invstd = torch.empty_like(mean)
+            if cfg.training:
+                stats = torch.zeros(G * OC * 2, device=x.device, dtype=torch.float64)
+                g = _geom(cfg, dt, N, H, W, P, Q, 0, G)
+                L.call('vs_conv_forward', g, mode, ptr(x), ptr(wp), ptr(bias), ptr(y), ptr(stats), L.stream())
+                L.call('vs_bn_finalize', ptr(stats), G, OC, rows // G, cfg.eps, cfg.momentum, ptr(mean), ptr(invstd),
+                     ptr(rmean), ptr(rvar), ptr(nbt), L.stream())
+            else:
+                g = _geom(cfg, dt, N, H, W, P, Q, 0, 1)
+                L.call('vs_conv_forward', g, mode, ptr(x), ptr(wp), ptr(bias), ptr(y), None, L.stream())
+                L.call('vs_bn_eval_stats', ptr(rmean), ptr(rvar), OC, cfg.eps, ptr(mean), ptr(invstd), L.stream())
+            out = torch.empty_like(y)
+            L.call('vs_bn_act_forward', ptr(y), ptr(out), L.dtype_code(y), rows, OC, G, ptr(mean), ptr(invstd),
+                 ptr(gamma), ptr(beta), act, L.stream())
+            ctx.save_for_backward(x, weight, y, mean, invstd, gamma, beta)
+            ctx.G = G
+        else:
+            g = _geom(cfg, dt, N, H, W, P, Q, act, 1)
+            L.call('vs_conv_forward', g, mode, ptr(x), ptr(wp), ptr(bias), ptr(y), None, L.stream())
+            out = y
+            ctx.save_for_backward(x, weight, out)
+        # python references to the leaf parameters (their ``_vs_grad`` arena views are looked up in backward)
+        ctx.params = (weight, bias, gamma, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg, (N, H, W, P, Q, OC), mode = ctx.cfg, ctx.dims, ctx.mode
+        dout = dout.contiguous()
+        dt = dout.dtype
+        rows = dout.numel() // OC
+        act = L.ACT[cfg.act]
+        dgamma = dbeta = None
+        p_weight, p_bias, p_gamma, p_beta = ctx.params
+        if cfg.has_bn:
+            x, weight, y, mean, invstd, gamma, beta = ctx.saved_tensors
+            G = ctx.G
+            sums = torch.zeros(G * OC * 2, device=dout.device, dtype=torch.float64)
+            if cfg.training:
+                L.call('vs_bn_act_backward_reduce', ptr(dout), ptr(y), L.dtype_code(y), rows, OC, G, ptr(mean),
+                     ptr(invstd), ptr(gamma), ptr(beta), act, ptr(sums), L.stream())
+                dgamma, dbeta = _grad_buffer(p_gamma), _grad_buffer(p_beta)
+            dy = torch.empty_like(y)
+            L.call('vs_bn_act_backward_apply', ptr(dout), ptr(y), ptr(dy), L.dtype_code(y), rows, OC, G, ptr(mean),
+                 ptr(invstd), ptr(gamma), ptr(beta), act, ptr(sums), int(cfg.training),
+                 ptr(dgamma[0]) if dgamma else None, ptr(dbeta[0]) if dbeta else None, L.stream())
+        else:
+            x, weight, out = ctx.saved_tensors
+            if act != 0:
+                dy = torch.empty_like(out)
+                L.call('vs_act_backward', ptr(dout), ptr(out), ptr(dy), L.dtype_code(out), out.numel(), act, L.stream())
+            else:
+                dy = dout
+        g = _geom(cfg, dt, N, H, W, P, Q, 0, 1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            back_mode = L.TRANSPOSED if mode == L.DIRECT else L.DIRECT
+            wp = packed_weight(weight, cfg.K, cfg.C, cfg.R * cfg.S, back_mode == L.TRANSPOSED, dt)
+            L.call('vs_conv_forward', g, back_mode, ptr(dy), ptr(wp), None, ptr(dx), None, L.stream())
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = _grad_buffer(p_weight)
+            small, big = (dy, x) if cfg.kind == 'conv' else (x, dy)
+            L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dw[0]), L.stream())
+        if p_bias is not None and ctx.needs_input_grad[2]:
+            db = _grad_buffer(p_bias)
+            L.call('vs_colsum', ptr(dy), L.dtype_code(dy), rows, OC, ptr(db[0]), L.stream())
+        return (dx, dw[1] if dw else None, db[1] if db else None, dgamma[1] if dgamma else None,
+                dbeta[1] if dbeta else None,
+                None, None, None, None)
+
+
+def _grad_buffer(p):
+    """(buffer the kernel accumulates into, what backward returns to autograd).
+
+    Parameters owned by a ``FlatState`` (see optim.py) expose ``_vs_grad``: a persistent fp32 view of
+    the flat gradient arena.  Kernels then accumulate straight into it and autograd gets ``None``
+    (no per-parameter add kernels); otherwise a fresh zeroed tensor is returned the normal way."""
+    g = getattr(p, '_vs_grad', None)
+    if g is not None:
+        return g, None
+    z = torch.zeros_like(p, dtype=torch.float32)
+    return z, z
+
+
+def conv_block(x, conv, bn=None, act=None, kind='conv', groups=1, wshape=None, flags=0):
+    """Run ``conv`` (nn.Conv2d / nn.ConvTranspose2d / nn.Linear used as parameter containers)
+    followed by the optional BatchNorm module ``bn`` and activation name ``act`` on NHWC ``x``."""
+    w = conv.weight
+    if wshape is None:
+        if w.dim() == 2:
+            wshape = (w.shape[0], w.shape[1], 1, 1)
+        else:
+            wshape = tuple(w.shape)
+    K, C, R, S = wshape
+    stride = conv.stride[0] if hasattr(conv, 'stride') else 1
+    pad = conv.padding[0] if hasattr(conv, 'padding') else 0
+    training = bool(bn.training) if bn is not None else False
+    cfg = ConvCfg(kind, K, C, R, S, stride, pad, act, groups, training, bn is not None,
+                  bn.eps if bn is not None else 0.0, bn.momentum if bn is not None else 0.0, flags)
+    if bn is not None:
+        return ConvBlockFn.apply(x, w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                 bn.num_batches_tracked, cfg)
+    return ConvBlockFn.apply(x, w, conv.bias, None, None, None, None, None, cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# layout boundary
+# ------------------------------------------------------------------------------------------------
+class ToInternalFn(torch.autograd.Function):
+    """fp32 NCHW [N,C,H,W] (reference layout) -> NHWC [N,H,W,C] of the compute dtype."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        L.require_cuda(x)
+        x = x.contiguous().float()
+        N, Cc, H, W = x.shape
+        out = torch.empty((N, H, W, Cc), device=x.device, dtype=dtype)
+        L.call('vs_nchw_to_nhwc', ptr(x), ptr(out), L.dtype_code(out), N, Cc, H, W, L.stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+        N, H, W, Cc = d.shape
+        out = torch.empty((N, Cc, H, W), device=d.device, dtype=torch.float32)
+        L.call('vs_nhwc_to_nchw', ptr(d), L.dtype_code(d), ptr(out), N, Cc, H, W, L.stream())
+        return out, None
+
+
+class ToExternalFn(torch.autograd.Function):
+    """NHWC compute dtype -> fp32 NCHW."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        N, H, W, Cc = x.shape
+        ctx.dtype = x.dtype
+        out = torch.empty((N, Cc, H, W), device=x.device, dtype=torch.float32)
+        L.call('vs_nhwc_to_nchw', ptr(x), L.dtype_code(x), ptr(out), N, Cc, H, W, L.stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous().float()
+        N, Cc, H, W = d.shape
+        out = torch.empty((N, H, W, Cc), device=d.device, dtype=ctx.dtype)
+        L.call('vs_nchw_to_nhwc', ptr(d), ptr(out), L.dtype_code(out), N, Cc, H, W, L.stream())
+        return out
+
+
+def to_internal(x):
+    """[N,C,H,W] or [N,C] fp32 -> NHWC compute dtype."""
+    if x.dim() == 2:
+        x = x.view(x.shape[0], x.shape[1], 1, 1)
+    return ToInternalFn.apply(x, _compute_dtype)
+
+
+def to_external(x):
+    return ToExternalFn.apply(x)
+
+
+def frames_window(frames, t0, nt, out=None, row0=0):
+    """frames [B,T,C,H,W] fp32 -> time-folded NHWC [B,H,W,nt*C] (conv.py:90); no gradient (data).
+    With ``out``/``row0`` the window is written into rows [row0, row0+B) of a larger batch."""
+    L.require_cuda(frames)
+    frames = frames.contiguous()
+    B, T, Cf, H, W = frames.shape
+    if out is None:
+        out = torch.empty((B, H, W, nt * Cf), device=frames.device, dtype=_compute_dtype)
+        row0 = 0
+    dst = out[row0:row0 + B]
+    L.call('vs_frames_to_nhwc', ptr(frames), B, T, Cf, H, W, t0, nt, ptr(dst), L.dtype_code(out), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# element-wise
+# ------------------------------------------------------------------------------------------------
+class AddActFn(torch.autograd.Function):
+    """act(a + b): residual connections (resnet.py:29,69; conv.py:465-466)."""
+
+    @staticmethod
+    def forward(ctx, a, b, act):
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        L.call('vs_add_act', ptr(a), ptr(b), ptr(out), L.dtype_code(a), a.numel(), L.ACT[act], L.stream())
+        ctx.act = L.ACT[act]
+        if ctx.act:
+            ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+        if ctx.act:
+            out, = ctx.saved_tensors
+            dx = torch.empty_like(out)
+            L.call('vs_act_backward', ptr(d), ptr(out), ptr(dx), L.dtype_code(out), out.numel(), ctx.act, L.stream())
+            d = dx
+        return d, d, None
+
+
+def add_act(a, b, act=None):
+    return AddActFn.apply(a, b, act)
+
+
+class ConcatFn(torch.autograd.Function):
+    """Channel concatenation of NHWC tensors; an input with fewer rows is broadcast over the groups
+    (one reference call's S code / skip tensors feeding G batched decoder calls)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [x.contiguous() for x in xs]
+        rows = max(x.numel() // x.shape[-1] for x in xs)
+        big = max(xs, key=lambda x: x.numel() // x.shape[-1])
+        Ct = sum(x.shape[-1] for x in xs)
+        out = torch.empty(big.shape[:-1] + (Ct,), device=big.device, dtype=big.dtype)
+        off, meta = 0, []
+        for x in xs:
+            c, r = x.shape[-1], x.numel() // x.shape[-1]
+            L.call('vs_copy_channels', ptr(x), c, r, ptr(out), Ct, off, rows, L.dtype_code(out), L.stream())
+            meta.append((tuple(x.shape), c, r, off))
+            off += c
+        ctx.meta, ctx.rows, ctx.Ct = meta, rows, Ct
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+        grads = []
+        for i, (shape, c, r, off) in enumerate(ctx.meta):
+            if not ctx.needs_input_grad[i]:
+                grads.append(None)
+                continue
+            g = torch.empty(shape, device=d.device, dtype=d.dtype)
+            L.call('vs_slice_channels_reduce', ptr(d), ctx.Ct, off, ctx.rows, ptr(g), c, r, L.dtype_code(d), L.stream())
+            grads.append(g)
+        return tuple(grads)
+
+
+def concat_channels(*xs):
+    return ConcatFn.apply(*xs)
+
+
+class MulBcastFn(torch.autograd.Function):
+    """s * t with s broadcast over groups ('mul' mixing: conv.py:223, mlp_encdec.py:47)."""
+
+    @staticmethod
+    def forward(ctx, s, t):
+        s, t = s.contiguous(), t.contiguous()
+        Cc = t.shape[-1]
+        out = torch.empty_like(t)
+        L.call('vs_mul_bcast', ptr(s), s.numel() // Cc, ptr(t), ptr(out), t.numel() // Cc, Cc, L.dtype_code(t), L.stream())
+        ctx.save_for_backward(s, t)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        s, t = ctx.saved_tensors
+        d = d.contiguous()
+        Cc = t.shape[-1]
+        ds = torch.empty_like(s) if ctx.needs_input_grad[0] else None
+        dt = torch.empty_like(t) if ctx.needs_input_grad[1] else None
+        L.call('vs_mul_bcast_backward', ptr(d), ptr(s), s.numel() // Cc, ptr(t), ptr(ds), ptr(dt), t.numel() // Cc, Cc,
+             L.dtype_code(t), L.stream())
+        return ds, dt
+
+
+def mul_bcast(s, t):
+    return MulBcastFn.apply(s, t)
+
+
+class MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        x = x.contiguous()
+        N, H, W, Cc = x.shape
+        P, Q = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        y = torch.empty((N, P, Q, Cc), device=x.device, dtype=x.dtype)
+        L.call('vs_maxpool_forward', ptr(x), ptr(y), L.dtype_code(x), N, H, W, Cc, k, stride, pad, L.stream())
+        ctx.save_for_backward(x)
+        ctx.geo = (k, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, d):
+        x, = ctx.saved_tensors
+        d = d.contiguous()
+        N, H, W, Cc = x.shape
+        dx = torch.empty_like(x)
+        L.call('vs_maxpool_backward', ptr(x), ptr(d), ptr(dx), L.dtype_code(x), N, H, W, Cc, *ctx.geo, L.stream())
+        return dx, None, None, None
+
+
+def maxpool(x, k=2, stride=2, pad=0):
+    return MaxPoolFn.apply(x, k, stride, pad)
+
+
+class Upsample2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        N, H, W, Cc = x.shape
+        y = torch.empty((N, 2 * H, 2 * W, Cc), device=x.device, dtype=x.dtype)
+        L.call('vs_upsample2_forward', ptr(x), ptr(y), L.dtype_code(x), N, H, W, Cc, L.stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+        N, H2, W2, Cc = d.shape
+        dx = torch.empty((N, H2 // 2, W2 // 2, Cc), device=d.device, dtype=d.dtype)
+        L.call('vs_upsample2_backward', ptr(d), ptr(dx), L.dtype_code(d), N, H2 // 2, W2 // 2, Cc, L.stream())
+        return dx
+
+
+def upsample2(x):
+    return Upsample2Fn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+def _btl(t):
+    """Describe an fp32 tensor as [B][T][L] with a contiguous inner run of L elements."""
+    if t.dim() >= 3:
+        inner = t[0, 0]
+        if inner.is_contiguous() or inner.numel() == 1:
+            return t.shape[0], t.shape[1], inner.numel(), t.stride(0), t.stride(1)
+    if not t.is_contiguous():
+        raise ValueError('loss operand must be contiguous or a [B,T,...] view with contiguous frames')
+    return 1, 1, t.numel(), 0, 0
+
+
+class LossTermsFn(torch.autograd.Function):
+    """All squared-error terms of the step in one pass each, combined on the device.
+
+    ``pairs[i]`` is a list of (a, b) operand pairs summed into term i (b may be None: sum of a^2);
+    term_i = coef_i * sum;  output = [term_0 .. term_{n-1}, sum_i lamb_i * term_i].
+    Replaces F.mse_loss / pow-mean / sum reductions of train.py:42,86,139,145-149.
+    Gradients flow to every ``a`` and to ``b`` when it requires grad.
+    """
+
+    @staticmethod
+    def forward(ctx, spec, *tensors):
+        # spec: list of (coef, lamb, [(ia, ib or -1), ...]) indexing into tensors
+        n = len(spec)
+        dev = tensors[0].device
+        acc = torch.zeros(n, device=dev, dtype=torch.float64)
+        descs = []
+        for i, (coef, lamb, pairs) in enumerate(spec):
+            for ia, ib in pairs:
+                a = tensors[ia]
+                b = tensors[ib] if ib >= 0 else None
+                assert a.dtype == torch.float32 and (b is None or b.dtype == torch.float32)
+                # a gradient is written with the operand's own strides: those must tile a dense buffer
+                if ctx.needs_input_grad[1 + ia] and not _dense_strides(a):
+                    a = a.contiguous()
+                if b is not None and ctx.needs_input_grad[1 + ib] and not _dense_strides(b):
+                    b = b.contiguous()
+                Ba, Ta, La, asb, ast = _btl(a)
+                if b is not None:
+                    Bb, Tb, Lb, bsb, bst = _btl(b)
+                    if (Ba, Ta, La) != (Bb, Tb, Lb):
+                        # fall back to a common flat description
+                        a, b = a.contiguous(), b.contiguous()
+                        Ba, Ta, La, asb, ast = 1, 1, a.numel(), 0, 0
+                        bsb, bst = 0, 0
+                else:
+                    bsb = bst = 0
+                slot = C_double_ptr(acc, i)
+                L.call('vs_sqdiff_sum', ptr(a), asb, ast, ptr(b), bsb, bst, Ba, Ta, La, slot, L.stream())
+                descs.append((i, ia, ib, a, b, (Ba, Ta, La, asb, ast, bsb, bst)))
+        terms = torch.empty(n + 1, device=dev, dtype=torch.float32)
+        coef = (L.C.c_double * n)(*[s[0] for s in spec])
+        lamb = (L.C.c_double * n)(*[s[1] for s in spec])
+        L.call('vs_loss_combine', ptr(acc), coef, lamb, n, ptr(terms), L.stream())
+        ctx.spec, ctx.descs, ctx.n = spec, descs, n
+        ctx.shapes = [(t.shape, t.stride(), t.requires_grad) for t in tensors]
+        return terms
+
+    @staticmethod
+    def backward(ctx, dterms):
+        dterms = dterms.contiguous()
+        n = ctx.n
+        grads = [None] * len(ctx.shapes)
+        g_total = dterms[n:n + 1]
+        for (i, ia, ib, a, b, (B, T, Ln, asb, ast, bsb, bst)) in ctx.descs:
+            coef, lamb, _ = ctx.spec[i]
+            g_term = dterms[i:i + 1]
+            for which, idx in ((0, ia), (1, ib)):
+                if idx < 0 or not ctx.needs_input_grad[1 + idx]:
+                    continue
+                tgt = a if which == 0 else b
+                first = grads[idx] is None
+                if first:
+                    # gradient laid out exactly like the operand (dense strides were enforced in forward)
+                    grads[idx] = torch.empty_strided(tgt.shape, tgt.stride(), device=tgt.device, dtype=torch.float32)
+                gbuf = grads[idx]
+                sgn = 2.0 * coef if which == 0 else -2.0 * coef
+                if which == 0:
+                    L.call('vs_sqdiff_backward', ptr(a), asb, ast, ptr(b), bsb, bst, B, T, Ln, sgn, g_term, g_total,
+                         lamb, ptr(gbuf), 0 if first else 1, L.stream())
+                else:
+                    # d/db (a-b)^2 = -2 (a-b): same kernel, destination indexed like b
+                    L.call('vs_sqdiff_backward', ptr(b), bsb, bst, ptr(a), asb, ast, B, T, Ln, -sgn, g_term, g_total,
+                         lamb, ptr(gbuf), 0 if first else 1, L.stream())
+        return (None,) + tuple(grads)
+
+
+def _dense_strides(t):
+    """True if t's strides are a permutation of a dense layout (every element of the buffer is covered)."""
+    order = sorted(range(t.dim()), key=lambda i: -t.stride(i))
+    expect = 1
+    for i in reversed(order):
+        if t.shape[i] != 1 and t.stride(i) != expect:
+            return False
+        expect *= t.shape[i]
+    return True
+
+
+def C_double_ptr(t, i):
+    return t[i:i + 1]
+
+
+def loss_terms(spec, tensors):
+    return LossTermsFn.apply(spec, *tensors)

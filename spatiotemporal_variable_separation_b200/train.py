@@ -1,0 +1,135 @@
+"""Training step (counterpart of /root/reference/var_sep/train.py).
+
+``zero_order_loss``, ``ae_loss`` and ``train`` keep the reference signatures.  ``step_losses`` is
+the GPU-organised body of one step (train.py:116-149): the same arithmetic, but the two Es calls,
+the two Et calls and the 1 + nt_pred + offset decoder calls are each ONE grouped launch sequence
+(BatchNorm statistics per call), and all loss terms are reduced by fused kernels.
+"""
+import numpy as np
+import torch
+from tqdm import tqdm
+
+from . import ops
+from .networks.model import _external_codes
+from .utils.helper import save
+
+
+def zero_order_loss(s_code_old, s_code_new, skipco):
+    """train.py:38-42 — mean((S_old - S_new)^2) over the code (and, with skipco, all skip tensors)."""
+    if skipco:
+        olds = [s_code_old[0]] + list(s_code_old[1])
+        news = [s_code_new[0]] + list(s_code_new[1])
+    else:
+        olds, news = [s_code_old], [s_code_new]
+    n = sum(t.numel() for t in olds)
+    tensors = [t.float() for t in olds + news]
+    k = len(olds)
+    return ops.loss_terms([(1.0 / n, 1.0, [(i, k + i) for i in range(k)])], tensors)[0]
+
+
+def draw_t_random(nt_cond, n_frames, offset):
+    """train.py:72-75 — host RNG (numpy global state), exclusive upper bound."""
+    if offset == 0:
+        return int(np.random.randint(nt_cond, n_frames))
+    return int(np.random.randint(nt_cond, n_frames + 1))
+
+
+def ae_loss(cond, target, sep_net, nt_cond, offset, skipco, t_random=None):
+    """train.py:45-88 through the public module calls (sequential form)."""
+    full_data = torch.cat([cond, target], dim=1)
+    s_code_old = sep_net.Es(full_data[:, :nt_cond], return_skip=skipco)
+    s_code_new = sep_net.Es(full_data[:, -nt_cond:], return_skip=skipco)
+    if t_random is None:
+        t_random = draw_t_random(nt_cond, full_data.size(1), offset)
+    t_code_random = sep_net.Et(full_data[:, t_random - nt_cond:t_random])
+    if skipco:
+        reconstruction = sep_net.decoder(s_code_old[0], t_code_random, skip=s_code_old[1])
+    else:
+        reconstruction = sep_net.decoder(s_code_old, t_code_random)
+    supervision = full_data[:, t_random - offset]
+    loss = ops.loss_terms([(1.0 / reconstruction.numel(), 1.0, [(0, 1)])], [reconstruction, supervision])[0]
+    return loss, s_code_new, s_code_old
+
+
+def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, lamb_s, lamb_t, lamb_pred,
+                average_tloss=False, t_random=None):
+    """One forward pass of the training objective.  ``full_data`` = cat(cond, target) [B,L,C,H,W] fp32.
+
+    Returns dict(total, ae, s, pred, t, forecasts, t_codes); ``total.backward()`` then produces every
+    parameter gradient.  Call order inside each network matches train.py:120-133 so the BatchNorm
+    running statistics evolve identically (Es: old,new; Et: random,cond; decoder: AE, forecasts).
+    """
+    assert offset == nt_cond or offset == 0                                           # train.py:103
+    B, n_frames = full_data.shape[0], full_data.shape[1]
+    if t_random is None:
+        t_random = draw_t_random(nt_cond, n_frames, offset)
+    # ---- encoders: two calls each, batched as two BatchNorm groups
+    s_both = sep_net.Es.encode(sep_net.encoder_input(full_data, [0, n_frames - nt_cond]), 2, skipco)
+    t_both = sep_net.Et.encode(sep_net.encoder_input(full_data, [t_random - nt_cond, 0]), 2)
+    if skipco:
+        s_code, s_skips = s_both
+        s_old, s_new = s_code[:B], s_code[B:]
+        skip_old, skip_new = [s[:B] for s in s_skips], [s[B:] for s in s_skips]
+    else:
+        s_old, s_new, skip_old, skip_new = s_both[:B], s_both[B:], None, None
+    t_rand, t_cond = t_both[:B], t_both[B:]
+    # ---- rollout + AE reconstruction and all forecasts in one grouped decode
+    forecasts, t_codes, _, _, recon = sep_net.forecast_internal(s_old, skip_old, t_cond, nt_pred + offset, B,
+                                                                extra_t=t_rand)
+    # ---- losses
+    supervision = full_data[:, t_random - offset]
+    f_off = nt_cond if offset == 0 else 0
+    target = full_data[:, f_off:]
+    olds = [_loss_operand(s_old)] + ([_loss_operand(s) for s in skip_old] if skipco else [])
+    news = [_loss_operand(s_new)] + ([_loss_operand(s) for s in skip_new] if skipco else [])
+    t0 = _external_codes(t_cond).reshape(B, -1)
+    tensors = [recon, supervision, forecasts, target, t0] + olds + news
+    k = len(olds)
+    n_s = sum(t.numel() for t in olds)
+    t_coef = 0.5 / t0.numel() if average_tloss else 0.5 / B                          # train.py:145-148
+    spec = [(1.0 / recon.numel(), lamb_ae, [(0, 1)]),
+            (1.0 / n_s, lamb_s, [(5 + i, 5 + k + i) for i in range(k)]),
+            (1.0 / forecasts.numel(), lamb_pred, [(2, 3)]),
+            (t_coef, lamb_t, [(4, -1)])]
+    terms = ops.loss_terms(spec, tensors)
+    return dict(total=terms[4], ae=terms[0], s=terms[1], pred=terms[2], t=terms[3], terms=terms,
+                forecasts=forecasts, t_codes=t_codes, t_random=t_random)
+
+
+def _loss_operand(h):
+    """internal tensor -> fp32 operand of the loss kernels (layout is irrelevant for a sum over all elements)."""
+    if h.dtype == torch.float32:
+        return h.contiguous()
+    return ops.to_external(h.reshape(-1, *h.shape[-3:]))
+
+
+def train(xp_dir, train_loader, device, sep_net, optimizer, scheduler, use_apex_amp, use_torch_amp, epochs, lamb_ae,
+          lamb_s, lamb_t, lamb_pred, offset, nt_cond, nt_pred, no_s, skipco, chkpt_interval, average_tloss):
+    """train.py:91-175.  Either AMP flag selects the bf16 tensor-core compute path (the analogue of the
+    reference's fp16 autocast; bf16 needs no loss scaling)."""
+    if use_apex_amp or use_torch_amp:
+        ops.set_compute_dtype(torch.bfloat16)
+    if no_s:
+        lamb_t = 0
+        print("No regularization on T as there is no S")
+    assert offset == nt_cond or offset == 0
+    try:
+        pb = tqdm(total=epochs * len(train_loader), ncols=0)
+        for epoch in range(epochs):
+            sep_net.train()
+            for cond, target in train_loader:
+                cond, target = cond.to(device, non_blocking=True), target.to(device, non_blocking=True)
+                optimizer.zero_grad()
+                full_data = torch.cat([cond, target], dim=1)
+                out = step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, lamb_s, lamb_t,
+                                  lamb_pred, average_tloss)
+                out['total'].backward()
+                optimizer.step()
+                pb.update()
+            if scheduler is not None:
+                scheduler.step()
+            if chkpt_interval is not None and (epoch + 1) % chkpt_interval == 0:
+                save(xp_dir, sep_net, epoch_number=epoch + 1)
+    except KeyboardInterrupt:
+        pass
+    save(xp_dir, sep_net)
