@@ -1,0 +1,273 @@
+"""Every entry point of libvarsep_sm100a.so against the executable specification (tests/emu.py),
+argument for argument, on the GPU.  fp32 storage: 2e-5 relative (fp32 accumulation, different
+summation order); bf16 storage: outputs are compared after rounding the specification's result to
+bf16 (1 ulp = 2^-8 relative).  Element-wise comparisons tolerate a 1e-4 fraction of outliers in the
+kernels whose result depends on the sign of a rounded pre-activation (a LeakyReLU/ReLU unit whose
+pre-activation rounds to the other side of zero legitimately takes the other slope).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from spatiotemporal_variable_separation_b200 import _lib as L
+from tests import emu
+
+pytestmark = pytest.mark.gpu
+DT = {'f32': torch.float32, 'bf16': torch.bfloat16}
+
+
+def run_both(name, args):
+    """args: list of CPU tensors / scalars / Geom.  Runs CUDA on device copies and the emulator on CPU
+    copies; returns (gpu tensors moved back, cpu tensors) in argument order."""
+    cpu = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+    gpu = [a.cuda() if isinstance(a, torch.Tensor) else a for a in args]
+    L.call(name, *gpu[:-1], L.stream())
+    torch.cuda.synchronize()
+    emu.emu_call(name, *cpu)
+    return [g.cpu() if isinstance(g, torch.Tensor) else g for g in gpu], cpu
+
+
+def close(a, b, dtype, what, outliers=0.0, scale=None):
+    a, b = a.double().flatten(), b.double().flatten()
+    if dtype == torch.bfloat16:
+        rtol = 2 ** -7
+    else:
+        rtol = 2e-5
+    ref = float(b.abs().max()) if scale is None else scale
+    bad = (a - b).abs() > rtol * b.abs() + rtol * ref * 1e-1 + 1e-30
+    frac = float(bad.double().mean())
+    assert frac <= outliers, f'{what}: {frac:.2e} of elements off (max err {float((a - b).abs().max()):.3e}, ref max {ref:.3e})'
+
+
+def geom(dtype, N, H, W, C, K, R, stride, pad, groups=1, act=0, flags=0):
+    P = (H + 2 * pad - R) // stride + 1
+    Q = (W + 2 * pad - R) // stride + 1
+    return L.Geom(0 if dtype == torch.float32 else 1, N, H, W, C, P, Q, K, R, R, stride, pad, groups, act, flags), P, Q
+
+
+# (N, H, W, C, K, R, stride, pad, groups): every conv geometry class of the five configurations
+CONV_CASES = [
+    (6, 16, 16, 16, 32, 4, 2, 1, 2),      # DCGAN k4 s2 p1
+    (4, 64, 64, 5, 8, 4, 2, 1, 1),        # first encoder layer, C % 4 != 0
+    (8, 4, 4, 24, 20, 4, 1, 0, 2),        # 4x4 valid conv == Flatten+Linear / first_upconv
+    (9, 1, 1, 37, 50, 1, 1, 0, 3),        # Linear, odd sizes
+    (4, 12, 12, 16, 24, 3, 1, 1, 2),      # VGG / SST 3x3
+    (2, 64, 64, 15, 16, 5, 2, 3, 1),      # ResNet18 stem, 64 -> 33
+    (4, 17, 17, 8, 16, 3, 2, 1, 2),       # ResNet18 stride-2 block, odd size
+    (4, 17, 17, 8, 16, 1, 2, 0, 1),       # ResNet18 1x1 s2 downsample
+    (4, 3, 3, 32, 12, 3, 1, 0, 1),        # ResNet18 conv_out
+    (4, 32, 32, 4, 64, 4, 2, 1, 4),       # last DCGAN decoder layer seen from the big side (C small)
+    (130, 8, 8, 8, 8, 4, 2, 1, 2),        # rows not a multiple of the tile, groups of 65 samples
+]
+
+
+@pytest.mark.parametrize('dt', ['f32', 'bf16'])
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('mode', [L.DIRECT, L.TRANSPOSED])
+def test_conv_forward(case, mode, dt):
+    N, H, W, C, K, R, stride, pad, G = case
+    dtype = DT[dt]
+    torch.manual_seed(1)
+    g, P, Q = geom(dtype, N, H, W, C, K, R, stride, pad, groups=G)
+    if mode == L.DIRECT:
+        x, OC, IC, oshape = torch.randn(N, H, W, C), K, C, (N, P, Q, K)
+    else:
+        x, OC, IC, oshape = torch.randn(N, P, Q, K), C, K, (N, H, W, C)
+    wp = torch.randn(OC, R * R, IC) / np.sqrt(IC * R * R)
+    bias = torch.randn(OC)
+    out = torch.zeros(oshape)
+    stats = torch.zeros(G * OC * 2, dtype=torch.float64)
+    x, wp, out = x.to(dtype), wp.to(dtype), out.to(dtype)
+    gpu, cpu = run_both('vs_conv_forward', [g, mode, x, wp, bias, out, stats, None])
+    close(gpu[5], cpu[5], dtype, 'conv out')
+    # statistics are taken from the fp32 accumulator on both sides
+    close(gpu[6].float(), cpu[6].float(), torch.float32, 'bn stats', scale=float(cpu[6].abs().max()))
+    # fused activation epilogue, no stats
+    for act in (2, 4):
+        g2, _, _ = geom(dtype, N, H, W, C, K, R, stride, pad, groups=1, act=act)
+        gpu, cpu = run_both('vs_conv_forward', [g2, mode, x, wp, bias, out.clone(), None, None])
+        close(gpu[5], cpu[5], dtype, f'conv out act={act}', outliers=1e-4)
+    # no bias
+    gpu, cpu = run_both('vs_conv_forward', [g2, mode, x, wp, None, out.clone(), None, None])
+    close(gpu[5], cpu[5], dtype, 'conv out no bias', outliers=1e-4)
+
+
+@pytest.mark.parametrize('dt', ['f32', 'bf16'])
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_wgrad_and_pack(case, dt):
+    N, H, W, C, K, R, stride, pad, G = case
+    dtype = DT[dt]
+    torch.manual_seed(2)
+    g, P, Q = geom(dtype, N, H, W, C, K, R, stride, pad)
+    small, big = torch.randn(N, P, Q, K).to(dtype), torch.randn(N, H, W, C).to(dtype)
+    dw = torch.randn(K, C, R, R)      # accumulate semantics: starts non-zero
+    gpu, cpu = run_both('vs_conv_wgrad', [g, small, big, dw, None])
+    close(gpu[3], cpu[3], torch.float32, 'wgrad', scale=float(cpu[3].abs().max()))
+    w = torch.randn(K, C, R, R)
+    for swap in (0, 1):
+        out = torch.zeros(K * C * R * R).to(dtype)
+        gpu, cpu = run_both('vs_pack_weight', [w, out, g.dtype, K, C, R * R, swap, None])
+        assert torch.equal(gpu[1], cpu[1])
+
+
+@pytest.mark.parametrize('dt', ['f32', 'bf16'])
+@pytest.mark.parametrize('rows,C,G', [(96, 64, 3), (130, 20, 2), (4096, 128, 4), (50, 1, 5), (64, 7, 1)])
+def test_bn_kernels(rows, C, G, dt):
+    dtype = DT[dt]
+    torch.manual_seed(3)
+    y = (torch.randn(rows, C) * 2 + 0.5).to(dtype)
+    stats = torch.stack([y.float().reshape(G, -1, C).double().sum(1),
+                         (y.float().reshape(G, -1, C).double() ** 2).sum(1)], -1).reshape(-1)
+    mean, invstd = torch.zeros(G * C), torch.zeros(G * C)
+    rmean, rvar = torch.randn(C), torch.rand(C) + 0.5
+    nbt = torch.zeros((), dtype=torch.int64) + 3
+    gpu, cpu = run_both('vs_bn_finalize', [stats, G, C, rows // G, 1e-5, 0.1, mean, invstd, rmean, rvar, nbt, None])
+    for i, n in ((6, 'mean'), (7, 'invstd'), (8, 'running_mean'), (9, 'running_var')):
+        close(gpu[i], cpu[i], torch.float32, n)
+    assert int(gpu[10]) == int(cpu[10]) == 3 + G
+    mean, invstd = cpu[6], cpu[7]
+    gamma, beta = torch.randn(C) * 0.1 + 1, torch.randn(C) * 0.1
+    for act in (0, 1, 2, 3, 4, 5):
+        out = torch.zeros(rows, C).to(dtype)
+        gpu, cpu = run_both('vs_bn_act_forward', [y, out, L.dtype_code(y), rows, C, G, mean, invstd, gamma, beta, act, None])
+        close(gpu[1], cpu[1], dtype, f'bn_act_forward act={act}', outliers=1e-4)
+        dout = torch.randn(rows, C).to(dtype)
+        sums = torch.zeros(G * C * 2, dtype=torch.float64)
+        gpu, cpu = run_both('vs_bn_act_backward_reduce',
+                            [dout, y, L.dtype_code(y), rows, C, G, mean, invstd, gamma, beta, act, sums, None])
+        close(gpu[11].float(), cpu[11].float(), torch.float32, f'bn reduce act={act}', scale=float(cpu[11].abs().max()))
+        sums = cpu[11]
+        for train in (1, 0):
+            dy = torch.zeros(rows, C).to(dtype)
+            dgamma, dbeta = torch.randn(C), torch.randn(C)
+            gpu, cpu = run_both('vs_bn_act_backward_apply',
+                                [dout, y, dy, L.dtype_code(y), rows, C, G, mean, invstd, gamma, beta, act, sums, train,
+                                 dgamma, dbeta, None])
+            close(gpu[2], cpu[2], dtype, f'bn apply act={act} train={train}', outliers=1e-4, scale=float(cpu[2].abs().max()))
+            close(gpu[14], cpu[14], torch.float32, 'dgamma')
+            close(gpu[15], cpu[15], torch.float32, 'dbeta')
+    m2, i2 = torch.zeros(C), torch.zeros(C)
+    gpu, cpu = run_both('vs_bn_eval_stats', [rmean, rvar, C, 1e-5, m2, i2, None])
+    close(gpu[4], cpu[4], torch.float32, 'eval mean')
+    close(gpu[5], cpu[5], torch.float32, 'eval invstd')
+
+
+@pytest.mark.parametrize('dt', ['f32', 'bf16'])
+def test_elementwise_kernels(dt):
+    dtype = DT[dt]
+    code = 0 if dtype == torch.float32 else 1
+    torch.manual_seed(4)
+    n = 10007
+    a, b = torch.randn(n).to(dtype), torch.randn(n).to(dtype)
+    for act in range(6):
+        gpu, cpu = run_both('vs_add_act', [a, b, torch.zeros(n).to(dtype), code, n, act, None])
+        close(gpu[2], cpu[2], dtype, f'add_act {act}', outliers=1e-4)
+        gpu, cpu = run_both('vs_act_backward', [a, cpu[2], torch.zeros(n).to(dtype), code, n, act, None])
+        close(gpu[2], cpu[2], dtype, f'act_backward {act}', outliers=1e-4)
+    # concat with broadcast + its backward
+    rows, src_rows = 24, 8
+    src, dst = torch.randn(src_rows, 5).to(dtype), torch.randn(rows, 12).to(dtype)
+    gpu, cpu = run_both('vs_copy_channels', [src, 5, src_rows, dst, 12, 4, rows, code, None])
+    assert torch.equal(gpu[3], cpu[3])
+    gpu, cpu = run_both('vs_slice_channels_reduce', [dst, 12, 4, rows, torch.zeros(src_rows, 5).to(dtype), 5, src_rows, code, None])
+    close(gpu[4], cpu[4], dtype, 'slice_reduce')
+    # mul mixing
+    s, t = torch.randn(src_rows, 6).to(dtype), torch.randn(rows, 6).to(dtype)
+    gpu, cpu = run_both('vs_mul_bcast', [s, src_rows, t, torch.zeros(rows, 6).to(dtype), rows, 6, code, None])
+    close(gpu[3], cpu[3], dtype, 'mul_bcast')
+    d = torch.randn(rows, 6).to(dtype)
+    gpu, cpu = run_both('vs_mul_bcast_backward', [d, s, src_rows, t, torch.zeros(src_rows, 6).to(dtype),
+                                                  torch.zeros(rows, 6).to(dtype), rows, 6, code, None])
+    close(gpu[4], cpu[4], dtype, 'mul_bcast ds')
+    close(gpu[5], cpu[5], dtype, 'mul_bcast dt')
+    # pooling (with exact ties, as after a ReLU) and upsampling
+    for (N, H, W, C, k, st, pad) in [(2, 8, 8, 6, 2, 2, 0), (2, 33, 33, 5, 3, 2, 1)]:
+        x = torch.relu(torch.randn(N, H, W, C)).to(dtype)
+        P = (H + 2 * pad - k) // st + 1
+        gpu, cpu = run_both('vs_maxpool_forward', [x, torch.zeros(N, P, P, C).to(dtype), code, N, H, W, C, k, st, pad, None])
+        assert torch.equal(gpu[1], cpu[1])
+        dy = torch.randn(N, P, P, C).to(dtype)
+        gpu, cpu = run_both('vs_maxpool_backward', [x, dy, torch.zeros(N, H, W, C).to(dtype), code, N, H, W, C, k, st, pad, None])
+        # ties between exact zeros may route to a different zero; the ReLU upstream kills those anyway
+        mask = (x.float() > 0)
+        close(gpu[2].float() * mask, cpu[2].float() * mask, dtype, 'maxpool_backward')
+    x = torch.randn(2, 5, 7, 3).to(dtype)
+    gpu, cpu = run_both('vs_upsample2_forward', [x, torch.zeros(2, 10, 14, 3).to(dtype), code, 2, 5, 7, 3, None])
+    assert torch.equal(gpu[1], cpu[1])
+    dy = torch.randn(2, 10, 14, 3).to(dtype)
+    gpu, cpu = run_both('vs_upsample2_backward', [dy, torch.zeros(2, 5, 7, 3).to(dtype), code, 2, 5, 7, 3, None])
+    close(gpu[1], cpu[1], dtype, 'upsample2_backward')
+    # layout boundary
+    fr = torch.randn(3, 7, 2, 6, 5)
+    gpu, cpu = run_both('vs_frames_to_nhwc', [fr, 3, 7, 2, 6, 5, 2, 4, torch.zeros(3, 6, 5, 8).to(dtype), code, None])
+    assert torch.equal(gpu[8], cpu[8])
+    xi = torch.randn(3, 6, 5, 4).to(dtype)
+    gpu, cpu = run_both('vs_nhwc_to_nchw', [xi, code, torch.zeros(3, 4, 6, 5), 3, 4, 6, 5, None])
+    assert torch.equal(gpu[2], cpu[2])
+    gpu, cpu = run_both('vs_nchw_to_nhwc', [cpu[2], torch.zeros(3, 6, 5, 4).to(dtype), code, 3, 4, 6, 5, None])
+    assert torch.equal(gpu[1], cpu[1])
+    # column sums
+    m = torch.randn(1000, 37).to(dtype)
+    gpu, cpu = run_both('vs_colsum', [m, code, 1000, 37, torch.randn(37), None])
+    close(gpu[4], cpu[4], torch.float32, 'colsum', scale=float(cpu[4].abs().max()))
+
+
+def test_loss_and_adam_kernels():
+    torch.manual_seed(5)
+    B, T, Ln = 4, 5, 96
+    a = torch.randn(T, B, Ln).transpose(0, 1)            # [B,T,L] view, strides (L, B*L, 1)
+    full = torch.randn(B, 9, Ln)
+    b = full[:, 4:]
+    abase, fbase = a.transpose(0, 1).contiguous().reshape(-1), full.reshape(-1)
+    acc = torch.zeros(2, dtype=torch.float64)
+    # the views are described by explicit strides; pass the base buffers (b starts 4 frames in)
+    boff = fbase[4 * Ln:]
+    gpu, cpu = run_both('vs_sqdiff_sum', [abase, Ln, B * Ln, boff, 9 * Ln, Ln, B, T, Ln, acc[0:1], None])
+    want = float(((a - b) ** 2).double().sum())
+    assert abs(float(gpu[9][0]) - want) < 1e-6 * want and abs(float(cpu[9][0]) - want) < 1e-6 * want
+    gpu, cpu = run_both('vs_sqdiff_sum', [abase, Ln, B * Ln, None, 0, 0, B, T, Ln, acc[1:2], None])
+    assert abs(float(gpu[9][0]) - float((a ** 2).double().sum())) < 1e-6 * want
+    gt = torch.tensor([0.5, 2.0])
+    for accumulate in (0, 1):
+        da = torch.randn(T * B * Ln)
+        gpu, cpu = run_both('vs_sqdiff_backward', [abase, Ln, B * Ln, boff, 9 * Ln, Ln, B, T, Ln, 0.25, gt[0:1], gt[1:2],
+                                                   45.0, da, accumulate, None])
+        close(gpu[13], cpu[13], torch.float32, 'sqdiff_backward')
+    accd = torch.tensor([3.0, 5.0, 7.0], dtype=torch.float64)
+    coef = (ctypes.c_double * 3)(0.5, 0.25, 2.0)
+    lamb = (ctypes.c_double * 3)(10.0, 45.0, 0.001)
+    terms = torch.zeros(4)
+    gpu, cpu = run_both('vs_loss_combine', [accd, coef, lamb, 3, terms, None])
+    close(gpu[4], cpu[4], torch.float32, 'loss_combine')
+    # Adam: 3 steps, host and device step counters, odd length (tail path)
+    n = 4 * 1000 + 3
+    p, g = torch.randn(n + 1)[:n].clone(), torch.randn(n)
+    P = torch.zeros(n + 5)
+    for use_dev in (False, True):
+        pg, gg, mg, vg = [torch.zeros(n + 1).cuda() for _ in range(4)]
+        pg[:n], gg[:n] = p.cuda(), g.cuda()
+        pc, mc, vc = p.clone(), torch.zeros(n), torch.zeros(n)
+        step_dev = torch.zeros(1, dtype=torch.int32).cuda()
+        for step in (1, 2, 3):
+            step_dev += 1
+            L.call('vs_adam_step', pg, gg, mg, vg, n, 4e-4, 0.5, 0.99, 1e-8, 0.5, 0 if use_dev else step,
+                   step_dev if use_dev else None, L.stream())
+            emu.emu_call('vs_adam_step', pc, g, mc, vc, n, 4e-4, 0.5, 0.99, 1e-8, 0.5, step, None, None)
+        torch.cuda.synchronize()
+        close(pg[:n].cpu(), pc, torch.float32, 'adam param')
+        close(vg[:n].cpu(), vc, torch.float32, 'adam v')
+        assert float(pg[n]) == 0.0
+
+
+def test_error_reporting_and_launch_count():
+    before = L.launch_count()
+    x = torch.zeros(8, device='cuda')
+    L.call('vs_add_act', x, x, x, 0, 8, 0, L.stream())
+    assert L.launch_count() == before + 1
+    bad = L.Geom(0, 2, 8, 8, 4, 5, 5, 4, 3, 3, 1, 1, 1, 0, 0)     # P/Q inconsistent
+    with pytest.raises(RuntimeError, match='inconsistent'):
+        L.call('vs_conv_forward', bad, 0, x, x, None, x, None, L.stream())
+    with pytest.raises(RuntimeError, match='dtype'):
+        L.call('vs_add_act', x, x, x, 7, 8, 0, L.stream())
