@@ -108,7 +108,7 @@ def test_two_fused_adam_steps_match_reference_train_loop(name):
                 continue
             s = summarize(str(n), state[str(n)])
             # running means carry the (noise-driven) pre-BN biases: looser
-            tol = 5e-3 if str(n).endswith('running_mean') else 2e-4
+            tol = 5e-3 if str(n).endswith('running_mean') else 5e-4
             assert np.all(np.abs(s - ref) <= tol * max(abs(ref[0]), 1e-12)), (n, s, ref)
 
 
