@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(cc, srcs))
-    r = subprocess.run([NVCC, '-shared', '-o', LIB] + objs + ['-lcuda', '-lcudart'], capture_output=True, text=True)
+    r = subprocess.run([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart'], capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError('link failed')

@@ -1,0 +1,594 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// Replaces the cuDNN kernels behind nn.Conv2d / nn.ConvTranspose2d of the DCGAN / VGG / SST stacks
+// (/root/reference/var_sep/networks/conv.py:119-123,147-170,258-263,295-318) for the layers whose
+// channel counts are multiples of 64.  One kernel covers
+//   - direct convolutions (any R x S, stride 1 or 2, zero padding),
+//   - transposed convolutions, decomposed into stride*stride output-parity classes so that no
+//     structurally-zero tap is ever multiplied (k4 s2 p1: four 2x2 stride-1 convolutions),
+// as a "tap GEMM": for every output tile of 128 pixels and every (tap, 64-channel chunk) one TMA box
+// of the NHWC input (shifted by the tap offset, zero-filled outside the image by the TMA unit, strided
+// for stride-2 convolutions) is multiplied with a [BN x 64] slab of the packed weights.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (TMEM -> registers -> bias / activation -> bf16 -> global).
+// Two CTAs are resident per SM so one tile's epilogue overlaps the other's main loop.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace vs {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_MAX_TAPS = 25, TC_MAX_CLASSES = 4;
+
+struct TcParams {
+    int N, OH, OW, OC;
+    int OHc, OWc, ost;        // class grid (output pixels of one parity class) and output sub-sampling
+    int WT, HT, NT;           // tile box in class-grid units, WT*HT*NT == 128
+    int tiles_w, tiles_h, tiles_n;
+    int IC, kchunks, ntaps;
+    int in_sh, in_sw;         // class-grid -> input coordinate multiplier
+    int act, has_bias;
+    signed char dh[TC_MAX_CLASSES][TC_MAX_TAPS], dw[TC_MAX_CLASSES][TC_MAX_TAPS];
+    unsigned char wtap[TC_MAX_CLASSES][TC_MAX_TAPS];
+    unsigned char ca[TC_MAX_CLASSES], cb[TC_MAX_CLASSES];
+};
+
+// ----------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t idesc_bf16_f32(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct TcSmem {
+    static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                         const __grid_constant__ CUtensorMap map_b,
+                                                         const __grid_constant__ TcParams p,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+    using S = TcSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cls = blockIdx.z;
+    const int n0 = blockIdx.y * BN;
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h;
+    const int tn = t / p.tiles_h;
+    const int j0 = tw * p.WT, i0 = th * p.HT, b0 = tn * p.NT;
+    const int nkb = p.ntaps * p.kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+                uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + S::A_BYTES;
+                mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                tma_load_4d(a_dst, &map_a, &full[s], kc * TC_BK, j0 * p.in_sw + p.dw[cls][tap], i0 * p.in_sh + p.dh[cls][tap], b0);
+                tma_load_2d(b_dst, &map_b, &full[s], p.wtap[cls][tap] * p.IC + kc * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16_f32(BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                    umma_bf16(tmem_base, kmajor_sw128_desc(a_addr + k * 32), kmajor_sw128_desc(b_addr + k * 32), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);          // smem slot reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full);              // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;             // tile-local pixel (TMEM lane)
+        const int w = m % p.WT, h = (m / p.WT) % p.HT, n = m / (p.WT * p.HT);
+        const int i = i0 + h, j = j0 + w, nn = b0 + n;
+        const bool ok = i < p.OHc && j < p.OWc && nn < p.N;
+        const long long pix = ((long long)nn * p.OH + (long long)i * p.ost + p.ca[cls]) * p.OW + (long long)j * p.ost + p.cb[cls];
+        __nv_bfloat16* dst = out + pix * p.OC + n0;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (ok) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = v * 8 + e * 2;
+                        float x0 = __uint_as_float(r[c]), x1 = __uint_as_float(r[c + 1]);
+                        if (p.has_bias) { x0 += __ldg(bias + n0 + c0 + c); x1 += __ldg(bias + n0 + c0 + c + 1); }
+                        x0 = act_fwd(x0, p.act);
+                        x1 = act_fwd(x1, p.act);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
+                        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+// per-(group, channel) sum / sum of squares of a bf16 [rows, C] matrix (BatchNorm batch statistics of
+// the tensor-core path's output; the CUDA-core path fuses them into its epilogue)
+__global__ void colstats_kernel(const __nv_bfloat16* __restrict__ y, int C, long long rpg, int chunks,
+                                double* __restrict__ stats) {
+    __shared__ double r1[8][65], r2[8][65];
+    const int c = blockIdx.x * 64 + threadIdx.x * 2;     // 32 threads x 2 channels
+    const int g = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
+    const long long per = (rpg + chunks - 1) / chunks;
+    const long long r0 = (long long)g * rpg + (long long)chunk * per;
+    long long r_end = r0 + per;
+    if (r_end > (long long)(g + 1) * rpg) r_end = (long long)(g + 1) * rpg;
+    // fp64 running sums (the kernel is HBM-bound; BatchNorm variances are differences of these sums)
+    double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;
+    if (c < C)
+        for (long long r = r0 + threadIdx.y; r < r_end; r += 8) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(y + r * C + c);
+            const float2 f = __bfloat1622float2(v);
+            s1a += f.x; s2a += (double)f.x * f.x; s1b += f.y; s2b += (double)f.y * f.y;
+        }
+    r1[threadIdx.y][threadIdx.x * 2] = s1a; r1[threadIdx.y][threadIdx.x * 2 + 1] = s1b;
+    r2[threadIdx.y][threadIdx.x * 2] = s2a; r2[threadIdx.y][threadIdx.x * 2 + 1] = s2b;
+    __syncthreads();
+    if (threadIdx.y < 2) {
+        const int cc = blockIdx.x * 64 + threadIdx.x * 2 + threadIdx.y;
+        if (cc < C) {
+            double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { t1 += r1[k][threadIdx.x * 2 + threadIdx.y]; t2 += r2[k][threadIdx.x * 2 + threadIdx.y]; }
+            atomicAdd(&stats[((long long)g * C + cc) * 2], t1);
+            atomicAdd(&stats[((long long)g * C + cc) * 2 + 1], t2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+static bool tc_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VARSEP_DISABLE_TC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const float* bias, void* out,
+                     int classes, cudaStream_t stream) {
+    using S = TcSmem<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return fail("tc_conv_kernel smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(p.OC / BN), (unsigned)classes);
+    tc_conv_kernel<BN, STAGES><<<grid, 192, S::TOTAL, stream>>>(ma, mb, p, bias, (__nv_bfloat16*)out);
+    return launched("tc_conv_kernel");
+}
+
+// returns 0 = done, -1 = geometry not eligible (caller falls back), >0 = error
+int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
+                    double* stats, cudaStream_t stream) {
+    if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || tc_disabled()) return -1;
+    const bool tr = mode == VS_CONV_TRANSPOSED;
+    const int IH = tr ? g->P : g->H, IW = tr ? g->Q : g->W, IC = tr ? g->K : g->C;
+    const int OH = tr ? g->H : g->P, OW = tr ? g->W : g->Q, OC = tr ? g->C : g->K;
+    const int st = g->stride;
+    if (IC % 64 != 0 || OC % 64 != 0 || st > 2 || g->R * g->S > TC_MAX_TAPS) return -1;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wp) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
+    const int ost = tr ? st : 1;
+    if (OH % ost != 0 || OW % ost != 0) return -1;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return -1;
+
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = g->N; p.OH = OH; p.OW = OW; p.OC = OC; p.ost = ost;
+    p.OHc = OH / ost; p.OWc = OW / ost;
+    p.WT = pow2ceil(p.OWc) < 128 ? pow2ceil(p.OWc) : 128;
+    p.HT = pow2ceil(p.OHc) < 128 / p.WT ? pow2ceil(p.OHc) : 128 / p.WT;
+    p.NT = 128 / (p.WT * p.HT);
+    p.tiles_w = (int)cdiv(p.OWc, p.WT); p.tiles_h = (int)cdiv(p.OHc, p.HT); p.tiles_n = (int)cdiv(g->N, p.NT);
+    p.IC = IC; p.kchunks = IC / 64;
+    p.in_sh = p.in_sw = tr ? 1 : st;
+    p.act = g->act; p.has_bias = bias != nullptr;
+    int classes = ost * ost, ntaps = -1;
+    for (int cls = 0; cls < classes; ++cls) {
+        const int a = cls / ost, b = cls % ost;
+        p.ca[cls] = (unsigned char)a; p.cb[cls] = (unsigned char)b;
+        int n = 0;
+        if (!tr) {
+            for (int r = 0; r < g->R; ++r)
+                for (int s = 0; s < g->S; ++s) { p.dh[cls][n] = (signed char)(r - g->pad); p.dw[cls][n] = (signed char)(s - g->pad); p.wtap[cls][n] = (unsigned char)(r * g->S + s); ++n; }
+        } else {
+            for (int r = (a + g->pad) % st; r < g->R; r += st)
+                for (int s = (b + g->pad) % st; s < g->S; s += st) {
+                    p.dh[cls][n] = (signed char)((a + g->pad - r) / st); p.dw[cls][n] = (signed char)((b + g->pad - s) / st);
+                    p.wtap[cls][n] = (unsigned char)(r * g->S + s); ++n;
+                }
+        }
+        if (ntaps >= 0 && n != ntaps) return -1;     // classes with unequal tap counts (odd filters, stride 2)
+        ntaps = n;
+    }
+    if (ntaps <= 0) return -1;
+    p.ntaps = ntaps;
+    if (p.WT * p.in_sw > 256 || p.HT * p.in_sh > 256) return -1;
+
+    // A: NHWC input [N, IH, IW, IC] viewed as (IC, IW, IH, N); traversal stride = convolution stride
+    CUtensorMap ma, mb;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)IC, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)IC * 2, (cuuint64_t)IC * IW * 2, (cuuint64_t)IC * IW * IH * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(p.WT * p.in_sw), (cuuint32_t)(p.HT * p.in_sh), (cuuint32_t)p.NT};
+        cuuint32_t estr[4] = {1, (cuuint32_t)p.in_sw, (cuuint32_t)p.in_sh, 1};
+        CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+    }
+    const int BN = OC % 128 == 0 ? 128 : 64;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)g->R * g->S * IC, (cuuint64_t)OC};
+        cuuint64_t strides[1] = {(cuuint64_t)g->R * g->S * IC * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    }
+    int rc = BN == 128 ? launch_tc<128, 3>(ma, mb, p, bias, out, classes, stream)
+                       : launch_tc<64, 4>(ma, mb, p, bias, out, classes, stream);
+    if (rc) return rc;
+    if (stats != nullptr) {
+        const long long rows = (long long)g->N * OH * OW, rpg = rows / g->groups;
+        const int cx = (int)cdiv(OC, 64);
+        long long chunks = cdiv(4LL * num_sms(), (long long)cx * g->groups);
+        if (chunks > cdiv(rpg, 64)) chunks = cdiv(rpg, 64);
+        if (chunks < 1) chunks = 1;
+        dim3 grid(cx, (unsigned)(g->groups * chunks)), block(32, 8);
+        colstats_kernel<<<grid, block, 0, stream>>>((const __nv_bfloat16*)out, OC, rpg, (int)chunks, stats);
+        rc = launched("colstats_kernel");
+    }
+    return rc;
+}
+
+}  // namespace vs
+
+// =================================================================================================
+// Weight gradient on the tensor cores.
+//   dw[k][c][tap] += sum_pix small[pix][k] * big[src(pix, tap)][c]
+// is a GEMM whose REDUCTION dimension is the pixel index, i.e. both operands are "MN-major" in
+// shared memory (channels contiguous, pixels along K): exactly what a TMA box of an NHWC tensor is.
+// A = 128 channels of `small` (two 64-channel boxes), B = BN channels of `big` gathered at the tap
+// offset (strided box for stride-2 convolutions, zero-filled outside the image), 64 pixels per
+// pipeline stage, fp32 accumulation in TMEM, split over pixel ranges across CTAs, and an epilogue of
+// fp32 reductions (red.global.add) straight into the torch-layout gradient.
+// =================================================================================================
+namespace vs {
+
+struct TcWgradParams {
+    int N, P, Q, K, C, R, S, stride, pad;
+    int WT, HT, NT, tiles_w, tiles_h, tiles_n;   // 64-pixel boxes over the small grid
+    int c_tiles, k_tiles;
+    int total_ptiles, ptiles_per_split;
+};
+
+// MN-major operand, 128-byte swizzle: 64-element chunks `lbo_bytes` apart, 8-pixel groups 1024 B apart
+__device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 2) tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_small,
+                                                          const __grid_constant__ CUtensorMap map_big,
+                                                          const __grid_constant__ TcWgradParams p,
+                                                          float* __restrict__ dw) {
+    constexpr int PIX = 64;
+    constexpr int A_BYTES = 128 * PIX * 2, B_BYTES = BN * PIX * 2, STAGE_BYTES = A_BYTES + B_BYTES, CHUNK = 64 * PIX * 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kt = blockIdx.x % p.k_tiles, ct = blockIdx.x / p.k_tiles;
+    const int tap = blockIdx.y;
+    const int r = tap / p.S, s = tap % p.S;
+    const int pt0 = blockIdx.z * p.ptiles_per_split;
+    int pt1 = pt0 + p.ptiles_per_split;
+    if (pt1 > p.total_ptiles) pt1 = p.total_ptiles;
+    const int nkb = pt1 - pt0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (nkb <= 0) {          // uniform: nothing to reduce for this split
+        __syncthreads();
+        if (warp == 1) tmem_dealloc<BN>(tmem_base);
+        return;
+    }
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                int t = pt0 + kb;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h;
+                const int tn = t / p.tiles_h;
+                const int q0 = tw * p.WT, p0 = th * p.HT, b0 = tn * p.NT;
+                uint8_t* a_dst = smem + st * STAGE_BYTES;
+                uint8_t* b_dst = a_dst + A_BYTES;
+                mbar_expect_tx(&full[st], STAGE_BYTES);
+                tma_load_4d(a_dst, &map_small, &full[st], kt * 128, q0, p0, b0);
+                tma_load_4d(a_dst + CHUNK, &map_small, &full[st], kt * 128 + 64, q0, p0, b0);
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                    tma_load_4d(b_dst + j * CHUNK, &map_big, &full[st], ct * BN + j * 64, q0 * p.stride - p.pad + s,
+                                p0 * p.stride - p.pad + r, b0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D=f32, A=B=bf16, both MN-major (bits 15, 16), M=128, N=BN
+            constexpr uint32_t idesc = idesc_bf16_f32(BN) | (1u << 15) | (1u << 16);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + st * STAGE_BYTES);
+                const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < PIX / 16; ++k) {
+                    // 16 pixels = two 8-pixel swizzle groups = 2048 bytes along K
+                    umma_bf16(tmem_base, mnmajor_sw128_desc(a_addr + k * 2048, CHUNK), mnmajor_sw128_desc(b_addr + k * 2048, CHUNK),
+                              idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[st]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int k = kt * 128 + q * 32 + lane;          // output row = channel of `small`
+        const int RS = p.R * p.S;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            float* dst = dw + ((long long)k * p.C + ct * BN + c0) * RS + tap;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) atomicAdd(dst + (long long)c * RS, __uint_as_float(v[c]));
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_tc_wgrad(const CUtensorMap& ms, const CUtensorMap& mb, const TcWgradParams& p, float* dw, int splits,
+                           cudaStream_t stream) {
+    constexpr int SMEM = STAGES * (128 * 64 * 2 + BN * 64 * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return fail("tc_wgrad_kernel smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid((unsigned)(p.k_tiles * p.c_tiles), (unsigned)(p.R * p.S), (unsigned)splits);
+    tc_wgrad_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(ms, mb, p, dw);
+    return launched("tc_wgrad_kernel");
+}
+
+int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream) {
+    if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || tc_disabled()) return -1;
+    if (g->K % 128 != 0 || g->C % 64 != 0 || g->stride > 2) return -1;
+    if ((reinterpret_cast<uintptr_t>(small_) | reinterpret_cast<uintptr_t>(big)) & 15) return -1;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return -1;
+    TcWgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = g->N; p.P = g->P; p.Q = g->Q; p.K = g->K; p.C = g->C; p.R = g->R; p.S = g->S; p.stride = g->stride; p.pad = g->pad;
+    p.WT = pow2ceil(g->Q) < 64 ? pow2ceil(g->Q) : 64;
+    p.HT = pow2ceil(g->P) < 64 / p.WT ? pow2ceil(g->P) : 64 / p.WT;
+    p.NT = 64 / (p.WT * p.HT);
+    // partial boxes would add zero-filled pixels of `small` (harmless) but the boxes must tile the grid exactly
+    // in W/H for the pixel <-> pixel correspondence between the two operands
+    if (g->Q % p.WT != 0 || g->P % p.HT != 0) return -1;
+    p.tiles_w = g->Q / p.WT; p.tiles_h = g->P / p.HT; p.tiles_n = (int)cdiv(g->N, p.NT);
+    p.total_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int BN = g->C % 128 == 0 ? 128 : 64;
+    p.k_tiles = g->K / 128; p.c_tiles = g->C / BN;
+    const long long base = (long long)p.k_tiles * p.c_tiles * g->R * g->S;
+    long long splits = cdiv(4LL * num_sms(), base);
+    if (splits > p.total_ptiles) splits = p.total_ptiles;
+    if (splits > 65535) splits = 65535;
+    if (splits < 1) splits = 1;
+    p.ptiles_per_split = (int)cdiv(p.total_ptiles, splits);
+    splits = cdiv(p.total_ptiles, p.ptiles_per_split);
+    if (p.WT * g->stride > 256 || p.HT * g->stride > 256) return -1;
+
+    CUtensorMap ms, mb;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g->K, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)g->K * 2, (cuuint64_t)g->K * g->Q * 2, (cuuint64_t)g->K * g->Q * g->P * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.WT, (cuuint32_t)p.HT, (cuuint32_t)p.NT};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult rc = enc(&ms, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(small_), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(small) failed: %d", (int)rc);
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g->C, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)g->C * 2, (cuuint64_t)g->C * g->W * 2, (cuuint64_t)g->C * g->W * g->H * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(p.WT * g->stride), (cuuint32_t)(p.HT * g->stride), (cuuint32_t)p.NT};
+        cuuint32_t estr[4] = {1, (cuuint32_t)g->stride, (cuuint32_t)g->stride, 1};
+        CUresult rc = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(big), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(big) failed: %d", (int)rc);
+    }
+    return BN == 128 ? launch_tc_wgrad<128, 3>(ms, mb, p, dw, (int)splits, stream)
+                     : launch_tc_wgrad<64, 4>(ms, mb, p, dw, (int)splits, stream);
+}
+
+}  // namespace vs

@@ -94,8 +94,55 @@ def test_conv_forward(case, mode, dt):
     close(gpu[5], cpu[5], dtype, 'conv out no bias', outliers=1e-4)
 
 
+# geometries eligible for the tcgen05 path (channel counts multiples of 64): DCGAN k4 s2 p1 in both
+# directions, 3x3 stride 1, tiles spanning several images, partial tiles, 2 output-channel tiles
+TC_CASES = [
+    (16, 16, 16, 64, 128, 4, 2, 1, 2),
+    (8, 8, 8, 128, 256, 4, 2, 1, 2),
+    (6, 32, 32, 64, 64, 4, 2, 1, 3),
+    (4, 16, 16, 64, 64, 3, 1, 1, 2),
+    (2, 32, 32, 128, 64, 3, 1, 1, 1),
+    (130, 8, 8, 64, 64, 4, 2, 1, 2),
+    (3, 64, 64, 64, 64, 3, 1, 1, 1),
+    (5, 4, 4, 64, 128, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+@pytest.mark.parametrize('mode', [L.DIRECT, L.TRANSPOSED])
+def test_conv_forward_tensor_core(case, mode):
+    """bf16 tcgen05 kernel against (a) the specification and (b) the CUDA-core kernel on the same inputs."""
+    N, H, W, C, K, R, stride, pad, G = case
+    dtype = torch.bfloat16
+    torch.manual_seed(7)
+    g, P, Q = geom(dtype, N, H, W, C, K, R, stride, pad, groups=G)
+    if mode == L.DIRECT:
+        x, OC, IC, oshape = torch.randn(N, H, W, C), K, C, (N, P, Q, K)
+    else:
+        x, OC, IC, oshape = torch.randn(N, P, Q, K), C, K, (N, H, W, C)
+    wp = (torch.randn(OC, R * R, IC) / np.sqrt(IC * R * R)).to(dtype)
+    bias = torch.randn(OC)
+    x = x.to(dtype)
+    out = torch.full(oshape, float('nan')).to(dtype)
+    stats = torch.zeros(G * OC * 2, dtype=torch.float64)
+    gpu, cpu = run_both('vs_conv_forward', [g, mode, x, wp, bias, out, stats, None])
+    close(gpu[5], cpu[5], dtype, 'tc conv out')
+    # the tensor-core path takes the statistics of the bf16-rounded output
+    yq = cpu[5].float().reshape(G, -1, OC).double()
+    want = torch.stack([yq.sum(1), (yq * yq).sum(1)], -1).reshape(-1)
+    close(gpu[6].float(), want.float(), torch.float32, 'tc bn stats', scale=float(want.abs().max()))
+    g2, _, _ = geom(dtype, N, H, W, C, K, R, stride, pad, act=2, flags=L.FLAG_FORCE_SIMT)
+    g3, _, _ = geom(dtype, N, H, W, C, K, R, stride, pad, act=2)
+    xs, ws, bs = x.cuda(), wp.cuda(), bias.cuda()
+    o_simt, o_tc = torch.zeros(oshape, dtype=dtype, device='cuda'), torch.zeros(oshape, dtype=dtype, device='cuda')
+    L.call('vs_conv_forward', g2, mode, xs, ws, bs, o_simt, None, L.stream())
+    L.call('vs_conv_forward', g3, mode, xs, ws, bs, o_tc, None, L.stream())
+    torch.cuda.synchronize()
+    close(o_tc.cpu(), o_simt.cpu(), dtype, 'tc vs simt', outliers=1e-4)
+
+
 @pytest.mark.parametrize('dt', ['f32', 'bf16'])
-@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('case', CONV_CASES + TC_CASES)
 def test_conv_wgrad_and_pack(case, dt):
     N, H, W, C, K, R, stride, pad, G = case
     dtype = DT[dt]
@@ -105,6 +152,13 @@ def test_conv_wgrad_and_pack(case, dt):
     dw = torch.randn(K, C, R, R)      # accumulate semantics: starts non-zero
     gpu, cpu = run_both('vs_conv_wgrad', [g, small, big, dw, None])
     close(gpu[3], cpu[3], torch.float32, 'wgrad', scale=float(cpu[3].abs().max()))
+    if dtype == torch.bfloat16:     # tensor-core kernel (when eligible) against the CUDA-core kernel
+        g2, _, _ = geom(dtype, N, H, W, C, K, R, stride, pad, flags=L.FLAG_FORCE_SIMT)
+        d1, d2 = torch.zeros(K, C, R, R, device='cuda'), torch.zeros(K, C, R, R, device='cuda')
+        L.call('vs_conv_wgrad', g, small.cuda(), big.cuda(), d1, L.stream())
+        L.call('vs_conv_wgrad', g2, small.cuda(), big.cuda(), d2, L.stream())
+        torch.cuda.synchronize()
+        close(d1.cpu(), d2.cpu(), torch.float32, 'tc wgrad vs simt', scale=float(d2.abs().max()))
     w = torch.randn(K, C, R, R)
     for swap in (0, 1):
         out = torch.zeros(K * C * R * R).to(dtype)
