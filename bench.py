@@ -142,7 +142,7 @@ def workload_name(cfg):
 class Trainer:
     """Model + fused Adam + (optionally) one captured CUDA graph per value of the host draw t_random."""
 
-    def __init__(self, cfg, device, dtype, world, use_graph):
+    def __init__(self, cfg, device, dtype, world, use_graph, overlap=True):
         from spatiotemporal_variable_separation_b200 import ops
         from spatiotemporal_variable_separation_b200.networks.factory import build_model
         from spatiotemporal_variable_separation_b200.optim import FusedAdam
@@ -157,7 +157,8 @@ class Trainer:
             for b in self.net.buffers():
                 dist.broadcast(b, 0)
         self.opt = FusedAdam(self.net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
-        self.opt.grad_scale = 1.0 / world
+        from spatiotemporal_variable_separation_b200.parallel import GradReducer
+        self.reducer = GradReducer(self.net, self.opt, overlap=overlap) if world > 1 else None
         B, T = cfg['batch_size'], cfg['nt_cond'] + cfg['nt_pred']
         self.full = torch.zeros(B, T, *cfg['shape'], device=device)        # static input buffer
         self.terms = torch.zeros(5, device=device)
@@ -169,11 +170,10 @@ class Trainer:
         self.opt.zero_grad()
         out = vs_train.step_losses(self.net, self.full, c['nt_cond'], c['nt_pred'], c['offset'], c['skipco'],
                                    c['lamb_ae'], c['lamb_s'], 0 if c['no_s'] else c['lamb_t'], c['lamb_pred'],
-                                   c['architecture'] == 'encoderSST', t_random)
+                                   c['architecture'] == 'encoderSST', t_random, self.reducer)
         out['total'].backward()
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.opt.flat_g)
+        if self.reducer is not None:
+            self.reducer.finish()
         self.opt.step()
         self.terms.copy_(out['terms'].detach())
 
@@ -213,7 +213,7 @@ def run_ours(args, cfg):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=device)
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
-    tr = Trainer(cfg, device, dtype, world, not args.no_graph)
+    tr = Trainer(cfg, device, dtype, world, not args.no_graph, overlap=not args.no_overlap)
     B, n_frames = cfg['batch_size'], cfg['nt_cond'] + cfg['nt_pred']
 
     # a pool of synthetic batches: pinned host copies (e2e) and device-resident copies (value)
@@ -364,6 +364,7 @@ def main():
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-overlap', action='store_true', help='all-reduce after backward instead of overlapped buckets')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     args = ap.parse_args()

@@ -41,6 +41,10 @@ int num_sms() {
 int conv_forward_simt(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                       double* stats, cudaStream_t stream);
 int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream);
+// streaming kernels for layers with a handful of channels on one side (same return convention)
+int conv_forward_thin(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
+                      double* stats, cudaStream_t stream);
+int conv_wgrad_thin(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream);
 int conv_wgrad_simt(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream);
 // tensor-core paths: 0 = done, -1 = geometry not eligible (fall back to the CUDA-core kernels), >0 = error
 int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
@@ -70,14 +74,18 @@ extern "C" int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* 
     if (int rc = check_geom(g)) return rc;
     VS_REQUIRE(mode == VS_CONV_DIRECT || mode == VS_CONV_TRANSPOSED, "bad mode %d", mode);
     VS_REQUIRE(stats == nullptr || g->act == VS_ACT_NONE, "statistics are taken of the pre-activation: act must be NONE");
-    const int rc = conv_forward_tc(g, mode, in, wp, bias, out, stats, as_stream(stream));
+    int rc = conv_forward_tc(g, mode, in, wp, bias, out, stats, as_stream(stream));
+    if (rc >= 0) return rc;
+    rc = conv_forward_thin(g, mode, in, wp, bias, out, stats, as_stream(stream));
     if (rc >= 0) return rc;
     return conv_forward_simt(g, mode, in, wp, bias, out, stats, as_stream(stream));
 }
 
 extern "C" int vs_conv_wgrad(const vs_conv_geom* g, const void* small_, const void* big, float* dw, void* stream) {
     if (int rc = check_geom(g)) return rc;
-    const int rc = conv_wgrad_tc(g, small_, big, dw, as_stream(stream));
+    int rc = conv_wgrad_thin(g, small_, big, dw, as_stream(stream));
+    if (rc >= 0) return rc;
+    rc = conv_wgrad_tc(g, small_, big, dw, as_stream(stream));
     if (rc >= 0) return rc;
     return conv_wgrad_simt(g, small_, big, dw, as_stream(stream));
 }

@@ -311,6 +311,11 @@ int conv_forward_simt(const vs_conv_geom* g, int mode, const void* in, const voi
     if (mode == VS_CONV_DIRECT) { a.IH = g->H; a.IW = g->W; a.IC = g->C; a.OH = g->P; a.OW = g->Q; a.OC = g->K; }
     else { a.IH = g->P; a.IW = g->Q; a.IC = g->K; a.OH = g->H; a.OW = g->W; a.OC = g->C; }
     a.n_per_group = g->N / g->groups;
+    // transposed convolution of a 1x1 input (first_upconv, conv.py:258): every output pixel (h,w) has exactly
+    // one contributing tap (r,s) = (h,w).  Declaring the class stride to be the filter size makes each output
+    // pixel position its own parity class with a single tap, i.e. R*S plain GEMMs instead of R*S-fold padding.
+    if (a.transposed && a.IH == 1 && a.IW == 1 && g->stride == 1 && g->pad == 0 && g->R == g->S && a.OH == g->R && a.OW == g->S)
+        a.stride = g->R;
     const int st = a.transposed ? a.stride : 1;
     const long long Mc0 = (long long)a.N * cdiv(a.OH, st) * cdiv(a.OW, st);
     dim3 grid((unsigned)cdiv(Mc0, BM), (unsigned)cdiv(a.OC, BN), (unsigned)(st * st));

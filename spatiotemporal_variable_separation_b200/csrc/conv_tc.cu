@@ -28,7 +28,7 @@ struct TcParams {
     int tiles_w, tiles_h, tiles_n;
     int IC, kchunks, ntaps;
     int in_sh, in_sw;         // class-grid -> input coordinate multiplier
-    int act, has_bias;
+    int act, has_bias, partial;
     signed char dh[TC_MAX_CLASSES][TC_MAX_TAPS], dw[TC_MAX_CLASSES][TC_MAX_TAPS];
     unsigned char wtap[TC_MAX_CLASSES][TC_MAX_TAPS];
     unsigned char ca[TC_MAX_CLASSES], cb[TC_MAX_CLASSES];
@@ -202,7 +202,17 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (ok) {
+            if (ok && p.partial) {
+                // OC not a multiple of the tile or rows not 16-byte aligned: predicated scalar stores
+                for (int c = 0; c < 32; ++c) {
+                    const int oc = n0 + c0 + c;
+                    if (oc < p.OC) {
+                        float x = __uint_as_float(r[c]);
+                        if (p.has_bias) x += __ldg(bias + oc);
+                        dst[c0 + c] = __float2bfloat16_rn(act_fwd(x, p.act));
+                    }
+                }
+            } else if (ok) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     uint32_t pk[4];
@@ -280,6 +290,9 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+int stats_of_output(const vs_conv_geom* g, int dtype, const void* out, long long rows, int OC, double* stats,
+                    cudaStream_t stream);   // conv_thin.cu
+
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 static bool tc_disabled() {
@@ -298,7 +311,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
         if (e != cudaSuccess) return fail("tc_conv_kernel smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(p.OC / BN), (unsigned)classes);
+    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)cdiv(p.OC, BN), (unsigned)classes);
     tc_conv_kernel<BN, STAGES><<<grid, 192, S::TOTAL, stream>>>(ma, mb, p, bias, (__nv_bfloat16*)out);
     return launched("tc_conv_kernel");
 }
@@ -311,8 +324,8 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     const int IH = tr ? g->P : g->H, IW = tr ? g->Q : g->W, IC = tr ? g->K : g->C;
     const int OH = tr ? g->H : g->P, OW = tr ? g->W : g->Q, OC = tr ? g->C : g->K;
     const int st = g->stride;
-    if (IC % 64 != 0 || OC % 64 != 0 || st > 2 || g->R * g->S > TC_MAX_TAPS) return -1;
-    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wp) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
+    if (IC % 64 != 0 || st > 2 || g->R * g->S > TC_MAX_TAPS) return -1;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wp)) & 15) return -1;
     const int ost = tr ? st : 1;
     if (OH % ost != 0 || OW % ost != 0) return -1;
     EncodeTiledFn enc = encode_fn();
@@ -364,6 +377,7 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(A) failed: %d", (int)r);
     }
     const int BN = OC % 128 == 0 ? 128 : 64;
+    p.partial = (OC % BN != 0) || (reinterpret_cast<uintptr_t>(out) & 15) ? 1 : 0;
     {
         cuuint64_t dims[2] = {(cuuint64_t)g->R * g->S * IC, (cuuint64_t)OC};
         cuuint64_t strides[1] = {(cuuint64_t)g->R * g->S * IC * 2};
@@ -377,6 +391,7 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     int rc = BN == 128 ? launch_tc<128, 3>(ma, mb, p, bias, out, classes, stream)
                        : launch_tc<64, 4>(ma, mb, p, bias, out, classes, stream);
     if (rc) return rc;
+    if (stats != nullptr && OC % 64 != 0) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
     if (stats != nullptr) {
         const long long rows = (long long)g->N * OH * OW, rpg = rows / g->groups;
         const int cx = (int)cdiv(OC, 64);

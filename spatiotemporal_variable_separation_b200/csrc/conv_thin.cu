@@ -1,0 +1,277 @@
+// HBM-bound "thin" convolutions: layers with a handful of channels on one side, where a 64x64 GEMM
+// tile would be >90 % padding.  In the reference these are the first encoder layer
+// (Conv 5->64, conv.py:119; AI 61 FLOP/B) and the last decoder layer (ConvTranspose 64->1..3,
+// conv.py:263,318; AI 15 FLOP/B) with their gradients.  No tensor cores: the work is streaming the
+// wide tensor once with coalesced 16-byte accesses; grids are sized from the pixel count.
+#include "common.cuh"
+
+namespace vs {
+
+struct ThinArgs {
+    int N, IH, IW, IC, OH, OW, OC, R, S, stride, pad, transposed, act;
+};
+
+__device__ __forceinline__ bool thin_src(const ThinArgs& a, int oh, int ow, int r, int s, int& ih, int& iw) {
+    if (a.transposed) {
+        const int th = oh + a.pad - r, tw = ow + a.pad - s;
+        if (th < 0 || tw < 0 || th % a.stride || tw % a.stride) return false;
+        ih = th / a.stride; iw = tw / a.stride;
+    } else {
+        ih = oh * a.stride - a.pad + r; iw = ow * a.stride - a.pad + s;
+        if (ih < 0 || iw < 0) return false;
+    }
+    return ih < a.IH && iw < a.IW;
+}
+
+// ---- few OUTPUT channels (OC <= 4), IC % 64 == 0: 8 lanes per output pixel, 8 channels per lane and tap.
+// wp: [OC][R*S][IC]
+template <typename T, int OC>
+__global__ void __launch_bounds__(256) thin_out_kernel(ThinArgs a, const T* __restrict__ in, const T* __restrict__ wp,
+                                                       const float* __restrict__ bias, T* __restrict__ out) {
+    const long long total = (long long)a.N * a.OH * a.OW;
+    const int sub = threadIdx.x & 7;
+    // 32 pixels per block iteration; the loop bound is block-uniform so the shuffles below are convergent
+    for (long long base = (long long)blockIdx.x * 32; base < total; base += (long long)gridDim.x * 32) {
+        const long long pix = base + (threadIdx.x >> 3);
+        const bool live = pix < total;
+        const int ow = (int)(pix % a.OW);
+        const int oh = (int)((pix / a.OW) % a.OH);
+        const int n = (int)(pix / ((long long)a.OW * a.OH));
+        float acc[OC];
+#pragma unroll
+        for (int o = 0; o < OC; ++o) acc[o] = 0.f;
+        // transposed: only the taps congruent to (o + pad) mod stride can contribute
+        const int r0 = a.transposed ? (oh + a.pad) % a.stride : 0, s0 = a.transposed ? (ow + a.pad) % a.stride : 0;
+        const int rs = a.transposed ? a.stride : 1;
+        if (live)
+            for (int r = r0; r < a.R; r += rs)
+                for (int s = s0; s < a.S; s += rs) {
+                    int ih, iw;
+                    if (!thin_src(a, oh, ow, r, s, ih, iw)) continue;
+                    const T* src = in + (((long long)n * a.IH + ih) * a.IW + iw) * a.IC;
+                    const T* w = wp + (long long)(r * a.S + s) * a.IC;
+                    for (int c = sub * 8; c < a.IC; c += 64) {
+                        const float4 x0 = ld4<T>(src + c), x1 = ld4<T>(src + c + 4);
+#pragma unroll
+                        for (int o = 0; o < OC; ++o) {
+                            const T* wo = w + (long long)o * a.R * a.S * a.IC + c;
+                            const float4 w0 = ld4<T>(wo), w1 = ld4<T>(wo + 4);
+                            acc[o] += x0.x * w0.x + x0.y * w0.y + x0.z * w0.z + x0.w * w0.w + x1.x * w1.x + x1.y * w1.y +
+                                      x1.z * w1.z + x1.w * w1.w;
+                        }
+                    }
+                }
+#pragma unroll
+        for (int o = 0; o < OC; ++o) {
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 4);
+        }
+        if (live && sub == 0) {
+#pragma unroll
+            for (int o = 0; o < OC; ++o) st<T>(out + pix * OC + o, act_fwd(acc[o] + (bias ? bias[o] : 0.f), a.act));
+        }
+    }
+}
+
+// ---- few INPUT channels (IC <= 8), OC % 8 == 0: one thread = one output pixel x 8 output channels.
+// weights staged in shared memory as fp32 [tap][c][oc]
+template <typename T>
+__global__ void __launch_bounds__(256) thin_in_kernel(ThinArgs a, const T* __restrict__ in, const T* __restrict__ wp,
+                                                      const float* __restrict__ bias, T* __restrict__ out) {
+    extern __shared__ float wsm[];
+    const int RS = a.R * a.S;
+    for (int i = threadIdx.x; i < RS * a.IC * a.OC; i += blockDim.x) {
+        const int oc = i % a.OC, c = (i / a.OC) % a.IC, tap = i / (a.OC * a.IC);
+        wsm[i] = ld<T>(wp + ((long long)oc * RS + tap) * a.IC + c);
+    }
+    __syncthreads();
+    const int groups = a.OC / 8;
+    const long long total = (long long)a.N * a.OH * a.OW * groups;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int og = (int)(idx % groups);
+        const long long pix = idx / groups;
+        const int ow = (int)(pix % a.OW);
+        const int oh = (int)((pix / a.OW) % a.OH);
+        const int n = (int)(pix / ((long long)a.OW * a.OH));
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[og * 8 + j] : 0.f;
+        for (int r = 0; r < a.R; ++r)
+            for (int s = 0; s < a.S; ++s) {
+                int ih, iw;
+                if (!thin_src(a, oh, ow, r, s, ih, iw)) continue;
+                const T* src = in + (((long long)n * a.IH + ih) * a.IW + iw) * a.IC;
+                const float* w = wsm + (long long)(r * a.S + s) * a.IC * a.OC + og * 8;
+                for (int c = 0; c < a.IC; ++c) {
+                    const float x = ld<T>(src + c);
+                    const float4 w0 = *reinterpret_cast<const float4*>(w + c * a.OC);
+                    const float4 w1 = *reinterpret_cast<const float4*>(w + c * a.OC + 4);
+                    acc[0] += x * w0.x; acc[1] += x * w0.y; acc[2] += x * w0.z; acc[3] += x * w0.w;
+                    acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
+                }
+            }
+        T* dst = out + pix * a.OC + og * 8;
+        st4<T>(dst, make_float4(act_fwd(acc[0], a.act), act_fwd(acc[1], a.act), act_fwd(acc[2], a.act), act_fwd(acc[3], a.act)));
+        st4<T>(dst + 4, make_float4(act_fwd(acc[4], a.act), act_fwd(acc[5], a.act), act_fwd(acc[6], a.act), act_fwd(acc[7], a.act)));
+    }
+}
+
+// ---- weight gradient with few channels on the gathered ("big") side: C <= 8, K % 64 == 0.
+// dw[k][c][tap] += sum_pix small[pix][k] * big[src(pix,tap)][c].  Block = 64 channel lanes x 4 pixel lanes;
+// each thread keeps its R*R*C accumulators in registers (filter size and C are template parameters).
+template <typename T, int RR, int CC>
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(vs_conv_geom g, const T* __restrict__ small_, const T* __restrict__ big,
+                                                         float* __restrict__ dw, long long rows_per_block) {
+    __shared__ float red[4][64];
+    const int kl = threadIdx.x & 63, pl = threadIdx.x >> 6;
+    const int k = blockIdx.y * 64 + kl;
+    const long long M = (long long)g.N * g.P * g.Q;
+    const long long m0 = (long long)blockIdx.x * rows_per_block;
+    const long long m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+    float acc[RR * RR * CC];
+#pragma unroll
+    for (int i = 0; i < RR * RR * CC; ++i) acc[i] = 0.f;
+    for (long long m = m0 + pl; m < m1; m += 4) {
+        const float v = ld<T>(small_ + m * g.K + k);
+        const int n = (int)(m / ((long long)g.P * g.Q));
+        const int rem = (int)(m - (long long)n * g.P * g.Q);
+        const int ph = rem / g.Q, pw = rem % g.Q;
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            const int ih = ph * g.stride - g.pad + r;
+#pragma unroll
+            for (int s = 0; s < RR; ++s) {
+                const int iw = pw * g.stride - g.pad + s;
+                const bool ok = ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+                const T* src = big + (((long long)n * g.H + ih) * g.W + iw) * CC;
+#pragma unroll
+                for (int c = 0; c < CC; ++c)
+                    if (ok) acc[(r * RR + s) * CC + c] = fmaf(v, ld<T>(src + c), acc[(r * RR + s) * CC + c]);
+            }
+        }
+    }
+    // reduce the 4 pixel lanes through shared memory, then one atomic per (k, c, tap)
+#pragma unroll
+    for (int i = 0; i < RR * RR * CC; ++i) {
+        __syncthreads();
+        red[pl][kl] = acc[i];
+        __syncthreads();
+        if (pl == 0) {
+            const float t = red[0][kl] + red[1][kl] + red[2][kl] + red[3][kl];
+            atomicAdd(&dw[((long long)k * CC + (i % CC)) * (RR * RR) + i / CC], t);
+        }
+    }
+}
+
+template <typename T>
+__global__ void colstats_any_kernel(const T* __restrict__ y, int C, long long rpg, int chunks, double* __restrict__ stats) {
+    __shared__ double r1[8][33], r2[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int g = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
+    const long long per = (rpg + chunks - 1) / chunks;
+    const long long r0 = (long long)g * rpg + (long long)chunk * per;
+    long long r_end = r0 + per;
+    if (r_end > (long long)(g + 1) * rpg) r_end = (long long)(g + 1) * rpg;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < C)
+        for (long long r = r0 + threadIdx.y; r < r_end; r += 8) {
+            const float v = ld<T>(y + r * C + c);
+            s1 += v; s2 += (double)v * v;
+        }
+    r1[threadIdx.y][threadIdx.x] = s1; r2[threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t1 += r1[k][threadIdx.x]; t2 += r2[k][threadIdx.x]; }
+        atomicAdd(&stats[((long long)g * C + c) * 2], t1);
+        atomicAdd(&stats[((long long)g * C + c) * 2 + 1], t2);
+    }
+}
+
+int stats_of_output(const vs_conv_geom* g, int dtype, const void* out, long long rows, int OC, double* stats,
+                           cudaStream_t stream) {
+    const long long rpg = rows / g->groups;
+    const int cx = (int)cdiv(OC, 32);
+    long long chunks = cdiv(4LL * num_sms(), (long long)cx * g->groups);
+    if (chunks > cdiv(rpg, 64)) chunks = cdiv(rpg, 64);
+    if (chunks < 1) chunks = 1;
+    dim3 grid(cx, (unsigned)(g->groups * chunks)), block(32, 8);
+    VS_DISPATCH_DTYPE(dtype, T, (colstats_any_kernel<T><<<grid, block, 0, stream>>>((const T*)out, OC, rpg, (int)chunks, stats)));
+    return launched("colstats_any_kernel");
+}
+
+// returns 0 = done, -1 = not a thin geometry, >0 error
+int conv_forward_thin(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
+                      double* stats, cudaStream_t stream) {
+    ThinArgs a;
+    a.N = g->N; a.R = g->R; a.S = g->S; a.stride = g->stride; a.pad = g->pad; a.act = g->act;
+    a.transposed = mode == VS_CONV_TRANSPOSED;
+    if (!a.transposed) { a.IH = g->H; a.IW = g->W; a.IC = g->C; a.OH = g->P; a.OW = g->Q; a.OC = g->K; }
+    else { a.IH = g->P; a.IW = g->Q; a.IC = g->K; a.OH = g->H; a.OW = g->W; a.OC = g->C; }
+    const long long pixels = (long long)a.N * a.OH * a.OW;
+    // kernel selection must not depend on the batch size: per-sample results have to be bit-identical
+    // whatever else is in the batch, so the threshold is on the per-sample pixel count
+    if (a.OH * a.OW < 256) return -1;
+    int rc;
+    if (a.OC <= 4 && a.IC % 64 == 0) {
+        long long blocks = cdiv(pixels * 8, 256);
+        if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+        VS_DISPATCH_DTYPE(g->dtype, T, {
+            switch (a.OC) {
+                case 1: thin_out_kernel<T, 1><<<(unsigned)blocks, 256, 0, stream>>>(a, (const T*)in, (const T*)wp, bias, (T*)out); break;
+                case 2: thin_out_kernel<T, 2><<<(unsigned)blocks, 256, 0, stream>>>(a, (const T*)in, (const T*)wp, bias, (T*)out); break;
+                case 3: thin_out_kernel<T, 3><<<(unsigned)blocks, 256, 0, stream>>>(a, (const T*)in, (const T*)wp, bias, (T*)out); break;
+                default: thin_out_kernel<T, 4><<<(unsigned)blocks, 256, 0, stream>>>(a, (const T*)in, (const T*)wp, bias, (T*)out); break;
+            }
+        });
+        rc = launched("thin_out_kernel");
+    } else if (a.IC <= 8 && a.OC % 8 == 0 && (long long)a.R * a.S * a.IC * a.OC * 4 <= 96 * 1024) {
+        const int smem = a.R * a.S * a.IC * a.OC * 4;
+        long long blocks = cdiv(pixels * (a.OC / 8), 256);
+        if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+        VS_DISPATCH_DTYPE(g->dtype, T, {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(thin_in_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            thin_in_kernel<T><<<(unsigned)blocks, 256, smem, stream>>>(a, (const T*)in, (const T*)wp, bias, (T*)out);
+        });
+        rc = launched("thin_in_kernel");
+    } else {
+        return -1;
+    }
+    if (rc) return rc;
+    if (stats != nullptr) rc = stats_of_output(g, g->dtype, out, pixels, a.OC, stats, stream);
+    return rc;
+}
+
+template <typename T, int RR>
+static bool launch_thin_wgrad_c(const vs_conv_geom* g, dim3 grid, const T* small_, const T* big, float* dw, long long rpb,
+                                cudaStream_t stream) {
+    switch (g->C) {
+        case 1: thin_wgrad_kernel<T, RR, 1><<<grid, 256, 0, stream>>>(*g, small_, big, dw, rpb); return true;
+        case 2: thin_wgrad_kernel<T, RR, 2><<<grid, 256, 0, stream>>>(*g, small_, big, dw, rpb); return true;
+        case 3: thin_wgrad_kernel<T, RR, 3><<<grid, 256, 0, stream>>>(*g, small_, big, dw, rpb); return true;
+        case 4: thin_wgrad_kernel<T, RR, 4><<<grid, 256, 0, stream>>>(*g, small_, big, dw, rpb); return true;
+        case 5: thin_wgrad_kernel<T, RR, 5><<<grid, 256, 0, stream>>>(*g, small_, big, dw, rpb); return true;
+        default: return false;
+    }
+}
+
+int conv_wgrad_thin(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream) {
+    const long long M = (long long)g->N * g->P * g->Q;
+    if (g->C > 5 || g->K % 64 != 0 || g->R != g->S || (g->R != 3 && g->R != 4) || g->P * g->Q < 256) return -1;
+    long long blocks = 8LL * num_sms() / (g->K / 64);
+    if (blocks > cdiv(M, 256)) blocks = cdiv(M, 256);
+    if (blocks < 1) blocks = 1;
+    const long long rpb = cdiv(cdiv(M, blocks), 4) * 4;
+    dim3 grid((unsigned)cdiv(M, rpb), (unsigned)(g->K / 64));
+    bool ok = false;
+    VS_DISPATCH_DTYPE(g->dtype, T, {
+        ok = g->R == 3 ? launch_thin_wgrad_c<T, 3>(g, grid, (const T*)small_, (const T*)big, dw, rpb, stream)
+                       : launch_thin_wgrad_c<T, 4>(g, grid, (const T*)small_, (const T*)big, dw, rpb, stream);
+    });
+    if (!ok) return -1;
+    return launched("thin_wgrad_kernel");
+}
+
+}  // namespace vs

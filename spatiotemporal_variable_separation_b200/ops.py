@@ -163,7 +163,11 @@ class ConvBlockFn(torch.autograd.Function):
             L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dw[0]), L.stream())
         if p_bias is not None and ctx.needs_input_grad[2]:
             db = _grad_buffer(p_bias)
-            L.call('vs_colsum', ptr(dy), L.dtype_code(dy), rows, OC, ptr(db[0]), L.stream())
+            if not (cfg.has_bn and cfg.training):
+                L.call('vs_colsum', ptr(dy), L.dtype_code(dy), rows, OC, ptr(db[0]), L.stream())
+            # else: BatchNorm's backward returns a dy whose per-(group, channel) sum is exactly zero, so the
+            # bias gradient is mathematically 0 (the reference computes rounding noise there);
+            # the (zero-initialised) buffer is left untouched instead of streaming dy once more.
         return (dx, dw[1] if dw else None, db[1] if db else None, dgamma[1] if dgamma else None,
                 dbeta[1] if dbeta else None,
                 None, None, None, None)

@@ -52,7 +52,7 @@ def ae_loss(cond, target, sep_net, nt_cond, offset, skipco, t_random=None):
 
 
 def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, lamb_s, lamb_t, lamb_pred,
-                average_tloss=False, t_random=None):
+                average_tloss=False, t_random=None, reducer=None):
     """One forward pass of the training objective.  ``full_data`` = cat(cond, target) [B,L,C,H,W] fp32.
 
     Returns dict(total, ae, s, pred, t, forecasts, t_codes); ``total.backward()`` then produces every
@@ -73,6 +73,10 @@ def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, l
     else:
         s_old, s_new, skip_old, skip_new = s_both[:B], s_both[B:], None, None
     t_rand, t_cond = t_both[:B], t_both[B:]
+    if reducer is not None:
+        # gradient buckets leave as soon as autograd is done with the networks downstream of these codes:
+        # dL/dt_both exists once the decoder AND the stepper have been back-propagated through
+        reducer.after(t_both, ('decoder', 't_resnet'))
     # ---- rollout + AE reconstruction and all forecasts in one grouped decode
     forecasts, t_codes, _, _, recon = sep_net.forecast_internal(s_old, skip_old, t_cond, nt_pred + offset, B,
                                                                 extra_t=t_rand)

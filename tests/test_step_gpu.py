@@ -54,7 +54,7 @@ def test_step_matches_reference_golden(name):
     check_against_golden(g, out, grads)
 
 
-@pytest.mark.parametrize('name', ['mnist-small', 'wave-small', 'mnist-small-skipco', 'chairs-small'])
+@pytest.mark.parametrize('name', ['mnist-small', 'wave-small', 'mnist-small-skipco', 'mnist-small-mul'])
 def test_two_fused_adam_steps_match_reference_train_loop(name):
     g = harness.load_golden(name)
     cfg = g['cfg']
