@@ -177,6 +177,24 @@ int vs_loss_combine(const double* acc, const double* coef_host, const double* la
 int vs_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
                  float beta2, float eps, float grad_scale, int32_t step_host, const int32_t* step_dev, void* stream);
 
+/* ---- latent rollout ------------------------------------------------------------------------
+ * replaces: the loop of model.py:78-83 over MLPResnet.forward (resnet.py:42-50, mlp.py:66-71):
+ * per time step and block  x <- x + L3(relu(L2(relu(L1 x)))),  one launch for the whole rollout (each CTA owns
+ * a few batch rows for all T-1 steps).  fp32 throughout.
+ * codes [T][B][d]: codes[0] given, codes[1..] written.  w_host: HOST array of 6*n_blocks device pointers
+ * {W1[h][d], b1[h], W2[h][h], b2[h], W3[d][h], b3[d]} per block (torch nn.Linear layout).
+ * Saved for backprop-through-time (each may be NULL when no backward follows):
+ *   hidden [n_blocks][2][T-1][B][h]  post-ReLU activations of L1 and L2,
+ *   xin    [n_blocks][T-1][B][d]     input of every block,   res [n_blocks][T-1][B][d]  its residual. */
+int vs_latent_rollout_forward(float* codes, const float* const* w_host, int32_t T, int32_t B, int32_t d, int32_t h,
+                              int32_t n_blocks, float* hidden, float* xin, float* res, void* stream);
+/* Adjoint recurrence.  dcodes [T][B][d] holds dL/dcodes[t] (from the decoder / losses) on entry; on exit
+ * dcodes[0] is the gradient w.r.t. the initial code.  Emits the pre-activation gradients needed for the
+ * weight gradients, which are then (T-1)*B-row GEMMs (vs_conv_wgrad / vs_colsum):
+ *   dres [n_blocks][T-1][B][d] = dL/d(residual),  dhidden [n_blocks][2][T-1][B][h] = dL/d(pre-ReLU of L1, L2). */
+int vs_latent_rollout_backward(float* dcodes, const float* const* w_host, int32_t T, int32_t B, int32_t d, int32_t h,
+                               int32_t n_blocks, const float* hidden, float* dres, float* dhidden, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

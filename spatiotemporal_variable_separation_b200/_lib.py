@@ -27,6 +27,7 @@ class Geom(C.Structure):
 _p, _i32, _i64, _f, _d = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 _PG = C.POINTER(Geom)
 _PD = C.POINTER(C.c_double)
+_PP = C.POINTER(C.c_void_p)
 
 # name -> argtypes (all return int status unless listed in _RET)
 SIGNATURES = {
@@ -59,6 +60,8 @@ SIGNATURES = {
     'vs_sqdiff_backward': [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _f, _p, _p, _f, _p, _i32, _p],
     'vs_loss_combine': [_p, _PD, _PD, _i32, _p, _p],
     'vs_adam_step': [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i32, _p, _p],
+    'vs_latent_rollout_forward': [_p, _PP, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p],
+    'vs_latent_rollout_backward': [_p, _PP, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p],
 }
 _RET = {'vs_last_error': C.c_char_p, 'vs_launch_count': C.c_int64}
 
@@ -97,6 +100,11 @@ def launch_count():
 
 def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pointer_array(tensors):
+    """Host array of device pointers (for entry points that take `const float* const*`)."""
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
 def ptr(t):

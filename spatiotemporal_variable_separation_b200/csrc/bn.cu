@@ -158,6 +158,184 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int G, int
     if (dgamma) dgamma[c] += (float)s2;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path ("column-stationary"): every thread owns 16 bytes of channels (8 bf16 / 4 fp32) for the whole
+// kernel, keeps that channel slice's statistics and affine parameters in registers and walks down the
+// rows of one (group, row-chunk): no integer division and no parameter reload in the streaming loop,
+// 16-byte coalesced accesses.  Eligible when C*sizeof(T)/16 divides 256.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+    static constexpr int W = 4;
+    static __device__ __forceinline__ void load(const float* p, float* v) {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec<__nv_bfloat16> {
+    static constexpr int W = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&b);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+struct ColPlan {
+    int tpr;             // threads per row = C / W
+    int rows_per_iter;   // 256 / tpr
+    int chunks;          // row chunks per group
+    long long rpg, per;  // rows per group, rows per chunk
+};
+
+template <typename T>
+static bool col_plan(long long rows, int C, int G, ColPlan& pl, int blocks_per_sm = 8) {
+    constexpr int W = Vec<T>::W;
+    if (C % W != 0) return false;
+    pl.tpr = C / W;
+    if (pl.tpr > 256 || 256 % pl.tpr != 0) return false;
+    pl.rows_per_iter = 256 / pl.tpr;
+    pl.rpg = rows / G;
+    long long chunks = cdiv((long long)blocks_per_sm * num_sms(), G);
+    const long long max_chunks = cdiv(pl.rpg, 4LL * pl.rows_per_iter);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    pl.per = cdiv(cdiv(pl.rpg, chunks), pl.rows_per_iter) * pl.rows_per_iter;
+    pl.chunks = (int)cdiv(pl.rpg, pl.per);
+    return (long long)G * pl.chunks <= 2147483647LL;
+}
+
+#define VS_COL_SETUP                                                                      \
+    constexpr int W = Vec<T>::W;                                                          \
+    const int c = (threadIdx.x % pl.tpr) * W, rl = threadIdx.x / pl.tpr;                  \
+    const int g = blockIdx.x / pl.chunks, chunk = blockIdx.x % pl.chunks;                 \
+    const long long r0 = (long long)g * pl.rpg + (long long)chunk * pl.per;               \
+    long long r1 = r0 + pl.per;                                                           \
+    if (r1 > (long long)(g + 1) * pl.rpg) r1 = (long long)(g + 1) * pl.rpg;
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_fwd_col_kernel(const T* __restrict__ y, T* __restrict__ out, int C, ColPlan pl,
+                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int act) {
+    VS_COL_SETUP
+    float mu[W], is[W], ga[W], be[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
+    for (long long r = r0 + rl; r < r1; r += pl.rows_per_iter) {
+        float v[W];
+        Vec<T>::load(y + r * C + c, v);
+#pragma unroll
+        for (int k = 0; k < W; ++k) v[k] = act_fwd(ga[k] * ((v[k] - mu[k]) * is[k]) + be[k], act);
+        Vec<T>::store(out + r * C + c, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_col_kernel(const T* __restrict__ dout, const T* __restrict__ y, T* __restrict__ dy,
+                                                               int C, ColPlan pl, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int act,
+                                                               const double* __restrict__ sums, int train) {
+    VS_COL_SETUP
+    float mu[W], is[W], ga[W], be[W], m1[W], m2[W];
+    const float inv_count = 1.f / (float)pl.rpg;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k];
+        m1[k] = train ? (float)sums[((long long)g * C + c + k) * 2] * inv_count : 0.f;
+        m2[k] = train ? (float)sums[((long long)g * C + c + k) * 2 + 1] * inv_count : 0.f;
+    }
+    for (long long r = r0 + rl; r < r1; r += pl.rows_per_iter) {
+        float v[W], d[W];
+        Vec<T>::load(y + r * C + c, v);
+        Vec<T>::load(dout + r * C + c, d);
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const float xh = (v[k] - mu[k]) * is[k];
+            const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
+            d[k] = ga[k] * is[k] * (dz - m1[k] - xh * m2[k]);
+        }
+        Vec<T>::store(dy + r * C + c, d);
+    }
+}
+
+// MODE 0: BatchNorm backward sums {sum dz, sum dz*xhat};  MODE 1: forward statistics {sum y, sum y^2}
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict__ dout, const T* __restrict__ y, int C, ColPlan pl,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                                            double* __restrict__ sums) {
+    VS_COL_SETUP
+    __shared__ float red[2][256 * 8];
+    float mu[W], is[W], ga[W], be[W], s1[W], s2[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        s1[k] = 0.f; s2[k] = 0.f;
+        if (MODE == 0) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
+    }
+    for (long long r = r0 + rl; r < r1; r += pl.rows_per_iter) {
+        float v[W], d[W];
+        Vec<T>::load(y + r * C + c, v);
+        if (MODE == 0) {
+            Vec<T>::load(dout + r * C + c, d);
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                const float xh = (v[k] - mu[k]) * is[k];
+                const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
+                s1[k] += dz; s2[k] += dz * xh;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < W; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
+        }
+    }
+    // reduce the row lanes of the block (threads with equal threadIdx.x % tpr), then fp64 atomics
+#pragma unroll
+    for (int k = 0; k < W; ++k) { red[0][threadIdx.x * W + k] = s1[k]; red[1][threadIdx.x * W + k] = s2[k]; }
+    __syncthreads();
+    if (rl == 0) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            double t1 = 0.0, t2 = 0.0;
+            for (int j = 0; j < pl.rows_per_iter; ++j) {
+                t1 += (double)red[0][(j * pl.tpr + threadIdx.x) * W + k];
+                t2 += (double)red[1][(j * pl.tpr + threadIdx.x) * W + k];
+            }
+            atomicAdd(&sums[((long long)g * C + c + k) * 2], t1);
+            atomicAdd(&sums[((long long)g * C + c + k) * 2 + 1], t2);
+        }
+    }
+}
+
+// per-(group, channel) sum / sum of squares of a stored [rows, C] tensor (second-pass BatchNorm statistics of
+// the tensor-core and thin convolution paths)
+int column_stats(const void* y, int dtype, long long rows, int C, int G, double* stats, cudaStream_t stream) {
+    VS_DISPATCH_DTYPE(dtype, T, {
+        ColPlan pl;
+        if (!col_plan<T>(rows, C, G, pl, 2)) return -1;
+        bn_reduce_col_kernel<T, 1><<<(unsigned)(G * pl.chunks), 256, 0, stream>>>(nullptr, (const T*)y, C, pl, nullptr, nullptr,
+                                                                                   nullptr, nullptr, 0, stats);
+    });
+    return launched("bn_reduce_col_kernel");
+}
+
 static int ew_blocks(long long work) {
     long long b = cdiv(work, 256);
     const long long cap = 8LL * num_sms();
@@ -191,6 +369,13 @@ extern "C" int vs_bn_act_forward(const void* y, void* out, int32_t dtype, int64_
     VS_REQUIRE(G >= 1 && rows % G == 0, "bn_act_forward: rows %lld not divisible by groups %d", (long long)rows, G);
     if (rows == 0) return 0;
     const long long rpg = rows / G;
+    VS_DISPATCH_DTYPE(dtype, T, {
+        ColPlan pl;
+        if (col_plan<T>(rows, C, G, pl)) {
+            bn_act_fwd_col_kernel<T><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)y, (T*)out, C, pl, mean, invstd, gamma, beta, act);
+            return launched("bn_act_fwd_col_kernel");
+        }
+    });
     const bool vec = (C % 4) == 0;
     const int blocks = ew_blocks(rows * C / (vec ? 4 : 1));
     VS_DISPATCH_DTYPE(dtype, T, {
@@ -206,6 +391,13 @@ extern "C" int vs_bn_act_backward_reduce(const void* dout, const void* y, int32_
     VS_REQUIRE(G >= 1 && rows % G == 0, "bn_act_backward_reduce: rows not divisible by groups");
     if (rows == 0) return 0;
     const long long rpg = rows / G;
+    VS_DISPATCH_DTYPE(dtype, T, {
+        ColPlan pl;
+        if (col_plan<T>(rows, C, G, pl, 2)) {
+            bn_reduce_col_kernel<T, 0><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, C, pl, mean, invstd, gamma, beta, act, sums);
+            return launched("bn_reduce_col_kernel");
+        }
+    });
     const int cx = (int)cdiv(C, 32);
     long long chunks = cdiv(4LL * num_sms(), (long long)cx * G);
     if (chunks > cdiv(rpg, 64)) chunks = cdiv(rpg, 64);
@@ -224,9 +416,17 @@ extern "C" int vs_bn_act_backward_apply(const void* dout, const void* y, void* d
     VS_REQUIRE(G >= 1 && rows % G == 0, "bn_act_backward_apply: rows not divisible by groups");
     if (rows == 0) return 0;
     const long long rpg = rows / G;
+    bool done = false;
+    VS_DISPATCH_DTYPE(dtype, T, {
+        ColPlan pl;
+        if (col_plan<T>(rows, C, G, pl)) {
+            bn_bwd_apply_col_kernel<T><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, C, pl, mean, invstd, gamma, beta, act, sums, train);
+            done = true;
+        }
+    });
     const bool vec = (C % 4) == 0;
     const int blocks = ew_blocks(rows * C / (vec ? 4 : 1));
-    VS_DISPATCH_DTYPE(dtype, T, {
+    if (!done) VS_DISPATCH_DTYPE(dtype, T, {
         if (vec) bn_bwd_apply_kernel<T, true><<<blocks, 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, rows, C, rpg, mean, invstd, gamma, beta, act, sums, train);
         else bn_bwd_apply_kernel<T, false><<<blocks, 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, rows, C, rpg, mean, invstd, gamma, beta, act, sums, train);
     });

@@ -25,7 +25,7 @@ struct TcParams {
     int N, OH, OW, OC;
     int OHc, OWc, ost;        // class grid (output pixels of one parity class) and output sub-sampling
     int WT, HT, NT;           // tile box in class-grid units, WT*HT*NT == 128
-    int tiles_w, tiles_h, tiles_n;
+    int tiles_w, tiles_h, tiles_n, n_tiles, classes, total_tiles;
     int IC, kchunks, ntaps;
     int in_sh, in_sw;         // class-grid -> input coordinate multiplier
     int act, has_bias, partial;
@@ -115,8 +115,19 @@ struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+
+// Persistent: every CTA walks a strided list of (pixel tile, output-channel tile, parity class) work items.
+// The TMA producer and the MMA issuer run ahead across tile boundaries (one smem ring for the whole kernel);
+// two TMEM accumulator stages let tile i+1's MMAs overlap tile i's epilogue.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__ CUtensorMap map_a,
                                                          const __grid_constant__ CUtensorMap map_b,
@@ -128,115 +139,145 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
-    uint64_t* tmem_full = bars + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint64_t* tmem_full = bars + 2 * STAGES;        // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cls = blockIdx.z;
-    const int n0 = blockIdx.y * BN;
-    int t = blockIdx.x;
-    const int tw = t % p.tiles_w; t /= p.tiles_w;
-    const int th = t % p.tiles_h;
-    const int tn = t / p.tiles_h;
-    const int j0 = tw * p.WT, i0 = th * p.HT, b0 = tn * p.NT;
     const int nkb = p.ntaps * p.kchunks;
+    const int total = p.total_tiles;
 
     if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // work item -> (class, output-channel tile, pixel tile); the class index is fastest so that the CTAs running
+    // at the same time read the same input pixels (L2 hits), then the channel tile, then the pixel tile
+#define VS_TC_DECODE(idx)                                                   \
+    const int cls = (idx) % p.classes;                                      \
+    const int rest_ = (idx) / p.classes;                                    \
+    const int n0 = (rest_ % p.n_tiles) * BN;                                \
+    int t_ = rest_ / p.n_tiles;                                             \
+    const int tw = t_ % p.tiles_w; t_ /= p.tiles_w;                         \
+    const int th = t_ % p.tiles_h;                                          \
+    const int tn = t_ / p.tiles_h;                                          \
+    const int j0 = tw * p.WT, i0 = th * p.HT, b0 = tn * p.NT;
+
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
-                uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-                uint8_t* b_dst = a_dst + S::A_BYTES;
-                mbar_expect_tx(&full[s], S::STAGE_BYTES);
-                tma_load_4d(a_dst, &map_a, &full[s], kc * TC_BK, j0 * p.in_sw + p.dw[cls][tap], i0 * p.in_sh + p.dh[cls][tap], b0);
-                tma_load_2d(b_dst, &map_b, &full[s], p.wtap[cls][tap] * p.IC + kc * TC_BK, n0);
+            int it = 0;
+            for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+                VS_TC_DECODE(idx)
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+                    uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + S::A_BYTES;
+                    mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                    tma_load_4d(a_dst, &map_a, &full[s], kc * TC_BK, j0 * p.in_sw + p.dw[cls][tap], i0 * p.in_sh + p.dh[cls][tap], b0);
+                    tma_load_2d(b_dst, &map_b, &full[s], p.wtap[cls][tap] * p.IC + kc * TC_BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_bf16_f32(BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            int it = 0, lt = 0;
+            for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-                const uint32_t b_addr = a_addr + S::A_BYTES;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + S::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                    umma_bf16(tmem_base, kmajor_sw128_desc(a_addr + k * 32), kmajor_sw128_desc(b_addr + k * 32), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        umma_bf16(tmem_d, kmajor_sw128_desc(a_addr + k * 32), kmajor_sw128_desc(b_addr + k * 32), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);          // smem slot reusable once these MMAs have read it
                 }
-                umma_commit(&empty[s]);          // smem slot reusable once these MMAs have read it
+                umma_commit(&tmem_full[acc]);        // accumulator of this tile complete
             }
-            umma_commit(tmem_full);              // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
         const int m = q * 32 + lane;             // tile-local pixel (TMEM lane)
         const int w = m % p.WT, h = (m / p.WT) % p.HT, n = m / (p.WT * p.HT);
-        const int i = i0 + h, j = j0 + w, nn = b0 + n;
-        const bool ok = i < p.OHc && j < p.OWc && nn < p.N;
-        const long long pix = ((long long)nn * p.OH + (long long)i * p.ost + p.ca[cls]) * p.OW + (long long)j * p.ost + p.cb[cls];
-        __nv_bfloat16* dst = out + pix * p.OC + n0;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
+        int lt = 0;
+        for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+            VS_TC_DECODE(idx)
+            const int acc = lt & 1;
+            const int i = i0 + h, j = j0 + w, nn = b0 + n;
+            const bool ok = i < p.OHc && j < p.OWc && nn < p.N;
+            const long long pix = ((long long)nn * p.OH + (long long)i * p.ost + p.ca[cls]) * p.OW + (long long)j * p.ost + p.cb[cls];
+            __nv_bfloat16* dst = out + pix * p.OC + n0;
+            mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (ok && p.partial) {
-                // OC not a multiple of the tile or rows not 16-byte aligned: predicated scalar stores
-                for (int c = 0; c < 32; ++c) {
-                    const int oc = n0 + c0 + c;
-                    if (oc < p.OC) {
-                        float x = __uint_as_float(r[c]);
-                        if (p.has_bias) x += __ldg(bias + oc);
-                        dst[c0 + c] = __float2bfloat16_rn(act_fwd(x, p.act));
-                    }
-                }
-            } else if (ok) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                if (ok && p.partial) {
+                    // OC not a multiple of the tile or rows not 16-byte aligned: predicated scalar stores
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int c = v * 8 + e * 2;
-                        float x0 = __uint_as_float(r[c]), x1 = __uint_as_float(r[c + 1]);
-                        if (p.has_bias) { x0 += __ldg(bias + n0 + c0 + c); x1 += __ldg(bias + n0 + c0 + c + 1); }
-                        x0 = act_fwd(x0, p.act);
-                        x1 = act_fwd(x1, p.act);
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
-                        pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                    for (int c = 0; c < 32; ++c) {
+                        const int oc = n0 + c0 + c;
+                        if (oc < p.OC) {
+                            float x = __uint_as_float(r[c]);
+                            if (p.has_bias) x += __ldg(bias + oc);
+                            dst[c0 + c] = __float2bfloat16_rn(act_fwd(x, p.act));
+                        }
                     }
-                    *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                } else if (ok) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = v * 8 + e * 2;
+                            float x0 = __uint_as_float(r[c]), x1 = __uint_as_float(r[c + 1]);
+                            if (p.has_bias) { x0 += __ldg(bias + n0 + c0 + c); x1 += __ldg(bias + n0 + c0 + c + 1); }
+                            x0 = act_fwd(x0, p.act);
+                            x1 = act_fwd(x1, p.act);
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
+                            pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                        }
+                        *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
                 }
             }
+            // this warp's quarter of the accumulator has been read: hand the stage back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem_base);
+        tmem_dealloc<2 * BN>(tmem_base);
     }
+#undef VS_TC_DECODE
 }
 
 // per-(group, channel) sum / sum of squares of a bf16 [rows, C] matrix (BatchNorm batch statistics of
@@ -311,8 +352,13 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
         if (e != cudaSuccess) return fail("tc_conv_kernel smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)cdiv(p.OC, BN), (unsigned)classes);
-    tc_conv_kernel<BN, STAGES><<<grid, 192, S::TOTAL, stream>>>(ma, mb, p, bias, (__nv_bfloat16*)out);
+    TcParams q = p;
+    q.classes = classes;
+    q.n_tiles = (int)cdiv(p.OC, BN);
+    q.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * q.n_tiles * classes;
+    const int resident = 2 * num_sms();                     // __launch_bounds__(192, 2)
+    const int grid = q.total_tiles < resident ? q.total_tiles : resident;
+    tc_conv_kernel<BN, STAGES><<<grid, 192, S::TOTAL, stream>>>(ma, mb, q, bias, (__nv_bfloat16*)out);
     return launched("tc_conv_kernel");
 }
 
@@ -391,7 +437,7 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     int rc = BN == 128 ? launch_tc<128, 3>(ma, mb, p, bias, out, classes, stream)
                        : launch_tc<64, 4>(ma, mb, p, bias, out, classes, stream);
     if (rc) return rc;
-    if (stats != nullptr && OC % 64 != 0) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
+    if (stats != nullptr) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
     if (stats != nullptr) {
         const long long rows = (long long)g->N * OH * OW, rpg = rows / g->groups;
         const int cx = (int)cdiv(OC, 64);

@@ -86,14 +86,14 @@ __global__ void __launch_bounds__(256) thin_in_kernel(ThinArgs a, const T* __res
         wsm[i] = ld<T>(wp + ((long long)oc * RS + tap) * a.IC + c);
     }
     __syncthreads();
-    const int groups = a.OC / 8;
-    const long long total = (long long)a.N * a.OH * a.OW * groups;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const unsigned groups = a.OC / 8;
+    const unsigned total = (unsigned)a.N * a.OH * a.OW * groups;      // < 2^32, checked by the launcher
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int og = (int)(idx % groups);
-        const long long pix = idx / groups;
+        const unsigned pix = idx / groups;
         const int ow = (int)(pix % a.OW);
         const int oh = (int)((pix / a.OW) % a.OH);
-        const int n = (int)(pix / ((long long)a.OW * a.OH));
+        const int n = (int)(pix / ((unsigned)a.OW * a.OH));
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[og * 8 + j] : 0.f;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) thin_in_kernel(ThinArgs a, const T* __res
                     acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
                 }
             }
-        T* dst = out + pix * a.OC + og * 8;
+        T* dst = out + (long long)pix * a.OC + og * 8;
         st4<T>(dst, make_float4(act_fwd(acc[0], a.act), act_fwd(acc[1], a.act), act_fwd(acc[2], a.act), act_fwd(acc[3], a.act)));
         st4<T>(dst + 4, make_float4(act_fwd(acc[4], a.act), act_fwd(acc[5], a.act), act_fwd(acc[6], a.act), act_fwd(acc[7], a.act)));
     }
@@ -132,10 +132,12 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(vs_conv_geom g, const T
     float acc[RR * RR * CC];
 #pragma unroll
     for (int i = 0; i < RR * RR * CC; ++i) acc[i] = 0.f;
+    const unsigned PQ = (unsigned)g.P * g.Q;
     for (long long m = m0 + pl; m < m1; m += 4) {
         const float v = ld<T>(small_ + m * g.K + k);
-        const int n = (int)(m / ((long long)g.P * g.Q));
-        const int rem = (int)(m - (long long)n * g.P * g.Q);
+        const unsigned mu = (unsigned)m;                     // M < 2^32, checked by the launcher
+        const int n = (int)(mu / PQ);
+        const int rem = (int)(mu - (unsigned)n * PQ);
         const int ph = rem / g.Q, pw = rem % g.Q;
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
@@ -190,8 +192,12 @@ __global__ void colstats_any_kernel(const T* __restrict__ y, int C, long long rp
     }
 }
 
+int column_stats(const void* y, int dtype, long long rows, int C, int G, double* stats, cudaStream_t stream);   // bn.cu
+
 int stats_of_output(const vs_conv_geom* g, int dtype, const void* out, long long rows, int OC, double* stats,
                            cudaStream_t stream) {
+    const int fast = column_stats(out, dtype, rows, OC, g->groups, stats, stream);
+    if (fast >= 0) return fast;
     const long long rpg = rows / g->groups;
     const int cx = (int)cdiv(OC, 32);
     long long chunks = cdiv(4LL * num_sms(), (long long)cx * g->groups);
@@ -227,7 +233,8 @@ int conv_forward_thin(const vs_conv_geom* g, int mode, const void* in, const voi
             }
         });
         rc = launched("thin_out_kernel");
-    } else if (a.IC <= 8 && a.OC % 8 == 0 && (long long)a.R * a.S * a.IC * a.OC * 4 <= 96 * 1024) {
+    } else if (a.IC <= 8 && a.OC % 8 == 0 && (long long)a.R * a.S * a.IC * a.OC * 4 <= 96 * 1024 &&
+               pixels * (a.OC / 8) < 4000000000LL) {
         const int smem = a.R * a.S * a.IC * a.OC * 4;
         long long blocks = cdiv(pixels * (a.OC / 8), 256);
         if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
@@ -259,7 +266,7 @@ static bool launch_thin_wgrad_c(const vs_conv_geom* g, dim3 grid, const T* small
 
 int conv_wgrad_thin(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream) {
     const long long M = (long long)g->N * g->P * g->Q;
-    if (g->C > 5 || g->K % 64 != 0 || g->R != g->S || (g->R != 3 && g->R != 4) || g->P * g->Q < 256) return -1;
+    if (g->C > 5 || g->K % 64 != 0 || g->R != g->S || (g->R != 3 && g->R != 4) || g->P * g->Q < 256 || M >= 4000000000LL) return -1;
     long long blocks = 8LL * num_sms() / (g->K / 64);
     if (blocks > cdiv(M, 256)) blocks = cdiv(M, 256);
     if (blocks < 1) blocks = 1;

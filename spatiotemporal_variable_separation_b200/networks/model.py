@@ -11,6 +11,7 @@ import torch.nn as nn
 
 from .. import ops
 from .mlp_encdec import MLPEncoder
+from .resnet import MLPResnet
 
 
 class SeparableNetwork(nn.Module):
@@ -55,14 +56,27 @@ class SeparableNetwork(nn.Module):
             ops.frames_window(frames, t0, nt, out, g * B)
         return out
 
-    def rollout(self, t_code, n_forecast):
-        """model.py:78-83 without the decoder: -> (list of n_forecast codes, residual lists)."""
-        codes, residuals = [t_code], []
+    def rollout(self, t_int, n_forecast):
+        """model.py:78-83 without the decoder.  Returns (t_all, t_codes, t_residuals):
+        t_all       internal codes of all n_forecast steps stacked along the batch (step-major) for ONE grouped decode,
+        t_codes     the reference's [B, T, ...] fp32 tensor,
+        t_residuals list over steps of lists over blocks (reference layout).
+        The MLP stepper runs as one fused launch per direction (ops.latent_rollout); the convolutional stepper
+        (SST) is a sequence of grouped conv blocks."""
+        B = t_int.shape[0]
+        if isinstance(self.t_resnet, MLPResnet):
+            t0 = _external_codes(t_int)                                        # [B, d] fp32
+            codes, res = ops.latent_rollout(t0, self.t_resnet, n_forecast)      # [T,B,d], [nb,T-1,B,d]
+            t_all = ops.to_internal(codes.reshape(n_forecast * B, -1))
+            residuals = [[res[j, t] for j in range(res.shape[0])] for t in range(n_forecast - 1)]
+            return t_all, codes.transpose(0, 1), residuals
+        codes, residuals = [t_int], []
         for _ in range(1, n_forecast):
-            t_code, t_res = self.t_resnet.step(t_code)
-            codes.append(t_code)
-            residuals.append(t_res)
-        return codes, residuals
+            t_int, t_res = self.t_resnet.step(t_int)
+            codes.append(t_int)
+            residuals.append([_external_codes(r) for r in t_res])
+        t_all = torch.cat(codes, 0) if len(codes) > 1 else codes[0]
+        return t_all, _external_codes(torch.stack(codes, 1)), residuals
 
     # ------------------------------------------------------------------------------------------
     # public API (model.py:52-89)
@@ -87,17 +101,17 @@ class SeparableNetwork(nn.Module):
         group 0 *before* the forecast groups (the auto-encoding call of train.py:79-82 precedes
         get_forecast, so its BatchNorm EMA update comes first).  Returns the reference tuple; with
         ``extra_t`` the reconstruction is returned as a fifth element."""
-        codes, residuals = self.rollout(t_int, n_forecast)
-        groups = list(codes) if extra_t is None else [extra_t] + list(codes)
-        t_all = torch.cat(groups, 0) if len(groups) > 1 else groups[0]
-        frames = self.decoder.decode_external(s_int, t_all, skip_int, groups=len(groups))
-        frames = frames.view(len(groups), B, *frames.shape[1:])
+        t_all, t_codes, t_residuals = self.rollout(t_int, n_forecast)
+        n_groups = n_forecast
+        if extra_t is not None:
+            t_all = torch.cat([extra_t, t_all], 0)
+            n_groups += 1
+        frames = self.decoder.decode_external(s_int, t_all, skip_int, groups=n_groups)
+        frames = frames.view(n_groups, B, *frames.shape[1:])
         if extra_t is not None:
             recon, frames = frames[0], frames[1:]
         forecasts = frames.transpose(0, 1)                                   # [B, T, C, H, W] view
-        t_codes = _external_codes(torch.stack(codes, 1))                    # [B, T, ...]
         s_code = _external_codes(s_int)
-        t_residuals = [[_external_codes(r) for r in step] for step in residuals]
         if extra_t is not None:
             return forecasts, t_codes, s_code, t_residuals, recon
         return forecasts, t_codes, s_code, t_residuals

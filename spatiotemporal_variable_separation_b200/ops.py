@@ -529,3 +529,78 @@ def C_double_ptr(t, i):
 
 def loss_terms(spec, tensors):
     return LossTermsFn.apply(spec, *tensors)
+
+
+# ------------------------------------------------------------------------------------------------
+# latent rollout (MLP residual stepper), one launch per direction
+# ------------------------------------------------------------------------------------------------
+class LatentRolloutFn(torch.autograd.Function):
+    """codes[t+1] = stepper(codes[t]) for t < T-1 (model.py:78-83 / resnet.py:42-50) as one kernel; the
+    backward is the adjoint recurrence as one kernel plus three (T-1)*B-row weight-gradient GEMMs per block.
+    Inputs: t0 [B,d] fp32 and, per block, W1,b1,W2,b2,W3,b3.  Returns (codes [T,B,d], res [nb,T-1,B,d])."""
+
+    @staticmethod
+    def forward(ctx, T, t0, *weights):
+        L.require_cuda(t0)
+        nb = len(weights) // 6
+        B, d = t0.shape
+        h = weights[0].shape[0]
+        dev = t0.device
+        codes = torch.empty((T, B, d), device=dev, dtype=torch.float32)
+        codes[0].copy_(t0)
+        n = max(T - 1, 0)
+        hidden = torch.empty((nb, 2, n, B, h), device=dev, dtype=torch.float32)
+        xin = torch.empty((nb, n, B, d), device=dev, dtype=torch.float32)
+        res = torch.empty((nb, n, B, d), device=dev, dtype=torch.float32)
+        ws = [w.detach().contiguous() for w in weights]
+        assert all(w.dtype == torch.float32 for w in ws)
+        L.call('vs_latent_rollout_forward', ptr(codes), L.pointer_array(ws), T, B, d, h, nb, ptr(hidden), ptr(xin), ptr(res),
+               L.stream())
+        ctx.save_for_backward(hidden, xin, *ws)
+        ctx.dims, ctx.params = (T, B, d, h, nb), weights
+        ctx.mark_non_differentiable(res)
+        return codes, res
+
+    @staticmethod
+    def backward(ctx, dcodes, _dres):
+        T, B, d, h, nb = ctx.dims
+        hidden, xin = ctx.saved_tensors[:2]
+        ws = ctx.saved_tensors[2:]
+        dcodes = dcodes.contiguous().clone()
+        n = T - 1
+        dev = dcodes.device
+        dres = torch.empty((nb, n, B, d), device=dev, dtype=torch.float32)
+        dhidden = torch.empty((nb, 2, n, B, h), device=dev, dtype=torch.float32)
+        if n > 0:
+            L.call('vs_latent_rollout_backward', ptr(dcodes), L.pointer_array(list(ws)), T, B, d, h, nb, ptr(hidden), ptr(dres),
+                   ptr(dhidden), L.stream())
+        grads = []
+        rows = n * B
+
+        def lin_grads(p_w, p_b, small, big, K, Cc):
+            # dW[K][Cc] += small[rows,K]^T big[rows,Cc];  db[K] += column sums of small
+            gw, gb = _grad_buffer(p_w), _grad_buffer(p_b)
+            if rows > 0:
+                g = L.Geom(L.VS_F32, rows, 1, 1, Cc, 1, 1, K, 1, 1, 1, 0, 1, 0, 0)
+                L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(gw[0]), L.stream())
+                L.call('vs_colsum', ptr(small), L.VS_F32, rows, K, ptr(gb[0]), L.stream())
+            return gw[1], gb[1]
+
+        for j in range(nb):
+            w1, b1, w2, b2, w3, b3 = ctx.params[6 * j:6 * j + 6]
+            g1 = lin_grads(w1, b1, dhidden[j, 0], xin[j], h, d)
+            g2 = lin_grads(w2, b2, dhidden[j, 1], hidden[j, 0], h, h)
+            g3 = lin_grads(w3, b3, dres[j], hidden[j, 1], d, h)
+            grads += [g1[0], g1[1], g2[0], g2[1], g3[0], g3[1]]
+        return (None, dcodes[0]) + tuple(grads)
+
+
+def latent_rollout(t0, stepper, T):
+    """t0 [B,d] fp32; stepper: networks.resnet.MLPResnet.  -> codes [T,B,d] fp32, res [nb,T-1,B,d]."""
+    weights = []
+    for blk in stepper.blocks:
+        lins = [m[-1] for m in blk.mlp.module]
+        assert len(lins) == 3
+        for lin in lins:
+            weights += [lin.weight, lin.bias]
+    return LatentRolloutFn.apply(T, t0, *weights)

@@ -288,9 +288,71 @@ def emu_call(name, *args):
 @contextlib.contextmanager
 def install():
     """Route the package's C-ABI calls to the emulator (CPU tensors allowed) for the duration."""
-    saved = (L.call, L.stream, L.require_cuda, L.launch_count)
+    saved = (L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array)
     L.call, L.stream, L.require_cuda, L.launch_count = emu_call, (lambda: None), (lambda *a: None), (lambda: -1)
+    L.pointer_array = _emu_pointer_array
     try:
         yield
     finally:
-        L.call, L.stream, L.require_cuda, L.launch_count = saved
+        L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array = saved
+
+
+# ---- latent rollout (appended after _TABLE is built: register explicitly) -------------------------
+def _ptrs_to_tensors(arr, registry):
+    return [registry[int(a)] for a in arr]
+
+
+_TENSOR_REGISTRY = {}
+
+
+def _register(ts):
+    for t in ts:
+        _TENSOR_REGISTRY[t.data_ptr()] = t
+
+
+def _blocks(w_host, nb):
+    ws = _ptrs_to_tensors(w_host, _TENSOR_REGISTRY)
+    return [ws[6 * j:6 * j + 6] for j in range(nb)]
+
+
+def vs_latent_rollout_forward(codes, w_host, T, B, d, h, nb, hidden, xin, res, stream):
+    x = codes[0].clone()
+    for t in range(1, T):
+        for j, (w1, b1, w2, b2, w3, b3) in enumerate(_blocks(w_host, nb)):
+            if xin is not None:
+                xin[j, t - 1] = x
+            u = F.relu(F.linear(x, w1, b1))
+            v = F.relu(F.linear(u, w2, b2))
+            r = F.linear(v, w3, b3)
+            if hidden is not None:
+                hidden[j, 0, t - 1], hidden[j, 1, t - 1] = u, v
+            if res is not None:
+                res[j, t - 1] = r
+            x = x + r
+        codes[t] = x
+
+
+def vs_latent_rollout_backward(dcodes, w_host, T, B, d, h, nb, hidden, dres, dhidden, stream):
+    blocks = _blocks(w_host, nb)
+    g = dcodes[T - 1].clone()
+    for t in range(T - 1, 0, -1):
+        for j in range(nb - 1, -1, -1):
+            w1, b1, w2, b2, w3, b3 = blocks[j]
+            dres[j, t - 1] = g
+            da2 = (g @ w3) * (hidden[j, 1, t - 1] > 0)
+            dhidden[j, 1, t - 1] = da2
+            da1 = (da2 @ w2) * (hidden[j, 0, t - 1] > 0)
+            dhidden[j, 0, t - 1] = da1
+            g = g + da1 @ w1
+        g = g + dcodes[t - 1]
+    dcodes[0] = g
+
+
+_TABLE.update({'vs_latent_rollout_forward': vs_latent_rollout_forward,
+               'vs_latent_rollout_backward': vs_latent_rollout_backward})
+_orig_pointer_array = L.pointer_array
+
+
+def _emu_pointer_array(tensors):
+    _register(tensors)
+    return [t.data_ptr() for t in tensors]

@@ -339,3 +339,40 @@ def test_error_reporting_and_launch_count():
         L.call('vs_conv_forward', bad, 0, x, x, None, x, None, L.stream())
     with pytest.raises(RuntimeError, match='dtype'):
         L.call('vs_add_act', x, x, x, 7, 8, 0, L.stream())
+
+
+@pytest.mark.parametrize('T,B,d,h,nb', [(15, 128, 20, 512, 1), (6, 5, 10, 64, 2), (25, 33, 32, 512, 3), (1, 4, 20, 64, 1)])
+def test_latent_rollout_kernels(T, B, d, h, nb):
+    """Fused rollout forward / adjoint against the specification (fp32; 2e-5 relative per tensor)."""
+    torch.manual_seed(11)
+    ws = []
+    for _ in range(nb):
+        ws += [torch.randn(h, d) / d ** 0.5, 0.1 * torch.randn(h), torch.randn(h, h) / h ** 0.5 * 0.7, 0.1 * torch.randn(h),
+               torch.randn(d, h) / h ** 0.5 * 0.3, 0.1 * torch.randn(d)]
+    n = max(T - 1, 0)
+    codes = torch.zeros(T, B, d)
+    codes[0] = torch.randn(B, d)
+    hidden, xin, res = torch.zeros(nb, 2, n, B, h), torch.zeros(nb, n, B, d), torch.zeros(nb, n, B, d)
+    # CPU specification
+    c_cpu, h_cpu, x_cpu, r_cpu = codes.clone(), hidden.clone(), xin.clone(), res.clone()
+    arr = emu._emu_pointer_array(ws)
+    emu.emu_call('vs_latent_rollout_forward', c_cpu, arr, T, B, d, h, nb, h_cpu, x_cpu, r_cpu, None)
+    # CUDA
+    wg = [w.cuda() for w in ws]
+    c_gpu, h_gpu, x_gpu, r_gpu = codes.cuda(), hidden.cuda(), xin.cuda(), res.cuda()
+    L.call('vs_latent_rollout_forward', c_gpu, L.pointer_array(wg), T, B, d, h, nb, h_gpu, x_gpu, r_gpu, L.stream())
+    torch.cuda.synchronize()
+    for a, b, name in ((c_gpu, c_cpu, 'codes'), (h_gpu, h_cpu, 'hidden'), (x_gpu, x_cpu, 'xin'), (r_gpu, r_cpu, 'res')):
+        if b.numel():
+            close(a.cpu(), b, torch.float32, 'rollout fwd ' + name, outliers=1e-4, scale=float(b.abs().max()))
+    if T == 1:
+        return
+    dcodes = torch.randn(T, B, d)
+    d_cpu, dres_cpu, dh_cpu = dcodes.clone(), torch.zeros(nb, n, B, d), torch.zeros(nb, 2, n, B, h)
+    emu.emu_call('vs_latent_rollout_backward', d_cpu, arr, T, B, d, h, nb, h_cpu, dres_cpu, dh_cpu, None)
+    d_gpu, dres_gpu, dh_gpu = dcodes.cuda(), torch.zeros(nb, n, B, d).cuda(), torch.zeros(nb, 2, n, B, h).cuda()
+    L.call('vs_latent_rollout_backward', d_gpu, L.pointer_array(wg), T, B, d, h, nb, h_cpu.cuda(), dres_gpu, dh_gpu, L.stream())
+    torch.cuda.synchronize()
+    close(d_gpu[0].cpu(), d_cpu[0], torch.float32, 'rollout bwd dcodes[0]', scale=float(d_cpu[0].abs().max()))
+    close(dres_gpu.cpu(), dres_cpu, torch.float32, 'rollout bwd dres', scale=float(dres_cpu.abs().max()))
+    close(dh_gpu.cpu(), dh_cpu, torch.float32, 'rollout bwd dhidden', outliers=1e-4, scale=float(dh_cpu.abs().max()))
