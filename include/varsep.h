@@ -190,7 +190,9 @@ int vs_latent_rollout_forward(float* codes, const float* const* w_host, int32_t 
                               int32_t n_blocks, float* hidden, float* xin, float* res, void* stream);
 /* Adjoint recurrence.  dcodes [T][B][d] holds dL/dcodes[t] (from the decoder / losses) on entry; on exit
  * dcodes[0] is the gradient w.r.t. the initial code.  Emits the pre-activation gradients needed for the
- * weight gradients, which are then (T-1)*B-row GEMMs (vs_conv_wgrad / vs_colsum):
+ * weight gradients, which are then (T-1)*B-row GEMMs (vs_conv_wgrad / vs_colsum).  w_host here holds the
+ * TRANSPOSED weights {W1^T[d][h], -, W2^T[h][h], -, W3^T[h][d], -} per block (bias slots ignored), so that the
+ * adjoint products stream rows exactly like the forward ones:
  *   dres [n_blocks][T-1][B][d] = dL/d(residual),  dhidden [n_blocks][2][T-1][B][h] = dL/d(pre-ReLU of L1, L2). */
 int vs_latent_rollout_backward(float* dcodes, const float* const* w_host, int32_t T, int32_t B, int32_t d, int32_t h,
                                int32_t n_blocks, const float* hidden, float* dres, float* dhidden, void* stream);

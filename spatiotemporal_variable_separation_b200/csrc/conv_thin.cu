@@ -117,45 +117,120 @@ __global__ void __launch_bounds__(256) thin_in_kernel(ThinArgs a, const T* __res
     }
 }
 
-// ---- weight gradient with few channels on the gathered ("big") side: C <= 8, K % 64 == 0.
-// dw[k][c][tap] += sum_pix small[pix][k] * big[src(pix,tap)][c].  Block = 64 channel lanes x 4 pixel lanes;
-// each thread keeps its R*R*C accumulators in registers (filter size and C are template parameters).
+// ---- few input values per pixel (R*S*IC <= 16, e.g. the dgrad of ConvTranspose 64->1): one thread computes ALL
+// output channels of one pixel; the R*S*IC gathered inputs sit in registers, the weights are broadcast LDS.128s.
+template <typename T, int KV, int OC>
+__global__ void __launch_bounds__(128) thin_in_wide_kernel(ThinArgs a, const T* __restrict__ in, const T* __restrict__ wp,
+                                                           const float* __restrict__ bias, T* __restrict__ out) {
+    __shared__ __align__(16) float wsm[KV * OC];      // [kv = tap*IC + c][oc]
+    const int RS = a.R * a.S;
+    for (int i = threadIdx.x; i < KV * OC; i += blockDim.x) {
+        const int oc = i % OC, kv = i / OC;
+        wsm[i] = kv < RS * a.IC ? ld<T>(wp + (long long)oc * RS * a.IC + kv) : 0.f;
+    }
+    __syncthreads();
+    const unsigned total = (unsigned)a.N * a.OH * a.OW;
+    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+        const int ow = (int)(pix % a.OW);
+        const int oh = (int)((pix / a.OW) % a.OH);
+        const int n = (int)(pix / ((unsigned)a.OW * a.OH));
+        float x[KV];
+#pragma unroll
+        for (int kv = 0; kv < KV; ++kv) x[kv] = 0.f;
+        int kv = 0;
+        for (int r = 0; r < a.R; ++r)
+            for (int s = 0; s < a.S; ++s) {
+                int ih, iw;
+                const bool ok = thin_src(a, oh, ow, r, s, ih, iw);
+                const T* src = in + (((long long)n * a.IH + ih) * a.IW + iw) * a.IC;
+                for (int c = 0; c < a.IC; ++c, ++kv) {
+                    const float v = ok ? ld<T>(src + c) : 0.f;
+#pragma unroll
+                    for (int q = 0; q < KV; ++q) if (q == kv) x[q] = v;      // keeps x[] in registers
+                }
+            }
+        T* dst = out + (long long)pix * OC;
+#pragma unroll
+        for (int o8 = 0; o8 < OC; o8 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[o8 + j] : 0.f;
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&wsm[q * OC + o8]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&wsm[q * OC + o8 + 4]);
+                acc[0] = fmaf(x[q], w0.x, acc[0]); acc[1] = fmaf(x[q], w0.y, acc[1]);
+                acc[2] = fmaf(x[q], w0.z, acc[2]); acc[3] = fmaf(x[q], w0.w, acc[3]);
+                acc[4] = fmaf(x[q], w1.x, acc[4]); acc[5] = fmaf(x[q], w1.y, acc[5]);
+                acc[6] = fmaf(x[q], w1.z, acc[6]); acc[7] = fmaf(x[q], w1.w, acc[7]);
+            }
+            st4<T>(dst + o8, make_float4(act_fwd(acc[0], a.act), act_fwd(acc[1], a.act), act_fwd(acc[2], a.act), act_fwd(acc[3], a.act)));
+            st4<T>(dst + o8 + 4, make_float4(act_fwd(acc[4], a.act), act_fwd(acc[5], a.act), act_fwd(acc[6], a.act), act_fwd(acc[7], a.act)));
+        }
+    }
+}
+
+// ---- weight gradient with few channels on the gathered ("big") side: C <= 5, K % 64 == 0.
+// dw[k][c][tap] += sum_pix small[pix][k] * big[src(pix,tap)][c].
+// Per 64-pixel tile the R*R*C gathered values of every pixel are staged ONCE in shared memory (the address
+// arithmetic and the scattered 2-byte loads are not repeated by the 64 channel lanes); then each thread
+// (channel k, pixel lane) streams `small` coalesced and does R*R*C FMAs per pixel against broadcast LDS.128s.
 template <typename T, int RR, int CC>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(vs_conv_geom g, const T* __restrict__ small_, const T* __restrict__ big,
                                                          float* __restrict__ dw, long long rows_per_block) {
+    constexpr int NV = RR * RR * CC, NVP = (NV + 3) / 4 * 4, TP = 64;
+    __shared__ __align__(16) float gs[TP][NVP];
     __shared__ float red[4][64];
     const int kl = threadIdx.x & 63, pl = threadIdx.x >> 6;
     const int k = blockIdx.y * 64 + kl;
     const long long M = (long long)g.N * g.P * g.Q;
     const long long m0 = (long long)blockIdx.x * rows_per_block;
     const long long m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
-    float acc[RR * RR * CC];
-#pragma unroll
-    for (int i = 0; i < RR * RR * CC; ++i) acc[i] = 0.f;
     const unsigned PQ = (unsigned)g.P * g.Q;
-    for (long long m = m0 + pl; m < m1; m += 4) {
-        const float v = ld<T>(small_ + m * g.K + k);
-        const unsigned mu = (unsigned)m;                     // M < 2^32, checked by the launcher
-        const int n = (int)(mu / PQ);
-        const int rem = (int)(mu - (unsigned)n * PQ);
-        const int ph = rem / g.Q, pw = rem % g.Q;
+    float acc[NVP];
 #pragma unroll
-        for (int r = 0; r < RR; ++r) {
-            const int ih = ph * g.stride - g.pad + r;
+    for (int i = 0; i < NVP; ++i) acc[i] = 0.f;
+    for (long long mt = m0; mt < m1; mt += TP) {
+        __syncthreads();
+        // stage: TP pixels x R*R taps, one (pixel, tap) pair per thread iteration
+        for (int i = threadIdx.x; i < TP * RR * RR; i += 256) {
+            const int px = i / (RR * RR), tap = i - px * (RR * RR);
+            const long long m = mt + px;
+            float v[CC];
 #pragma unroll
-            for (int s = 0; s < RR; ++s) {
-                const int iw = pw * g.stride - g.pad + s;
-                const bool ok = ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
-                const T* src = big + (((long long)n * g.H + ih) * g.W + iw) * CC;
+            for (int c = 0; c < CC; ++c) v[c] = 0.f;
+            if (m < m1) {
+                const unsigned mu = (unsigned)m;
+                const int n = (int)(mu / PQ);
+                const int rem = (int)(mu - (unsigned)n * PQ);
+                const int ih = (rem / g.Q) * g.stride - g.pad + tap / RR, iw = (rem % g.Q) * g.stride - g.pad + tap % RR;
+                if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+                    const T* src = big + (((long long)n * g.H + ih) * g.W + iw) * CC;
 #pragma unroll
-                for (int c = 0; c < CC; ++c)
-                    if (ok) acc[(r * RR + s) * CC + c] = fmaf(v, ld<T>(src + c), acc[(r * RR + s) * CC + c]);
+                    for (int c = 0; c < CC; ++c) v[c] = ld<T>(src + c);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CC; ++c) gs[px][tap * CC + c] = v[c];
+        }
+        __syncthreads();
+        for (int px = pl; px < TP; px += 4) {
+            const long long m = mt + px;
+            if (m >= m1) break;
+            const float v = ld<T>(small_ + m * g.K + k);
+#pragma unroll
+            for (int i4 = 0; i4 < NVP / 4; ++i4) {
+                const float4 b = *reinterpret_cast<const float4*>(&gs[px][i4 * 4]);
+                acc[i4 * 4 + 0] = fmaf(v, b.x, acc[i4 * 4 + 0]);
+                acc[i4 * 4 + 1] = fmaf(v, b.y, acc[i4 * 4 + 1]);
+                acc[i4 * 4 + 2] = fmaf(v, b.z, acc[i4 * 4 + 2]);
+                acc[i4 * 4 + 3] = fmaf(v, b.w, acc[i4 * 4 + 3]);
             }
         }
     }
     // reduce the 4 pixel lanes through shared memory, then one atomic per (k, c, tap)
 #pragma unroll
-    for (int i = 0; i < RR * RR * CC; ++i) {
+    for (int i = 0; i < NV; ++i) {
         __syncthreads();
         red[pl][kl] = acc[i];
         __syncthreads();
@@ -233,6 +308,11 @@ int conv_forward_thin(const vs_conv_geom* g, int mode, const void* in, const voi
             }
         });
         rc = launched("thin_out_kernel");
+    } else if (a.R * a.S * a.IC <= 16 && a.OC == 64 && pixels < 4000000000LL) {
+        long long blocks = cdiv(pixels, 128);
+        if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+        VS_DISPATCH_DTYPE(g->dtype, T, (thin_in_wide_kernel<T, 16, 64><<<(unsigned)blocks, 128, 0, stream>>>(a, (const T*)in, (const T*)wp, bias, (T*)out)));
+        rc = launched("thin_in_wide_kernel");
     } else if (a.IC <= 8 && a.OC % 8 == 0 && (long long)a.R * a.S * a.IC * a.OC * 4 <= 96 * 1024 &&
                pixels * (a.OC / 8) < 4000000000LL) {
         const int smem = a.R * a.S * a.IC * a.OC * 4;
@@ -270,7 +350,7 @@ int conv_wgrad_thin(const vs_conv_geom* g, const void* small_, const void* big, 
     long long blocks = 8LL * num_sms() / (g->K / 64);
     if (blocks > cdiv(M, 256)) blocks = cdiv(M, 256);
     if (blocks < 1) blocks = 1;
-    const long long rpb = cdiv(cdiv(M, blocks), 4) * 4;
+    const long long rpb = cdiv(cdiv(M, blocks), 64) * 64;
     dim3 grid((unsigned)cdiv(M, rpb), (unsigned)(g->K / 64));
     bool ok = false;
     VS_DISPATCH_DTYPE(g->dtype, T, {

@@ -23,60 +23,58 @@ struct RolloutWeights {
 };
 
 // out[r][n] = act(bias[n] + sum_k W[n][k] * in[r][k])   for RB rows held in shared memory.
-// One warp per output n (lanes split k, coalesced float4 reads of row n of W), shuffle reduction.
-template <int RB, bool RELU>
+// One warp per group of NO outputs: lanes split k, the NO weight rows are fetched with back-to-back coalesced
+// float4 loads (NO*nin/128 independent requests in flight per lane - the layer is L2-latency bound, not FLOP
+// bound), then NO*RB shuffle reductions.
+template <int RB, bool RELU, int NO>
 __device__ __forceinline__ void dense_rows(const float* __restrict__ W, const float* __restrict__ bias, int nout, int nin,
                                            const float* __restrict__ in_s, int in_ld, float* __restrict__ out_s, int out_ld) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = RO_THREADS / 32;
-    for (int n = warp; n < nout; n += nwarps) {
-        float acc[RB];
+    for (int n0 = warp * NO; n0 < nout; n0 += nwarps * NO) {
+        float acc[NO][RB];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-        const float* wr = W + (long long)n * nin;
+        for (int o = 0; o < NO; ++o)
+#pragma unroll
+            for (int r = 0; r < RB; ++r) acc[o][r] = 0.f;
         if ((nin & 3) == 0) {
             for (int k = lane * 4; k < nin; k += 128) {
-                const float4 w = *reinterpret_cast<const float4*>(wr + k);
+                float4 w[NO];
+#pragma unroll
+                for (int o = 0; o < NO; ++o)
+                    w[o] = n0 + o < nout ? __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + o) * nin + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     const float4 x = *reinterpret_cast<const float4*>(in_s + r * in_ld + k);
-                    acc[r] += w.x * x.x + w.y * x.y + w.z * x.z + w.w * x.w;
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) acc[o][r] += w[o].x * x.x + w[o].y * x.y + w[o].z * x.z + w[o].w * x.w;
                 }
             }
         } else {
             for (int k = lane; k < nin; k += 32) {
-                const float w = wr[k];
 #pragma unroll
-                for (int r = 0; r < RB; ++r) acc[r] = fmaf(w, in_s[r * in_ld + k], acc[r]);
+                for (int o = 0; o < NO; ++o) {
+                    const float w = n0 + o < nout ? __ldg(W + (long long)(n0 + o) * nin + k) : 0.f;
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) acc[o][r] = fmaf(w, in_s[r * in_ld + k], acc[o][r]);
+                }
             }
         }
 #pragma unroll
-        for (int r = 0; r < RB; ++r) acc[r] = warp_sum(acc[r]);
+        for (int o = 0; o < NO; ++o)
+#pragma unroll
+            for (int r = 0; r < RB; ++r) acc[o][r] = warp_sum(acc[o][r]);
         if (lane == 0) {
-            const float b = bias ? bias[n] : 0.f;
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                const float v = acc[r] + b;
-                out_s[r * out_ld + n] = RELU ? fmaxf(v, 0.f) : v;
+            for (int o = 0; o < NO; ++o) {
+                if (n0 + o >= nout) break;
+                const float b = bias ? bias[n0 + o] : 0.f;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const float v = acc[o][r] + b;
+                    out_s[r * out_ld + n0 + o] = RELU ? fmaxf(v, 0.f) : v;
+                }
             }
         }
-    }
-}
-
-// out[r][k] = sum_n W[n][k] * in[r][n]   (transpose product): one thread per k, coalesced over k.
-template <int RB>
-__device__ __forceinline__ void dense_rows_t(const float* __restrict__ W, int nout_rows, int ncols, const float* __restrict__ in_s,
-                                             int in_ld, float* __restrict__ out_s, int out_ld) {
-    for (int k = threadIdx.x; k < ncols; k += RO_THREADS) {
-        float acc[RB];
-#pragma unroll
-        for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-        for (int n = 0; n < nout_rows; ++n) {
-            const float w = W[(long long)n * ncols + k];
-#pragma unroll
-            for (int r = 0; r < RB; ++r) acc[r] = fmaf(w, in_s[r * in_ld + n], acc[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < RB; ++r) out_s[r * out_ld + k] = acc[r];
     }
 }
 
@@ -99,11 +97,11 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_fwd_kernel(float* __restri
         for (int j = 0; j < nb; ++j) {
             const long long slot = (long long)j * (T - 1) + (t - 1);
             if (xin) for (int i = threadIdx.x; i < nrow * d; i += RO_THREADS) xin[(slot * B + row0) * d + i] = x[i];
-            dense_rows<RB, true>(w.w1[j], w.b1[j], h, d, x, d, u, h);
+            dense_rows<RB, true, 4>(w.w1[j], w.b1[j], h, d, x, d, u, h);
             __syncthreads();
-            dense_rows<RB, true>(w.w2[j], w.b2[j], h, h, u, h, v, h);
+            dense_rows<RB, true, 4>(w.w2[j], w.b2[j], h, h, u, h, v, h);
             __syncthreads();
-            dense_rows<RB, false>(w.w3[j], w.b3[j], d, h, v, h, rr, d);
+            dense_rows<RB, false, 2>(w.w3[j], w.b3[j], d, h, v, h, rr, d);
             __syncthreads();
             if (hidden)
                 for (int i = threadIdx.x; i < nrow * h; i += RO_THREADS) {
@@ -140,7 +138,7 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_bwd_kernel(float* __restri
             const long long slot = (long long)j * (T - 1) + (t - 1);
             // dr = g (gradient of the residual output);  d(a2) = (dr W3) * [h2 > 0]
             for (int i = threadIdx.x; i < nrow * d; i += RO_THREADS) dres[(slot * B + row0) * d + i] = g[i];
-            dense_rows_t<RB>(w.w3[j], d, h, g, d, b, h);
+            dense_rows<RB, false, 4>(w.w3[j], nullptr, h, d, g, d, b, h);          // w3 = W3^T [h][d]
             __syncthreads();
             for (int i = threadIdx.x; i < nrow * h; i += RO_THREADS) {
                 const float hv = hidden[(hslot(j, 1, t) * B + row0) * h + i];
@@ -150,7 +148,7 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_bwd_kernel(float* __restri
             }
             __syncthreads();
             // d(a1) = (d(a2) W2) * [h1 > 0]
-            dense_rows_t<RB>(w.w2[j], h, h, b, h, a, h);
+            dense_rows<RB, false, 4>(w.w2[j], nullptr, h, h, b, h, a, h);          // w2 = W2^T [h][h]
             __syncthreads();
             for (int i = threadIdx.x; i < nrow * h; i += RO_THREADS) {
                 const float hv = hidden[(hslot(j, 0, t) * B + row0) * h + i];
@@ -160,7 +158,7 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_bwd_kernel(float* __restri
             }
             __syncthreads();
             // dx_in = g + d(a1) W1
-            dense_rows_t<RB>(w.w1[j], h, d, a, h, tmp, d);
+            dense_rows<RB, false, 2>(w.w1[j], nullptr, d, h, a, h, tmp, d);        // w1 = W1^T [d][h]
             __syncthreads();
             for (int i = threadIdx.x; i < RB * d; i += RO_THREADS) g[i] += tmp[i];
             __syncthreads();

@@ -572,7 +572,14 @@ class LatentRolloutFn(torch.autograd.Function):
         dres = torch.empty((nb, n, B, d), device=dev, dtype=torch.float32)
         dhidden = torch.empty((nb, 2, n, B, h), device=dev, dtype=torch.float32)
         if n > 0:
-            L.call('vs_latent_rollout_backward', ptr(dcodes), L.pointer_array(list(ws)), T, B, d, h, nb, ptr(hidden), ptr(dres),
+            # the adjoint products need W^T: packed fp32 transposes, cached per parameter like every packed weight
+            wt = []
+            for j in range(nb):
+                w1, b1, w2, b2, w3, b3 = ctx.params[6 * j:6 * j + 6]
+                wt += [packed_weight(w1, h, d, 1, True, torch.float32), ws[6 * j + 1],
+                       packed_weight(w2, h, h, 1, True, torch.float32), ws[6 * j + 3],
+                       packed_weight(w3, d, h, 1, True, torch.float32), ws[6 * j + 5]]
+            L.call('vs_latent_rollout_backward', ptr(dcodes), L.pointer_array(wt), T, B, d, h, nb, ptr(hidden), ptr(dres),
                    ptr(dhidden), L.stream())
         grads = []
         rows = n * B

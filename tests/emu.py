@@ -333,17 +333,18 @@ def vs_latent_rollout_forward(codes, w_host, T, B, d, h, nb, hidden, xin, res, s
 
 
 def vs_latent_rollout_backward(dcodes, w_host, T, B, d, h, nb, hidden, dres, dhidden, stream):
-    blocks = _blocks(w_host, nb)
+    blocks = _blocks(w_host, nb)          # TRANSPOSED weights: W1^T [d][h], W2^T [h][h], W3^T [h][d] (flat buffers)
     g = dcodes[T - 1].clone()
     for t in range(T - 1, 0, -1):
         for j in range(nb - 1, -1, -1):
-            w1, b1, w2, b2, w3, b3 = blocks[j]
+            w1t, _, w2t, _, w3t, _ = blocks[j]
+            w1t, w2t, w3t = w1t.reshape(d, h), w2t.reshape(h, h), w3t.reshape(h, d)
             dres[j, t - 1] = g
-            da2 = (g @ w3) * (hidden[j, 1, t - 1] > 0)
+            da2 = (g @ w3t.t()) * (hidden[j, 1, t - 1] > 0)
             dhidden[j, 1, t - 1] = da2
-            da1 = (da2 @ w2) * (hidden[j, 0, t - 1] > 0)
+            da1 = (da2 @ w2t.t()) * (hidden[j, 0, t - 1] > 0)
             dhidden[j, 0, t - 1] = da1
-            g = g + da1 @ w1
+            g = g + da1 @ w1t.t()
         g = g + dcodes[t - 1]
     dcodes[0] = g
 

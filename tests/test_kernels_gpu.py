@@ -369,9 +369,11 @@ def test_latent_rollout_kernels(T, B, d, h, nb):
         return
     dcodes = torch.randn(T, B, d)
     d_cpu, dres_cpu, dh_cpu = dcodes.clone(), torch.zeros(nb, n, B, d), torch.zeros(nb, 2, n, B, h)
-    emu.emu_call('vs_latent_rollout_backward', d_cpu, arr, T, B, d, h, nb, h_cpu, dres_cpu, dh_cpu, None)
+    wt = [w.t().contiguous() if w.dim() == 2 else w for w in ws]        # the adjoint takes transposed weights
+    emu.emu_call('vs_latent_rollout_backward', d_cpu, emu._emu_pointer_array(wt), T, B, d, h, nb, h_cpu, dres_cpu, dh_cpu, None)
     d_gpu, dres_gpu, dh_gpu = dcodes.cuda(), torch.zeros(nb, n, B, d).cuda(), torch.zeros(nb, 2, n, B, h).cuda()
-    L.call('vs_latent_rollout_backward', d_gpu, L.pointer_array(wg), T, B, d, h, nb, h_cpu.cuda(), dres_gpu, dh_gpu, L.stream())
+    wtg = [w.cuda() for w in wt]
+    L.call('vs_latent_rollout_backward', d_gpu, L.pointer_array(wtg), T, B, d, h, nb, h_cpu.cuda(), dres_gpu, dh_gpu, L.stream())
     torch.cuda.synchronize()
     close(d_gpu[0].cpu(), d_cpu[0], torch.float32, 'rollout bwd dcodes[0]', scale=float(d_cpu[0].abs().max()))
     close(dres_gpu.cpu(), dres_cpu, torch.float32, 'rollout bwd dres', scale=float(dres_cpu.abs().max()))
