@@ -74,7 +74,13 @@ extern "C" int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* 
     if (int rc = check_geom(g)) return rc;
     VS_REQUIRE(mode == VS_CONV_DIRECT || mode == VS_CONV_TRANSPOSED, "bad mode %d", mode);
     VS_REQUIRE(stats == nullptr || g->act == VS_ACT_NONE, "statistics are taken of the pre-activation: act must be NONE");
-    int rc = conv_forward_tc(g, mode, in, wp, bias, out, stats, as_stream(stream));
+    int rc = -1;
+    // 64 -> 1 channel transposed convolution: the dedicated streaming kernel reads the input once (the tensor-core
+    // tap GEMM would fetch it 16 times to fill 1 of 64 accumulator columns)
+    if (mode == VS_CONV_TRANSPOSED && g->C == 1 && g->K == 64 && g->R == 4 && g->stride == 2)
+        rc = conv_forward_thin(g, mode, in, wp, bias, out, stats, as_stream(stream));
+    if (rc >= 0) return rc;
+    rc = conv_forward_tc(g, mode, in, wp, bias, out, stats, as_stream(stream));
     if (rc >= 0) return rc;
     rc = conv_forward_thin(g, mode, in, wp, bias, out, stats, as_stream(stream));
     if (rc >= 0) return rc;

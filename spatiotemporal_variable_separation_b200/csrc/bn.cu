@@ -290,20 +290,37 @@ __global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict_
         s1[k] = 0.f; s2[k] = 0.f;
         if (MODE == 0) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
     }
-    for (long long r = r0 + rl; r < r1; r += pl.rows_per_iter) {
-        float v[W], d[W];
+    // two independent rows in flight per thread (the loop is latency-, not bandwidth-limited otherwise)
+    for (long long r = r0 + rl; r < r1; r += 2 * pl.rows_per_iter) {
+        const long long rb = r + pl.rows_per_iter;
+        const bool has_b = rb < r1;
+        float v[W], d[W], v2[W], d2[W];
         Vec<T>::load(y + r * C + c, v);
+        if (has_b) Vec<T>::load(y + rb * C + c, v2);
         if (MODE == 0) {
             Vec<T>::load(dout + r * C + c, d);
+            if (has_b) Vec<T>::load(dout + rb * C + c, d2);
 #pragma unroll
             for (int k = 0; k < W; ++k) {
                 const float xh = (v[k] - mu[k]) * is[k];
                 const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
                 s1[k] += dz; s2[k] += dz * xh;
             }
+            if (has_b) {
+#pragma unroll
+                for (int k = 0; k < W; ++k) {
+                    const float xh = (v2[k] - mu[k]) * is[k];
+                    const float dz = d2[k] * act_grad_from_in(ga[k] * xh + be[k], act);
+                    s1[k] += dz; s2[k] += dz * xh;
+                }
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < W; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
+            if (has_b) {
+#pragma unroll
+                for (int k = 0; k < W; ++k) { s1[k] += v2[k]; s2[k] = fmaf(v2[k], v2[k], s2[k]); }
+            }
         }
     }
     // reduce the row lanes of the block (threads with equal threadIdx.x % tpr), then fp64 atomics
@@ -329,7 +346,7 @@ __global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict_
 int column_stats(const void* y, int dtype, long long rows, int C, int G, double* stats, cudaStream_t stream) {
     VS_DISPATCH_DTYPE(dtype, T, {
         ColPlan pl;
-        if (!col_plan<T>(rows, C, G, pl, 2)) return -1;
+        if (!col_plan<T>(rows, C, G, pl, 8)) return -1;
         bn_reduce_col_kernel<T, 1><<<(unsigned)(G * pl.chunks), 256, 0, stream>>>(nullptr, (const T*)y, C, pl, nullptr, nullptr,
                                                                                    nullptr, nullptr, 0, stats);
     });
@@ -393,7 +410,7 @@ extern "C" int vs_bn_act_backward_reduce(const void* dout, const void* y, int32_
     const long long rpg = rows / G;
     VS_DISPATCH_DTYPE(dtype, T, {
         ColPlan pl;
-        if (col_plan<T>(rows, C, G, pl, 2)) {
+        if (col_plan<T>(rows, C, G, pl, 8)) {
             bn_reduce_col_kernel<T, 0><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, C, pl, mean, invstd, gamma, beta, act, sums);
             return launched("bn_reduce_col_kernel");
         }

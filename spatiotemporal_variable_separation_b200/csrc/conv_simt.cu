@@ -302,6 +302,27 @@ __global__ void colsum_kernel(const T* __restrict__ a, long long rows, int C, fl
     }
 }
 
+// column sums when C <= 4: every thread strides over rows, block reduction, one atomic per column and block
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_narrow_kernel(const T* __restrict__ a, long long rows, int C, float* __restrict__ db) {
+    __shared__ float red[8][4];
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+        for (int c = 0; c < C; ++c) s[c] += ld<T>(a + r * C + c);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[c] = warp_sum(s[c]);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[threadIdx.x >> 5][c] = s[c];
+    __syncthreads();
+    if (threadIdx.x < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        atomicAdd(&db[threadIdx.x], t);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 int conv_forward_simt(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                       double* stats, cudaStream_t stream) {
@@ -362,6 +383,12 @@ extern "C" int vs_pack_weight(const float* w, void* out, int32_t dtype, int32_t 
 
 extern "C" int vs_colsum(const void* a, int32_t dtype, int64_t rows, int32_t C, float* db, void* stream) {
     if (rows == 0 || C == 0) return 0;
+    if (C <= 4) {
+        long long blocks = cdiv(rows, 1024);
+        if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+        VS_DISPATCH_DTYPE(dtype, T, (colsum_narrow_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const T*)a, rows, C, db)));
+        return launched("colsum_narrow_kernel");
+    }
     const int cx = (int)cdiv(C, 32);
     long long by = cdiv(2LL * num_sms(), cx);
     if (by > cdiv(rows, 64)) by = cdiv(rows, 64);

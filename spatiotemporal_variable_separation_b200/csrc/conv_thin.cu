@@ -74,6 +74,85 @@ __global__ void __launch_bounds__(256) thin_out_kernel(ThinArgs a, const T* __re
     }
 }
 
+// ---- last DCGAN decoder layer: ConvTranspose k4 s2 p1, 64 -> 1 channel (conv.py:263).  HBM-bound (AI 15 FLOP/B):
+// the kernel's job is to read every input pixel ONCE.  A block stages an 8x32 input tile + 1-pixel halo in shared
+// memory; 8 lanes share one input position (i,j) - each owns 8 of the 64 channels and keeps its 16x8 filter
+// taps in registers - and produce the 2x2 output pixels (2i+a, 2j+b) from the 3x3 neighbourhood (every
+// neighbour feeds exactly the parity classes whose tap index r = a + 1 - 2*di is valid), then 3 shuffles.
+template <typename T>
+__global__ void __launch_bounds__(256) convT_k4s2_to1_kernel(const T* __restrict__ in, const T* __restrict__ wp, const float* __restrict__ bias,
+                                                             T* __restrict__ out, int N, int H, int W, int act) {
+    constexpr int TH = 8, TW = 32, PH = TH + 2, PW = TW + 2, IC = 64;
+    extern __shared__ __align__(16) unsigned char patch_raw[];
+    T* patch = reinterpret_cast<T*>(patch_raw);
+    const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+    int b = blockIdx.x;
+    const int tw = b % tiles_w; b /= tiles_w;
+    const int th = b % tiles_h;
+    const int n = b / tiles_h;
+    const int i0 = th * TH, j0 = tw * TW;
+    // stage the patch (zero outside the image): 16-byte chunks, coalesced over channels then columns
+    constexpr int CH16 = IC * (int)sizeof(T) / 16, EPC = 16 / (int)sizeof(T);
+    for (int q = threadIdx.x; q < PH * PW * CH16; q += 256) {
+        const int ch = q % CH16, px = q / CH16;
+        const int pi = px / PW, pj = px % PW;
+        const int ih = i0 - 1 + pi, iw = j0 - 1 + pj;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+            v = *reinterpret_cast<const uint4*>(in + (((long long)n * H + ih) * W + iw) * IC + ch * EPC);
+        *reinterpret_cast<uint4*>(patch + (long long)px * IC + ch * EPC) = v;
+    }
+    // this lane's filter slice: w[tap][8 channels]
+    const int sub = threadIdx.x & 7;
+    float w[16][8];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const float4 a = ld4<T>(wp + t * IC + sub * 8), c = ld4<T>(wp + t * IC + sub * 8 + 4);
+        w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = c.x; w[t][5] = c.y; w[t][6] = c.z; w[t][7] = c.w;
+    }
+    const float bv = bias ? bias[0] : 0.f;
+    __syncthreads();
+    const int OW = 2 * W;
+    for (int pos = threadIdx.x >> 3; pos < TH * TW; pos += 32) {
+        const int li = pos / TW, lj = pos % TW;
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+        for (int di = -1; di <= 1; ++di)
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                const T* px = patch + ((long long)(li + 1 + di) * PW + (lj + 1 + dj)) * IC + sub * 8;
+                const float4 x0 = ld4<T>(px), x1 = ld4<T>(px + 4);
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const int r = a + 1 - 2 * di;
+                    if (r < 0 || r > 3) continue;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int s = c + 1 - 2 * dj;
+                        if (s < 0 || s > 3) continue;
+                        const float* ww = w[r * 4 + s];
+                        acc[a][c] += x0.x * ww[0] + x0.y * ww[1] + x0.z * ww[2] + x0.w * ww[3] + x1.x * ww[4] + x1.y * ww[5] +
+                                     x1.z * ww[6] + x1.w * ww[7];
+                    }
+                }
+            }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                acc[a][c] += __shfl_xor_sync(0xffffffffu, acc[a][c], 1);
+                acc[a][c] += __shfl_xor_sync(0xffffffffu, acc[a][c], 2);
+                acc[a][c] += __shfl_xor_sync(0xffffffffu, acc[a][c], 4);
+            }
+        const int i = i0 + li, j = j0 + lj;
+        if (sub < 2 && i < H && j < W) {        // lane 0 writes output row 2i, lane 1 row 2i+1 (two adjacent pixels each)
+            T* dst = out + ((long long)n * 2 * H + 2 * i + sub) * OW + 2 * j;
+            st<T>(dst, act_fwd(acc[sub][0] + bv, act));
+            st<T>(dst + 1, act_fwd(acc[sub][1] + bv, act));
+        }
+    }
+}
+
 // ---- few INPUT channels (IC <= 8), OC % 8 == 0: one thread = one output pixel x 8 output channels.
 // weights staged in shared memory as fp32 [tap][c][oc]
 template <typename T>
@@ -296,7 +375,17 @@ int conv_forward_thin(const vs_conv_geom* g, int mode, const void* in, const voi
     // whatever else is in the batch, so the threshold is on the per-sample pixel count
     if (a.OH * a.OW < 256) return -1;
     int rc;
-    if (a.OC <= 4 && a.IC % 64 == 0) {
+    if (a.transposed && a.OC == 1 && a.IC == 64 && a.R == 4 && a.S == 4 && a.stride == 2 && a.pad == 1 && a.OH == 2 * a.IH &&
+        a.OW == 2 * a.IW) {
+        const long long blocks = (long long)a.N * cdiv(a.IH, 8) * cdiv(a.IW, 32);
+        VS_REQUIRE(blocks < 2147483647LL, "convT_k4s2_to1: grid too large");
+        VS_DISPATCH_DTYPE(g->dtype, T, {
+            const int smem = 10 * 34 * 64 * (int)sizeof(T);
+            if (smem > 48 * 1024) cudaFuncSetAttribute(convT_k4s2_to1_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            convT_k4s2_to1_kernel<T><<<(unsigned)blocks, 256, smem, stream>>>((const T*)in, (const T*)wp, bias, (T*)out, a.N, a.IH, a.IW, a.act);
+        });
+        rc = launched("convT_k4s2_to1_kernel");
+    } else if (a.OC <= 4 && a.IC % 64 == 0) {
         long long blocks = cdiv(pixels * 8, 256);
         if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
         VS_DISPATCH_DTYPE(g->dtype, T, {
