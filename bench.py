@@ -282,6 +282,7 @@ def run_ours(args, cfg):
     roof = conv_roofline(tr, dev, draws, dtype)
 
     if rank != 0:
+        _shutdown(tr, world)
         return
     peaks, src = measured_peaks()
     flop_seq = FLOP_PER_SEQ[cfg['data']]
@@ -312,9 +313,19 @@ def run_ours(args, cfg):
                                 'sample': f'{info["steps"]} full-batch ({info["batch"]}) steps after 1 warm-up, '
                                           f'{info["ms_per_step"]:.0f} ms/step, {info["threads"]} threads'}
     print(json.dumps(line), flush=True)
+    _shutdown(tr, world)
+
+
+def _shutdown(tr, world):
+    """Collective teardown on EVERY rank: drop the captured graphs (they hold NCCL work) before the group."""
+    tr.graphs.clear()
+    torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
+        dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 def conv_roofline(tr, dev, draws, dtype):

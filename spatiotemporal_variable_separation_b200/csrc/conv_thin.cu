@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) thin_out_kernel(ThinArgs a, const T* __re
 // taps in registers - and produce the 2x2 output pixels (2i+a, 2j+b) from the 3x3 neighbourhood (every
 // neighbour feeds exactly the parity classes whose tap index r = a + 1 - 2*di is valid), then 3 shuffles.
 template <typename T>
-__global__ void __launch_bounds__(256) convT_k4s2_to1_kernel(const T* __restrict__ in, const T* __restrict__ wp, const float* __restrict__ bias,
+__global__ void __launch_bounds__(128) convT_k4s2_to1_kernel(const T* __restrict__ in, const T* __restrict__ wp, const float* __restrict__ bias,
                                                              T* __restrict__ out, int N, int H, int W, int act) {
     constexpr int TH = 8, TW = 32, PH = TH + 2, PW = TW + 2, IC = 64;
     extern __shared__ __align__(16) unsigned char patch_raw[];
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) convT_k4s2_to1_kernel(const T* __restrict
     const int i0 = th * TH, j0 = tw * TW;
     // stage the patch (zero outside the image): 16-byte chunks, coalesced over channels then columns
     constexpr int CH16 = IC * (int)sizeof(T) / 16, EPC = 16 / (int)sizeof(T);
-    for (int q = threadIdx.x; q < PH * PW * CH16; q += 256) {
+    for (int q = threadIdx.x; q < PH * PW * CH16; q += 128) {
         const int ch = q % CH16, px = q / CH16;
         const int pi = px / PW, pj = px % PW;
         const int ih = i0 - 1 + pi, iw = j0 - 1 + pj;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) convT_k4s2_to1_kernel(const T* __restrict
     const float bv = bias ? bias[0] : 0.f;
     __syncthreads();
     const int OW = 2 * W;
-    for (int pos = threadIdx.x >> 3; pos < TH * TW; pos += 32) {
+    for (int pos = threadIdx.x >> 3; pos < TH * TW; pos += 16) {
         const int li = pos / TW, lj = pos % TW;
         float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
@@ -382,7 +382,7 @@ int conv_forward_thin(const vs_conv_geom* g, int mode, const void* in, const voi
         VS_DISPATCH_DTYPE(g->dtype, T, {
             const int smem = 10 * 34 * 64 * (int)sizeof(T);
             if (smem > 48 * 1024) cudaFuncSetAttribute(convT_k4s2_to1_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            convT_k4s2_to1_kernel<T><<<(unsigned)blocks, 256, smem, stream>>>((const T*)in, (const T*)wp, bias, (T*)out, a.N, a.IH, a.IW, a.act);
+            convT_k4s2_to1_kernel<T><<<(unsigned)blocks, 128, smem, stream>>>((const T*)in, (const T*)wp, bias, (T*)out, a.N, a.IH, a.IW, a.act);
         });
         rc = launched("convT_k4s2_to1_kernel");
     } else if (a.OC <= 4 && a.IC % 64 == 0) {
