@@ -153,6 +153,71 @@ __global__ void __launch_bounds__(128) convT_k4s2_to1_kernel(const T* __restrict
     }
 }
 
+// ---- first DCGAN encoder layer: Conv k4 s2 p1, IC <= 8 input channels -> OC (multiple of 8, <= 128) (conv.py:119).
+// A block stages the (2*8+2) x (2*32+2) input patch of an 8x32 output tile and the whole filter in shared
+// memory (fp32); each thread owns one output pixel, holds its 16*IC window values in registers and walks over
+// the output channels 8 at a time with broadcast LDS.128 weight reads: no global-memory latency in the FMA loop.
+template <typename T, int IC>
+__global__ void __launch_bounds__(256) conv_k4s2_fewin_kernel(const T* __restrict__ in, const T* __restrict__ wp, const float* __restrict__ bias,
+                                                              T* __restrict__ out, int N, int H, int W, int OC, int act) {
+    constexpr int TH = 8, TW = 32, PH = 2 * TH + 2, PW = 2 * TW + 2;
+    extern __shared__ __align__(16) float fsm[];
+    float* wsm = fsm;                              // [16][IC][OC]
+    float* patch = fsm + 16 * IC * OC;             // [PH][PW][IC]
+    const int P = H / 2, Q = W / 2;
+    const int tiles_w = (Q + TW - 1) / TW, tiles_h = (P + TH - 1) / TH;
+    int b = blockIdx.x;
+    const int tw = b % tiles_w; b /= tiles_w;
+    const int th = b % tiles_h;
+    const int n = b / tiles_h;
+    const int p0 = th * TH, q0 = tw * TW;
+    for (int i = threadIdx.x; i < 16 * IC * OC; i += 256) {
+        const int oc = i % OC, c = (i / OC) % IC, tap = i / (OC * IC);
+        wsm[i] = ld<T>(wp + ((long long)oc * 16 + tap) * IC + c);
+    }
+    for (int i = threadIdx.x; i < PH * PW * IC; i += 256) {
+        const int c = i % IC, px = i / IC;
+        const int ih = 2 * p0 - 1 + px / PW, iw = 2 * q0 - 1 + px % PW;
+        patch[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? ld<T>(in + (((long long)n * H + ih) * W + iw) * IC + c) : 0.f;
+    }
+    __syncthreads();
+    const int li = threadIdx.x / TW, lj = threadIdx.x % TW;
+    const int p = p0 + li, q = q0 + lj;
+    float x[16 * IC];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int c = 0; c < IC; ++c) x[(r * 4 + s) * IC + c] = patch[((2 * li + r) * PW + 2 * lj + s) * IC + c];
+    if (p >= P || q >= Q) return;
+    T* dst = out + (((long long)n * P + p) * Q + q) * OC;
+    for (int o8 = 0; o8 < OC; o8 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[o8 + j] : 0.f;
+#pragma unroll
+        for (int kv = 0; kv < 16 * IC; ++kv) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wsm + kv * OC + o8);
+            const float4 w1 = *reinterpret_cast<const float4*>(wsm + kv * OC + o8 + 4);
+            acc[0] = fmaf(x[kv], w0.x, acc[0]); acc[1] = fmaf(x[kv], w0.y, acc[1]);
+            acc[2] = fmaf(x[kv], w0.z, acc[2]); acc[3] = fmaf(x[kv], w0.w, acc[3]);
+            acc[4] = fmaf(x[kv], w1.x, acc[4]); acc[5] = fmaf(x[kv], w1.y, acc[5]);
+            acc[6] = fmaf(x[kv], w1.z, acc[6]); acc[7] = fmaf(x[kv], w1.w, acc[7]);
+        }
+        st4<T>(dst + o8, make_float4(act_fwd(acc[0], act), act_fwd(acc[1], act), act_fwd(acc[2], act), act_fwd(acc[3], act)));
+        st4<T>(dst + o8 + 4, make_float4(act_fwd(acc[4], act), act_fwd(acc[5], act), act_fwd(acc[6], act), act_fwd(acc[7], act)));
+    }
+}
+
+template <typename T, int IC>
+static void launch_fewin(const ThinArgs& a, const T* in, const T* wp, const float* bias, T* out, cudaStream_t stream) {
+    const int smem = (16 * IC * a.OC + 18 * 66 * IC) * (int)sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(conv_k4s2_fewin_kernel<T, IC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const long long blocks = (long long)a.N * cdiv(a.OH, 8) * cdiv(a.OW, 32);
+    conv_k4s2_fewin_kernel<T, IC><<<(unsigned)blocks, 256, smem, stream>>>(in, wp, bias, out, a.N, a.IH, a.IW, a.OC, a.act);
+}
+
 // ---- few INPUT channels (IC <= 8), OC % 8 == 0: one thread = one output pixel x 8 output channels.
 // weights staged in shared memory as fp32 [tap][c][oc]
 template <typename T>
@@ -272,6 +337,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(vs_conv_geom g, const T
     for (long long mt = m0; mt < m1; mt += TP) {
         __syncthreads();
         // stage: TP pixels x R*R taps, one (pixel, tap) pair per thread iteration
+#pragma unroll
         for (int i = threadIdx.x; i < TP * RR * RR; i += 256) {
             const int px = i / (RR * RR), tap = i - px * (RR * RR);
             const long long m = mt + px;
@@ -293,10 +359,17 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(vs_conv_geom g, const T
             for (int c = 0; c < CC; ++c) gs[px][tap * CC + c] = v[c];
         }
         __syncthreads();
-        for (int px = pl; px < TP; px += 4) {
-            const long long m = mt + px;
-            if (m >= m1) break;
-            const float v = ld<T>(small_ + m * g.K + k);
+        // all 16 loads of this thread's pixels are issued before the first FMA (the loop is latency-bound otherwise)
+        float xv[TP / 4];
+#pragma unroll
+        for (int q = 0; q < TP / 4; ++q) {
+            const long long m = mt + pl + 4 * q;
+            xv[q] = m < m1 ? ld<T>(small_ + m * g.K + k) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < TP / 4; ++q) {
+            const int px = pl + 4 * q;
+            const float v = xv[q];
 #pragma unroll
             for (int i4 = 0; i4 < NVP / 4; ++i4) {
                 const float4 b = *reinterpret_cast<const float4*>(&gs[px][i4 * 4]);
@@ -397,6 +470,21 @@ int conv_forward_thin(const vs_conv_geom* g, int mode, const void* in, const voi
             }
         });
         rc = launched("thin_out_kernel");
+    } else if (!a.transposed && a.IC <= 8 && a.OC % 8 == 0 && a.OC <= 128 && a.R == 4 && a.S == 4 && a.stride == 2 && a.pad == 1 &&
+               a.IH == 2 * a.OH && a.IW == 2 * a.OW && (16 * a.IC * a.OC + 18 * 66 * a.IC) * 4 <= 160 * 1024) {
+        VS_DISPATCH_DTYPE(g->dtype, T, {
+            switch (a.IC) {
+                case 1: launch_fewin<T, 1>(a, (const T*)in, (const T*)wp, bias, (T*)out, stream); break;
+                case 2: launch_fewin<T, 2>(a, (const T*)in, (const T*)wp, bias, (T*)out, stream); break;
+                case 3: launch_fewin<T, 3>(a, (const T*)in, (const T*)wp, bias, (T*)out, stream); break;
+                case 4: launch_fewin<T, 4>(a, (const T*)in, (const T*)wp, bias, (T*)out, stream); break;
+                case 5: launch_fewin<T, 5>(a, (const T*)in, (const T*)wp, bias, (T*)out, stream); break;
+                case 6: launch_fewin<T, 6>(a, (const T*)in, (const T*)wp, bias, (T*)out, stream); break;
+                case 7: launch_fewin<T, 7>(a, (const T*)in, (const T*)wp, bias, (T*)out, stream); break;
+                default: launch_fewin<T, 8>(a, (const T*)in, (const T*)wp, bias, (T*)out, stream); break;
+            }
+        });
+        rc = launched("conv_k4s2_fewin_kernel");
     } else if (a.R * a.S * a.IC <= 16 && a.OC == 64 && pixels < 4000000000LL) {
         long long blocks = cdiv(pixels, 128);
         if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
