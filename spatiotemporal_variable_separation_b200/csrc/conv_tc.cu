@@ -28,7 +28,7 @@ struct TcParams {
     int tiles_w, tiles_h, tiles_n, n_tiles, classes, total_tiles;
     int IC, kchunks, ntaps;
     int in_sh, in_sw;         // class-grid -> input coordinate multiplier
-    int act, has_bias, partial;
+    int act, has_bias, partial, n_per_group;
     signed char dh[TC_MAX_CLASSES][TC_MAX_TAPS], dw[TC_MAX_CLASSES][TC_MAX_TAPS];
     unsigned char wtap[TC_MAX_CLASSES][TC_MAX_TAPS];
     unsigned char ca[TC_MAX_CLASSES], cb[TC_MAX_CLASSES];
@@ -114,7 +114,7 @@ template <int BN, int STAGES>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 2 * 4 /*tile statistics*/;
     static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
 };
 
@@ -125,6 +125,23 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
 
+// Column sums over the 32 lanes (= 32 accumulator rows) of a warp for 32 columns at once: butterfly in which every
+// step halves the number of live values per lane (31 shuffles instead of 32 x 5).  On return v[0] is the sum over
+// all lanes of column `lane`.
+__device__ __forceinline__ float warp_transpose_sum32(float* v, int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float give = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+        }
+    }
+    return v[0];
+}
+
 // Persistent: every CTA walks a strided list of (pixel tile, output-channel tile, parity class) work items.
 // The TMA producer and the MMA issuer run ahead across tile boundaries (one smem ring for the whole kernel);
 // two TMEM accumulator stages let tile i+1's MMAs overlap tile i's epilogue.
@@ -132,7 +149,8 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__ CUtensorMap map_a,
                                                          const __grid_constant__ CUtensorMap map_b,
                                                          const __grid_constant__ TcParams p,
-                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                         double* __restrict__ stats) {
     using S = TcSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -142,6 +160,7 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
     uint64_t* tmem_full = bars + 2 * STAGES;        // [2]
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* sstat = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);      // [BN][2] per-tile column sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.ntaps * p.kchunks;
@@ -155,6 +174,7 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -248,21 +268,35 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
                             dst[c0 + c] = __float2bfloat16_rn(act_fwd(x, p.act));
                         }
                     }
-                } else if (ok) {
+                } else {
+                    float xs[32];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        uint32_t pk[4];
+                    for (int c = 0; c < 32; ++c) {
+                        float x = __uint_as_float(r[c]);
+                        if (p.has_bias) x += __ldg(bias + n0 + c0 + c);
+                        xs[c] = x;
+                    }
+                    if (ok) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int c = v * 8 + e * 2;
-                            float x0 = __uint_as_float(r[c]), x1 = __uint_as_float(r[c + 1]);
-                            if (p.has_bias) { x0 += __ldg(bias + n0 + c0 + c); x1 += __ldg(bias + n0 + c0 + c + 1); }
-                            x0 = act_fwd(x0, p.act);
-                            x1 = act_fwd(x1, p.act);
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
-                            pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                        for (int v = 0; v < 4; ++v) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = v * 8 + e * 2;
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(act_fwd(xs[c], p.act), act_fwd(xs[c + 1], p.act));
+                                pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                            }
+                            *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
-                        *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    if (stats != nullptr) {
+                        // BatchNorm batch statistics of the fp32 accumulator (+bias), fused: 32 rows x 32 columns per warp
+                        float sq[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) { xs[c] = ok ? xs[c] : 0.f; sq[c] = xs[c] * xs[c]; }
+                        const float s1 = warp_transpose_sum32(xs, lane), s2 = warp_transpose_sum32(sq, lane);
+                        atomicAdd(&sstat[(c0 + lane) * 2], s1);
+                        atomicAdd(&sstat[(c0 + lane) * 2 + 1], s2);
                     }
                 }
             }
@@ -270,6 +304,18 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (stats != nullptr) {
+                // the four epilogue warps have added their 32-row partials: one fp64 atomic per column and tile
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int g = b0 / p.n_per_group;            // a tile never straddles BatchNorm groups (checked by the host)
+                const int t = threadIdx.x - 64;              // 0..127
+                for (int i = t; i < 2 * BN; i += 128) {
+                    const int col = n0 + (i >> 1);
+                    if (col < p.OC) atomicAdd(&stats[((long long)g * p.OC + col) * 2 + (i & 1)], (double)sstat[i]);
+                    sstat[i] = 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
         }
     }
     __syncthreads();
@@ -344,7 +390,7 @@ static bool tc_disabled() {
 
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const float* bias, void* out,
-                     int classes, cudaStream_t stream) {
+                     int classes, double* stats, cudaStream_t stream) {
     using S = TcSmem<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -358,7 +404,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     q.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * q.n_tiles * classes;
     const int resident = 2 * num_sms();                     // __launch_bounds__(192, 2)
     const int grid = q.total_tiles < resident ? q.total_tiles : resident;
-    tc_conv_kernel<BN, STAGES><<<grid, 192, S::TOTAL, stream>>>(ma, mb, q, bias, (__nv_bfloat16*)out);
+    tc_conv_kernel<BN, STAGES><<<grid, 192, S::TOTAL, stream>>>(ma, mb, q, bias, (__nv_bfloat16*)out, stats);
     return launched("tc_conv_kernel");
 }
 
@@ -434,10 +480,13 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
-    int rc = BN == 128 ? launch_tc<128, 3>(ma, mb, p, bias, out, classes, stream)
-                       : launch_tc<64, 4>(ma, mb, p, bias, out, classes, stream);
+    // statistics are fused into the epilogue when every 128-pixel tile lies inside one BatchNorm group
+    p.n_per_group = g->N / g->groups;
+    const bool fuse_stats = stats != nullptr && !p.partial && (p.n_per_group % p.NT) == 0;
+    int rc = BN == 128 ? launch_tc<128, 3>(ma, mb, p, bias, out, classes, fuse_stats ? stats : nullptr, stream)
+                       : launch_tc<64, 4>(ma, mb, p, bias, out, classes, fuse_stats ? stats : nullptr, stream);
     if (rc) return rc;
-    if (stats != nullptr) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
+    if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
     if (stats != nullptr) {
         const long long rows = (long long)g->N * OH * OW, rpg = rows / g->groups;
         const int cx = (int)cdiv(OC, 64);
