@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== kernels" ; timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu --tb=line 2>&1 | tail -8 | tee gpurun_out/test_kernels.log
+echo "== kernels" ; timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu --tb=line 2>&1 | tail -25 | tee gpurun_out/test_kernels.log
 echo "== step" ; timeout 1200 python -m pytest tests/test_step_gpu.py -q -m gpu --tb=short 2>&1 | tail -15 | tee gpurun_out/test_step.log
 echo "== launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py > gpurun_out/prof.log 2>&1

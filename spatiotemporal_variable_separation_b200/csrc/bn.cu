@@ -238,12 +238,21 @@ __global__ void __launch_bounds__(256) bn_act_fwd_col_kernel(const T* __restrict
     float mu[W], is[W], ga[W], be[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
-    for (long long r = r0 + rl; r < r1; r += pl.rows_per_iter) {
-        float v[W];
+    // two independent rows in flight per thread
+    for (long long r = r0 + rl; r < r1; r += 2 * pl.rows_per_iter) {
+        const long long rb = r + pl.rows_per_iter;
+        const bool has_b = rb < r1;
+        float v[W], v2[W];
         Vec<T>::load(y + r * C + c, v);
+        if (has_b) Vec<T>::load(y + rb * C + c, v2);
 #pragma unroll
         for (int k = 0; k < W; ++k) v[k] = act_fwd(ga[k] * ((v[k] - mu[k]) * is[k]) + be[k], act);
         Vec<T>::store(out + r * C + c, v);
+        if (has_b) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) v2[k] = act_fwd(ga[k] * ((v2[k] - mu[k]) * is[k]) + be[k], act);
+            Vec<T>::store(out + rb * C + c, v2);
+        }
     }
 }
 
@@ -262,10 +271,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_col_kernel(const T* __restri
         m1[k] = train ? (float)sums[((long long)g * C + c + k) * 2] * inv_count : 0.f;
         m2[k] = train ? (float)sums[((long long)g * C + c + k) * 2 + 1] * inv_count : 0.f;
     }
-    for (long long r = r0 + rl; r < r1; r += pl.rows_per_iter) {
-        float v[W], d[W];
+    for (long long r = r0 + rl; r < r1; r += 2 * pl.rows_per_iter) {
+        const long long rb = r + pl.rows_per_iter;
+        const bool has_b = rb < r1;
+        float v[W], d[W], v2[W], d2[W];
         Vec<T>::load(y + r * C + c, v);
         Vec<T>::load(dout + r * C + c, d);
+        if (has_b) { Vec<T>::load(y + rb * C + c, v2); Vec<T>::load(dout + rb * C + c, d2); }
 #pragma unroll
         for (int k = 0; k < W; ++k) {
             const float xh = (v[k] - mu[k]) * is[k];
@@ -273,6 +285,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_col_kernel(const T* __restri
             d[k] = ga[k] * is[k] * (dz - m1[k] - xh * m2[k]);
         }
         Vec<T>::store(dy + r * C + c, d);
+        if (has_b) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                const float xh = (v2[k] - mu[k]) * is[k];
+                const float dz = d2[k] * act_grad_from_in(ga[k] * xh + be[k], act);
+                d2[k] = ga[k] * is[k] * (dz - m1[k] - xh * m2[k]);
+            }
+            Vec<T>::store(dy + rb * C + c, d2);
+        }
     }
 }
 

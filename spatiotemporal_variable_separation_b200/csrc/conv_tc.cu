@@ -20,6 +20,7 @@
 namespace vs {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_MAX_TAPS = 25, TC_MAX_CLASSES = 4;
+constexpr int TC_EPI_WARPS = 8, TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 
 struct TcParams {
     int N, OH, OW, OC;
@@ -146,7 +147,7 @@ __device__ __forceinline__ float warp_transpose_sum32(float* v, int lane) {
 // The TMA producer and the MMA issuer run ahead across tile boundaries (one smem ring for the whole kernel);
 // two TMEM accumulator stages let tile i+1's MMAs overlap tile i's epilogue.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_constant__ CUtensorMap map_a,
                                                          const __grid_constant__ CUtensorMap map_b,
                                                          const __grid_constant__ TcParams p,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
         prefetch_tmap(&map_a);
         prefetch_tmap(&map_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -239,8 +240,11 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
             }
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: warps 2..9.  A warp may only touch the TMEM lane quarter (warp % 4); the two warps that share a
+        // quarter split the accumulator columns =====
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int COLS_PER_WARP = BN / (TC_EPI_WARPS / 4);
         const int m = q * 32 + lane;             // tile-local pixel (TMEM lane)
         const int w = m % p.WT, h = (m / p.WT) % p.HT, n = m / (p.WT * p.HT);
         int lt = 0;
@@ -254,28 +258,23 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
             mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-                if (ok && p.partial) {
-                    // OC not a multiple of the tile or rows not 16-byte aligned: predicated scalar stores
+                // one coalesced bias load per chunk, broadcast by shuffle (instead of 32 loads per thread); the
+                // shuffles are executed by all lanes before any per-lane predicate
+                const float bias_l = (p.has_bias && n0 + c0 + lane < p.OC) ? __ldg(bias + n0 + c0 + lane) : 0.f;
+                float xs[32];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int oc = n0 + c0 + c;
-                        if (oc < p.OC) {
-                            float x = __uint_as_float(r[c]);
-                            if (p.has_bias) x += __ldg(bias + oc);
-                            dst[c0 + c] = __float2bfloat16_rn(act_fwd(x, p.act));
-                        }
+                for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                if (p.partial) {
+                    // OC not a multiple of the tile or rows not 16-byte aligned: predicated scalar stores
+                    if (ok) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (n0 + c0 + c < p.OC) dst[c0 + c] = __float2bfloat16_rn(act_fwd(xs[c], p.act));
                     }
                 } else {
-                    float xs[32];
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        float x = __uint_as_float(r[c]);
-                        if (p.has_bias) x += __ldg(bias + n0 + c0 + c);
-                        xs[c] = x;
-                    }
                     if (ok) {
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
@@ -283,7 +282,8 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const int c = v * 8 + e * 2;
-                                __nv_bfloat162 b2 = __floats2bfloat162_rn(act_fwd(xs[c], p.act), act_fwd(xs[c + 1], p.act));
+                                __nv_bfloat162 b2 = p.act == VS_ACT_NONE ? __floats2bfloat162_rn(xs[c], xs[c + 1])
+                                                                         : __floats2bfloat162_rn(act_fwd(xs[c], p.act), act_fwd(xs[c + 1], p.act));
                                 pk[e] = *reinterpret_cast<uint32_t*>(&b2);
                             }
                             *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -291,10 +291,13 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
                     }
                     if (stats != nullptr) {
                         // BatchNorm batch statistics of the fp32 accumulator (+bias), fused: 32 rows x 32 columns per warp
-                        float sq[32];
+                        float wk[32];
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) { xs[c] = ok ? xs[c] : 0.f; sq[c] = xs[c] * xs[c]; }
-                        const float s1 = warp_transpose_sum32(xs, lane), s2 = warp_transpose_sum32(sq, lane);
+                        for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] : 0.f;
+                        const float s1 = warp_transpose_sum32(wk, lane);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] * xs[c] : 0.f;
+                        const float s2 = warp_transpose_sum32(wk, lane);
                         atomicAdd(&sstat[(c0 + lane) * 2], s1);
                         atomicAdd(&sstat[(c0 + lane) * 2 + 1], s2);
                     }
@@ -306,15 +309,15 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (stats != nullptr) {
                 // the four epilogue warps have added their 32-row partials: one fp64 atomic per column and tile
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
                 const int g = b0 / p.n_per_group;            // a tile never straddles BatchNorm groups (checked by the host)
-                const int t = threadIdx.x - 64;              // 0..127
-                for (int i = t; i < 2 * BN; i += 128) {
+                const int t = threadIdx.x - 64;              // 0 .. 32*TC_EPI_WARPS-1
+                for (int i = t; i < 2 * BN; i += 32 * TC_EPI_WARPS) {
                     const int col = n0 + (i >> 1);
                     if (col < p.OC) atomicAdd(&stats[((long long)g * p.OC + col) * 2 + (i & 1)], (double)sstat[i]);
                     sstat[i] = 0.f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
             }
         }
     }
@@ -324,40 +327,6 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
         tmem_dealloc<2 * BN>(tmem_base);
     }
 #undef VS_TC_DECODE
-}
-
-// per-(group, channel) sum / sum of squares of a bf16 [rows, C] matrix (BatchNorm batch statistics of
-// the tensor-core path's output; the CUDA-core path fuses them into its epilogue)
-__global__ void colstats_kernel(const __nv_bfloat16* __restrict__ y, int C, long long rpg, int chunks,
-                                double* __restrict__ stats) {
-    __shared__ double r1[8][65], r2[8][65];
-    const int c = blockIdx.x * 64 + threadIdx.x * 2;     // 32 threads x 2 channels
-    const int g = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
-    const long long per = (rpg + chunks - 1) / chunks;
-    const long long r0 = (long long)g * rpg + (long long)chunk * per;
-    long long r_end = r0 + per;
-    if (r_end > (long long)(g + 1) * rpg) r_end = (long long)(g + 1) * rpg;
-    // fp64 running sums (the kernel is HBM-bound; BatchNorm variances are differences of these sums)
-    double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;
-    if (c < C)
-        for (long long r = r0 + threadIdx.y; r < r_end; r += 8) {
-            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(y + r * C + c);
-            const float2 f = __bfloat1622float2(v);
-            s1a += f.x; s2a += (double)f.x * f.x; s1b += f.y; s2b += (double)f.y * f.y;
-        }
-    r1[threadIdx.y][threadIdx.x * 2] = s1a; r1[threadIdx.y][threadIdx.x * 2 + 1] = s1b;
-    r2[threadIdx.y][threadIdx.x * 2] = s2a; r2[threadIdx.y][threadIdx.x * 2 + 1] = s2b;
-    __syncthreads();
-    if (threadIdx.y < 2) {
-        const int cc = blockIdx.x * 64 + threadIdx.x * 2 + threadIdx.y;
-        if (cc < C) {
-            double t1 = 0.0, t2 = 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { t1 += r1[k][threadIdx.x * 2 + threadIdx.y]; t2 += r2[k][threadIdx.x * 2 + threadIdx.y]; }
-            atomicAdd(&stats[((long long)g * C + cc) * 2], t1);
-            atomicAdd(&stats[((long long)g * C + cc) * 2 + 1], t2);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -402,9 +371,9 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     q.classes = classes;
     q.n_tiles = (int)cdiv(p.OC, BN);
     q.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * q.n_tiles * classes;
-    const int resident = 2 * num_sms();                     // __launch_bounds__(192, 2)
+    const int resident = 2 * num_sms();                     // __launch_bounds__(TC_THREADS, 2)
     const int grid = q.total_tiles < resident ? q.total_tiles : resident;
-    tc_conv_kernel<BN, STAGES><<<grid, 192, S::TOTAL, stream>>>(ma, mb, q, bias, (__nv_bfloat16*)out, stats);
+    tc_conv_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, q, bias, (__nv_bfloat16*)out, stats);
     return launched("tc_conv_kernel");
 }
 
@@ -487,16 +456,6 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
                        : launch_tc<64, 4>(ma, mb, p, bias, out, classes, fuse_stats ? stats : nullptr, stream);
     if (rc) return rc;
     if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
-    if (stats != nullptr) {
-        const long long rows = (long long)g->N * OH * OW, rpg = rows / g->groups;
-        const int cx = (int)cdiv(OC, 64);
-        long long chunks = cdiv(4LL * num_sms(), (long long)cx * g->groups);
-        if (chunks > cdiv(rpg, 64)) chunks = cdiv(rpg, 64);
-        if (chunks < 1) chunks = 1;
-        dim3 grid(cx, (unsigned)(g->groups * chunks)), block(32, 8);
-        colstats_kernel<<<grid, block, 0, stream>>>((const __nv_bfloat16*)out, OC, rpg, (int)chunks, stats);
-        rc = launched("colstats_kernel");
-    }
     return rc;
 }
 

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_fwd_kernel(float* __restri
             if (xin) for (int i = threadIdx.x; i < nrow * d; i += RO_THREADS) xin[(slot * B + row0) * d + i] = x[i];
             dense_rows<RB, true, 4>(w.w1[j], w.b1[j], h, d, x, d, u, h);
             __syncthreads();
-            dense_rows<RB, true, 4>(w.w2[j], w.b2[j], h, h, u, h, v, h);
+            dense_rows<RB, true, 8>(w.w2[j], w.b2[j], h, h, u, h, v, h);
             __syncthreads();
             dense_rows<RB, false, 2>(w.w3[j], w.b3[j], d, h, v, h, rr, d);
             __syncthreads();
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_bwd_kernel(float* __restri
             }
             __syncthreads();
             // d(a1) = (d(a2) W2) * [h1 > 0]
-            dense_rows<RB, false, 4>(w.w2[j], nullptr, h, h, b, h, a, h);          // w2 = W2^T [h][h]
+            dense_rows<RB, false, 8>(w.w2[j], nullptr, h, h, b, h, a, h);          // w2 = W2^T [h][h]
             __syncthreads();
             for (int i = threadIdx.x; i < nrow * h; i += RO_THREADS) {
                 const float hv = hidden[(hslot(j, 0, t) * B + row0) * h + i];
