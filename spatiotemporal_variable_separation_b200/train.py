@@ -52,7 +52,7 @@ def ae_loss(cond, target, sep_net, nt_cond, offset, skipco, t_random=None):
 
 
 def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, lamb_s, lamb_t, lamb_pred,
-                average_tloss=False, t_random=None, reducer=None):
+                average_tloss=False, t_random=None, reducer=None, overlap_encoders=True):
     """One forward pass of the training objective.  ``full_data`` = cat(cond, target) [B,L,C,H,W] fp32.
 
     Returns dict(total, ae, s, pred, t, forecasts, t_codes); ``total.backward()`` then produces every
@@ -63,9 +63,22 @@ def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, l
     B, n_frames = full_data.shape[0], full_data.shape[1]
     if t_random is None:
         t_random = draw_t_random(nt_cond, n_frames, offset)
-    # ---- encoders: two calls each, batched as two BatchNorm groups
-    s_both = sep_net.Es.encode(sep_net.encoder_input(full_data, [0, n_frames - nt_cond]), 2, skipco)
+    # ---- encoders: two calls each, batched as two BatchNorm groups.  Es and Et are independent until the decoder, and
+    # their launches (and the 64-CTA latent rollout that follows Et) each fill only part of the GPU, so the content
+    # encoder runs on a side stream next to the dynamic encoder + rollout; autograd replays the same split in backward.
+    side = _side_stream(full_data) if overlap_encoders else None
+    if side is not None:
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            s_both = sep_net.Es.encode(sep_net.encoder_input(full_data, [0, n_frames - nt_cond]), 2, skipco)
+    else:
+        s_both = sep_net.Es.encode(sep_net.encoder_input(full_data, [0, n_frames - nt_cond]), 2, skipco)
     t_both = sep_net.Et.encode(sep_net.encoder_input(full_data, [t_random - nt_cond, 0]), 2)
+    if side is not None:
+        main.wait_stream(side)
+        for t in ([s_both[0]] + list(s_both[1]) if skipco else [s_both]):
+            t.record_stream(main)                                     # produced on `side`, consumed on `main`
     if skipco:
         s_code, s_skips = s_both
         s_old, s_new = s_code[:B], s_code[B:]
@@ -98,6 +111,19 @@ def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, l
     terms = ops.loss_terms(spec, tensors)
     return dict(total=terms[4], ae=terms[0], s=terms[1], pred=terms[2], t=terms[3], terms=terms,
                 forecasts=forecasts, t_codes=t_codes, t_random=t_random)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(t):
+    """One persistent side stream per device (None on CPU tensors, i.e. under the test emulator)."""
+    if not t.is_cuda:
+        return None
+    dev = t.device.index
+    if dev not in _SIDE_STREAMS:
+        _SIDE_STREAMS[dev] = torch.cuda.Stream(device=t.device)
+    return _SIDE_STREAMS[dev]
 
 
 def _loss_operand(h):
