@@ -70,7 +70,8 @@ class ClockSampler:
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].startswith('Active') for r in self.rows)]
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'reasons': reasons, 'samples': len(sm),
+                'window': 'warm-up + timed steps of the device-resident run (GPU under the same load throughout)'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -291,7 +292,12 @@ def run_ours(args, cfg):
         return ms, losses
 
     with ClockSampler(local) as clocks:
+        time.sleep(0.3)                       # let nvidia-smi start streaming before the load begins
         ms, _ = timed(args.warmup, args.steps, False, 0)
+        if len(clocks.rows) < 3:              # very short runs: keep the GPU under the same load until 3 samples exist
+            t_end = time.time() + 2.0
+            while len(clocks.rows) < 3 and time.time() < t_end:
+                timed(0, max(args.steps, 10), False, 0)
     ms_e2e, losses = timed(max(3, args.warmup // 2), args.steps, True, args.steps + args.warmup)
     value = world * B * args.steps / (ms * 1e-3)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)

@@ -323,17 +323,21 @@ template <typename T, int RR, int CC>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(vs_conv_geom g, const T* __restrict__ small_, const T* __restrict__ big,
                                                          float* __restrict__ dw, long long rows_per_block) {
     constexpr int NV = RR * RR * CC, NVP = (NV + 3) / 4 * 4, TP = 64;
+    constexpr int KPT = NVP <= 32 ? 2 : 1;            // channels per thread (register budget: KPT * NVP accumulators)
+    constexpr int KT = 64 / KPT, PL = 256 / KT;       // channel threads, pixel lanes
     __shared__ __align__(16) float gs[TP][NVP];
-    __shared__ float red[4][64];
-    const int kl = threadIdx.x & 63, pl = threadIdx.x >> 6;
+    __shared__ float red[PL][64];
+    const int kl = (threadIdx.x % KT) * KPT, pl = threadIdx.x / KT;
     const int k = blockIdx.y * 64 + kl;
     const long long M = (long long)g.N * g.P * g.Q;
     const long long m0 = (long long)blockIdx.x * rows_per_block;
     const long long m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
     const unsigned PQ = (unsigned)g.P * g.Q;
-    float acc[NVP];
+    float acc[KPT][NVP];
 #pragma unroll
-    for (int i = 0; i < NVP; ++i) acc[i] = 0.f;
+    for (int j = 0; j < KPT; ++j)
+#pragma unroll
+        for (int i = 0; i < NVP; ++i) acc[j][i] = 0.f;
     for (long long mt = m0; mt < m1; mt += TP) {
         __syncthreads();
         // stage: TP pixels x R*R taps, one (pixel, tap) pair per thread iteration
@@ -359,36 +363,42 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(vs_conv_geom g, const T
             for (int c = 0; c < CC; ++c) gs[px][tap * CC + c] = v[c];
         }
         __syncthreads();
-        // all 16 loads of this thread's pixels are issued before the first FMA (the loop is latency-bound otherwise)
-        float xv[TP / 4];
+        // all loads of this thread's pixels are issued before the first FMA (the loop is latency-bound otherwise)
+        float xv[TP / PL][KPT];
 #pragma unroll
-        for (int q = 0; q < TP / 4; ++q) {
-            const long long m = mt + pl + 4 * q;
-            xv[q] = m < m1 ? ld<T>(small_ + m * g.K + k) : 0.f;
+        for (int q = 0; q < TP / PL; ++q) {
+            const long long m = mt + pl + PL * q;
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) xv[q][j] = m < m1 ? ld<T>(small_ + m * g.K + k + j) : 0.f;
         }
 #pragma unroll
-        for (int q = 0; q < TP / 4; ++q) {
-            const int px = pl + 4 * q;
-            const float v = xv[q];
+        for (int q = 0; q < TP / PL; ++q) {
+            const int px = pl + PL * q;
 #pragma unroll
             for (int i4 = 0; i4 < NVP / 4; ++i4) {
                 const float4 b = *reinterpret_cast<const float4*>(&gs[px][i4 * 4]);
-                acc[i4 * 4 + 0] = fmaf(v, b.x, acc[i4 * 4 + 0]);
-                acc[i4 * 4 + 1] = fmaf(v, b.y, acc[i4 * 4 + 1]);
-                acc[i4 * 4 + 2] = fmaf(v, b.z, acc[i4 * 4 + 2]);
-                acc[i4 * 4 + 3] = fmaf(v, b.w, acc[i4 * 4 + 3]);
+#pragma unroll
+                for (int j = 0; j < KPT; ++j) {
+                    acc[j][i4 * 4 + 0] = fmaf(xv[q][j], b.x, acc[j][i4 * 4 + 0]);
+                    acc[j][i4 * 4 + 1] = fmaf(xv[q][j], b.y, acc[j][i4 * 4 + 1]);
+                    acc[j][i4 * 4 + 2] = fmaf(xv[q][j], b.z, acc[j][i4 * 4 + 2]);
+                    acc[j][i4 * 4 + 3] = fmaf(xv[q][j], b.w, acc[j][i4 * 4 + 3]);
+                }
             }
         }
     }
-    // reduce the 4 pixel lanes through shared memory, then one atomic per (k, c, tap)
+    // reduce the pixel lanes through shared memory, then one atomic per (k, c, tap)
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         __syncthreads();
-        red[pl][kl] = acc[i];
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) red[pl][kl + j] = acc[j][i];
         __syncthreads();
-        if (pl == 0) {
-            const float t = red[0][kl] + red[1][kl] + red[2][kl] + red[3][kl];
-            atomicAdd(&dw[((long long)k * CC + (i % CC)) * (RR * RR) + i / CC], t);
+        if (threadIdx.x < 64) {
+            float t = 0.f;
+#pragma unroll
+            for (int l = 0; l < PL; ++l) t += red[l][threadIdx.x];
+            atomicAdd(&dw[((long long)(blockIdx.y * 64 + threadIdx.x) * CC + (i % CC)) * (RR * RR) + i / CC], t);
         }
     }
 }
