@@ -355,19 +355,21 @@ def _shutdown(tr, world):
 
 
 def conv_roofline(tr, dev, draws, dtype):
-    """Average launch duration and algorithmic FLOPs of the convolution-forward entry point (fprop and
-    dgrad of every layer), measured with CUDA events on the launching stream over two extra steps."""
+    """Roofline of the dominant kernel, tc_conv_kernel (tcgen05 tap GEMM: fprop and dgrad of every eligible conv
+    layer).  CUDA events on the launching stream around each vs_conv_forward call of two extra eager steps; only the
+    calls that the library routes to the tensor-core kernel (vs_conv_forward_path == 1) are counted.  Algorithmic
+    FLOPs per launch = 2*N*P*Q*K*C*R*S (for a stride-2 transposed convolution the parity decomposition multiplies no
+    structurally-zero tap, so this is also the executed count)."""
     from spatiotemporal_variable_separation_b200 import _lib
     records = []
     orig = _lib.call
+    lib = _lib.load()
 
     def timed_call(name, *a):
-        if name != 'vs_conv_forward':
+        if name != 'vs_conv_forward' or lib.vs_conv_forward_path(a[0], a[1]) != 1:
             return orig(name, *a)
         g = a[0]
         flops = 2.0 * g.N * g.P * g.Q * g.K * g.C * g.R * g.S
-        if a[1] == _lib.TRANSPOSED and g.stride > 1:
-            pass        # parity decomposition skips the structurally-zero taps: algorithmic FLOPs are the same
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         orig(name, *a)
@@ -386,9 +388,15 @@ def conv_roofline(tr, dev, draws, dtype):
         tr.use_graph = use_graph
     tot_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
     tot_flop = sum(f for _, _, f in records)
-    return {'bound': 'tensor', 'kernel': 'vs_conv_forward (fprop + dgrad launches of every conv/linear layer)',
-            'achieved': tot_flop / (tot_ms * 1e-3) / 1e12, 'unit': 'TFLOP/s', 'launches': len(records),
-            'avg_launch_ms': tot_ms / max(len(records), 1), 'traffic': None}
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get('tc_conv_kernel', {}).get('dram_bytes_per_launch')
+    return {'bound': 'tensor', 'kernel': 'tc_conv_kernel (tcgen05 fprop + dgrad launches)',
+            'achieved': tot_flop / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0, 'unit': 'TFLOP/s',
+            'launches': len(records) // 2, 'avg_launch_ms': tot_ms / max(len(records), 1),
+            'flop_per_launch': tot_flop / max(len(records), 1), 'traffic': traffic,
+            'traffic_note': 'avg dram__bytes_read+write per tc_conv_kernel launch from the ncu pass in profiles/ (bytes)'}
 
 
 def main():

@@ -65,6 +65,11 @@ int64_t     vs_launch_count(void);
 int vs_pack_weight(const float* w, void* out, int32_t dtype, int32_t K, int32_t C, int32_t RS, int32_t swap,
                    void* stream);
 
+/* All packed copies of a model in one launch (after the optimizer step).  table: DEVICE array of n rows
+ * { const float* src; void* dst; int32 K, C, RS, swap, dtype, first_block; } (40 bytes, 8-byte aligned), rows ordered
+ * by first_block; row i owns blocks [first_block_i, first_block_{i+1}) of 1024 elements each. */
+int vs_pack_weights_multi(const void* table, int32_t n, int32_t total_blocks, void* stream);
+
 /* ---- convolution / linear -------------------------------------------------------------------
  * replaces: aten::convolution (Conv2d / ConvTranspose2d forward; conv.py:119-123,147-170,258-263,
  * 295-318,327-343,363-417,435,517-533; resnet.py:57-63) and aten::addmm (mlp.py:40, conv.py:124).
@@ -75,6 +80,11 @@ int vs_pack_weight(const float* w, void* out, int32_t dtype, int32_t K, int32_t 
  * (BatchNorm batch statistics fused into the producer; act must then be VS_ACT_NONE). */
 int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* in, const void* wp, const float* bias,
                     void* out, double* stats, void* stream);
+
+/* Which kernel family vs_conv_forward would use for this geometry: 0 = CUDA-core gather GEMM, 1 = tcgen05/TMA tap
+ * GEMM, 2 = thin streaming kernel, -1 = invalid geometry.  Host-only (no launch); used by bench.py to attribute
+ * the measured launch times to the tensor-core kernel for the roofline. */
+int vs_conv_forward_path(const vs_conv_geom* g, int32_t mode);
 
 /* replaces: aten::convolution_backward, weight part.  dw[K][C][R][S] (fp32, torch layout) +=
  * sum over pixels of small[n,p,q,k] * big[n, p*stride-pad+r, q*stride-pad+s, c].

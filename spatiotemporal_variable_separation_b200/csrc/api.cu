@@ -87,6 +87,20 @@ extern "C" int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* 
     return conv_forward_simt(g, mode, in, wp, bias, out, stats, as_stream(stream));
 }
 
+// which kernel family vs_conv_forward dispatches this geometry to: 0 = CUDA-core gather GEMM, 1 = tcgen05 tap GEMM,
+// 2 = thin streaming kernel.  Pure host logic (no launch); mirrors the dispatch order above.
+namespace vs {
+int conv_forward_tc_eligible(const vs_conv_geom* g, int mode);
+int conv_forward_thin_eligible(const vs_conv_geom* g, int mode);
+}
+extern "C" int vs_conv_forward_path(const vs_conv_geom* g, int32_t mode) {
+    if (check_geom(g)) return -1;
+    if (mode == VS_CONV_TRANSPOSED && g->C == 1 && g->K == 64 && g->R == 4 && g->stride == 2 && conv_forward_thin_eligible(g, mode)) return 2;
+    if (conv_forward_tc_eligible(g, mode)) return 1;
+    if (conv_forward_thin_eligible(g, mode)) return 2;
+    return 0;
+}
+
 extern "C" int vs_conv_wgrad(const vs_conv_geom* g, const void* small_, const void* big, float* dw, void* stream) {
     if (int rc = check_geom(g)) return rc;
     int rc = conv_wgrad_thin(g, small_, big, dw, as_stream(stream));

@@ -281,6 +281,32 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     }
 }
 
+// all packed weight copies of a model in ONE launch: table rows = {src, dst, K, C, RS, swap, dtype, first_block}
+struct PackEntry { const float* src; void* dst; int K, C, RS, swap, dtype, first_block; };
+__global__ void pack_multi_kernel(const PackEntry* __restrict__ table, int n) {
+    // binary search of the entry that owns this block
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PackEntry e = table[lo];
+    const long long total = (long long)e.K * e.C * e.RS;
+    const long long base = (long long)(blockIdx.x - e.first_block) * 1024;
+    for (int t = threadIdx.x; t < 1024; t += blockDim.x) {
+        const long long i = base + t;
+        if (i >= total) return;
+        const int B = e.swap ? e.K : e.C;
+        const int b = (int)(i % B);
+        const int tap = (int)((i / B) % e.RS);
+        const int a = (int)(i / ((long long)B * e.RS));
+        const int k = e.swap ? b : a, c = e.swap ? a : b;
+        const float v = e.src[((long long)k * e.C + c) * e.RS + tap];
+        if (e.dtype == VS_F32) reinterpret_cast<float*>(e.dst)[i] = v;
+        else reinterpret_cast<__nv_bfloat16*>(e.dst)[i] = __float2bfloat16_rn(v);
+    }
+}
+
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ a, long long rows, int C, float* __restrict__ db,
                               long long rows_per_block) {
@@ -379,6 +405,12 @@ extern "C" int vs_pack_weight(const float* w, void* out, int32_t dtype, int32_t 
     const int blocks = (int)(cdiv(total, 256) < 4096 ? cdiv(total, 256) : 4096);
     VS_DISPATCH_DTYPE(dtype, T, (pack_weight_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(w, (T*)out, K, C, RS, swap)));
     return launched("pack_weight_kernel");
+}
+
+extern "C" int vs_pack_weights_multi(const void* table, int32_t n, int32_t total_blocks, void* stream) {
+    if (n <= 0 || total_blocks <= 0) return 0;
+    pack_multi_kernel<<<(unsigned)total_blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const PackEntry*>(table), n);
+    return launched("pack_multi_kernel");
 }
 
 extern "C" int vs_colsum(const void* a, int32_t dtype, int64_t rows, int32_t C, float* db, void* stream) {

@@ -377,6 +377,17 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     return launched("tc_conv_kernel");
 }
 
+int conv_forward_tc_eligible(const vs_conv_geom* g, int mode) {
+    if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || tc_disabled()) return 0;
+    const bool tr = mode == VS_CONV_TRANSPOSED;
+    const int IC = tr ? g->K : g->C, OH = tr ? g->H : g->P, OW = tr ? g->W : g->Q;
+    const int st = g->stride, ost = tr ? st : 1;
+    if (IC % 64 != 0 || st > 2 || g->R * g->S > TC_MAX_TAPS) return 0;
+    if (OH % ost != 0 || OW % ost != 0) return 0;
+    if (tr && st == 2 && ((g->R % 2) || (g->S % 2))) return 0;      // parity classes with unequal tap counts
+    return 1;
+}
+
 // returns 0 = done, -1 = geometry not eligible (caller falls back), >0 = error
 int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                     double* stats, cudaStream_t stream) {

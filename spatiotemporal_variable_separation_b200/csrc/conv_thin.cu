@@ -445,6 +445,15 @@ int stats_of_output(const vs_conv_geom* g, int dtype, const void* out, long long
     return launched("colstats_any_kernel");
 }
 
+int conv_forward_thin_eligible(const vs_conv_geom* g, int mode) {
+    const bool tr = mode == VS_CONV_TRANSPOSED;
+    const int IC = tr ? g->K : g->C, OC = tr ? g->C : g->K, OH = tr ? g->H : g->P, OW = tr ? g->W : g->Q;
+    if (OH * OW < 256) return 0;
+    if (OC <= 4 && IC % 64 == 0) return 1;
+    if (IC <= 8 && OC % 8 == 0) return 1;
+    return 0;
+}
+
 // returns 0 = done, -1 = not a thin geometry, >0 error
 int conv_forward_thin(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                       double* stats, cudaStream_t stream) {

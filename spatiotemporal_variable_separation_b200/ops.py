@@ -52,7 +52,38 @@ def packed_weight(w, K, C, RS, swap, dtype):
     out = hit[1] if hit is not None else torch.empty(K * C * RS, device=w.device, dtype=dtype)
     L.call('vs_pack_weight', ptr(w), ptr(out), L.dtype_code(out), K, C, RS, int(swap), L.stream())
     cache[key] = (tag, out)
+    if hit is None:
+        _pack_registry.append((w, key, out))
+        _pack_table.clear()
     return out
+
+
+# every (parameter, layout) pair that has ever been packed; lets the optimizer refresh all of them in one launch
+_pack_registry = []
+_pack_table = {}
+
+
+def repack_all():
+    """Refresh every known packed copy with ONE kernel (called by FusedAdam.step after the arena update) and mark
+    them current, so the next step's forward / backward find cache hits instead of ~30 small pack launches."""
+    import struct
+    live = [(w, key, out) for (w, key, out) in _pack_registry if w.is_cuda]
+    if not live:
+        return
+    if 'table' not in _pack_table:
+        rows, first = [], 0
+        for w, (K, C, RS, swap, dtype), out in live:
+            rows.append(struct.pack('<QQiiiiii', w.data_ptr(), out.data_ptr(), K, C, RS, int(swap),
+                                    L.VS_F32 if dtype == torch.float32 else L.VS_BF16, first))
+            first += (K * C * RS + 1023) // 1024
+        blob = torch.frombuffer(bytearray(b''.join(rows)), dtype=torch.uint8).to(live[0][0].device)
+        _pack_table.update(table=blob, n=len(rows), blocks=first, ptrs=[(w.data_ptr(), out.data_ptr()) for w, _, out in live])
+    elif _pack_table['ptrs'] != [(w.data_ptr(), out.data_ptr()) for w, _, out in live]:
+        _pack_table.clear()
+        return repack_all()
+    L.call('vs_pack_weights_multi', ptr(_pack_table['table']), _pack_table['n'], _pack_table['blocks'], L.stream())
+    for w, key, out in live:
+        w.__dict__['_vs_pack'][key] = ((w._version, w.data_ptr(), _pack_epoch), out)
 
 
 ConvCfg = namedtuple('ConvCfg', 'kind K C R S stride pad act groups training has_bn eps momentum flags')

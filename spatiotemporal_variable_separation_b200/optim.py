@@ -59,6 +59,7 @@ class FusedAdam:
         L.call('vs_adam_step', ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.numel,
              self.lr, self.betas[0], self.betas[1], self.eps, float(self.grad_scale), 0, ptr(self.step_dev), L.stream())
         ops.invalidate_packed()
+        ops.repack_all()
 
     def grad_of(self, p):
         return p._vs_grad

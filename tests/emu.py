@@ -61,6 +61,14 @@ def vs_pack_weight(w, out, dtype, K, C, RS, swap, stream):
     _store(out, w3.permute(1, 2, 0) if swap else w3.permute(0, 2, 1))
 
 
+def vs_pack_weights_multi(table, n, total_blocks, stream):
+    import struct
+    raw = bytes(table.numpy().tobytes())
+    for i in range(n):
+        src, dst, K, C, RS, swap, dtype, first = struct.unpack_from('<QQiiiiii', raw, 40 * i)
+        vs_pack_weight(_TENSOR_REGISTRY[src], _TENSOR_REGISTRY[dst], dtype, K, C, RS, swap, None)
+
+
 def _geo(g):
     return {k: getattr(g, k) for k, _ in L.Geom._fields_}
 
@@ -288,13 +296,15 @@ def emu_call(name, *args):
 @contextlib.contextmanager
 def install():
     """Route the package's C-ABI calls to the emulator (CPU tensors allowed) for the duration."""
-    saved = (L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array)
+    from spatiotemporal_variable_separation_b200 import ops
+    saved = (L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array, ops.repack_all)
     L.call, L.stream, L.require_cuda, L.launch_count = emu_call, (lambda: None), (lambda *a: None), (lambda: -1)
     L.pointer_array = _emu_pointer_array
+    ops.repack_all = lambda: None      # the table holds raw device pointers; the emulator repacks lazily per call instead
     try:
         yield
     finally:
-        L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array = saved
+        L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array, ops.repack_all = saved
 
 
 # ---- latent rollout (appended after _TABLE is built: register explicitly) -------------------------
