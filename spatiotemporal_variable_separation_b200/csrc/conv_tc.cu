@@ -267,40 +267,39 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                 float xs[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
-                if (p.partial) {
-                    // OC not a multiple of the tile or rows not 16-byte aligned: predicated scalar stores
+                if (p.partial || n0 + BN > p.OC) {
+                    // tail tile in OC, or rows not 16-byte aligned: predicated scalar stores
                     if (ok) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
                             if (n0 + c0 + c < p.OC) dst[c0 + c] = __float2bfloat16_rn(act_fwd(xs[c], p.act));
                     }
-                } else {
-                    if (ok) {
+                } else if (ok) {
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            uint32_t pk[4];
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t pk[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int c = v * 8 + e * 2;
-                                __nv_bfloat162 b2 = p.act == VS_ACT_NONE ? __floats2bfloat162_rn(xs[c], xs[c + 1])
-                                                                         : __floats2bfloat162_rn(act_fwd(xs[c], p.act), act_fwd(xs[c + 1], p.act));
-                                pk[e] = *reinterpret_cast<uint32_t*>(&b2);
-                            }
-                            *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = v * 8 + e * 2;
+                            __nv_bfloat162 b2 = p.act == VS_ACT_NONE ? __floats2bfloat162_rn(xs[c], xs[c + 1])
+                                                                     : __floats2bfloat162_rn(act_fwd(xs[c], p.act), act_fwd(xs[c + 1], p.act));
+                            pk[e] = *reinterpret_cast<uint32_t*>(&b2);
                         }
+                        *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
-                    if (stats != nullptr) {
-                        // BatchNorm batch statistics of the fp32 accumulator (+bias), fused: 32 rows x 32 columns per warp
-                        float wk[32];
+                }
+                if (stats != nullptr) {
+                    // BatchNorm batch statistics of the fp32 accumulator (+bias), fused: 32 rows x 32 columns per warp
+                    // (columns past OC hold exact zeros: zero-filled weight rows, no bias)
+                    float wk[32];
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] : 0.f;
-                        const float s1 = warp_transpose_sum32(wk, lane);
+                    for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] : 0.f;
+                    const float s1 = warp_transpose_sum32(wk, lane);
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] * xs[c] : 0.f;
-                        const float s2 = warp_transpose_sum32(wk, lane);
-                        atomicAdd(&sstat[(c0 + lane) * 2], s1);
-                        atomicAdd(&sstat[(c0 + lane) * 2 + 1], s2);
-                    }
+                    for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] * xs[c] : 0.f;
+                    const float s2 = warp_transpose_sum32(wk, lane);
+                    atomicAdd(&sstat[(c0 + lane) * 2], s1);
+                    atomicAdd(&sstat[(c0 + lane) * 2 + 1], s2);
                 }
             }
             // this warp's quarter of the accumulator has been read: hand the stage back to the MMA issuer
@@ -382,7 +381,7 @@ int conv_forward_tc_eligible(const vs_conv_geom* g, int mode) {
     const bool tr = mode == VS_CONV_TRANSPOSED;
     const int IC = tr ? g->K : g->C, OH = tr ? g->H : g->P, OW = tr ? g->W : g->Q;
     const int st = g->stride, ost = tr ? st : 1;
-    if (IC % 64 != 0 || st > 2 || g->R * g->S > TC_MAX_TAPS) return 0;
+    if (IC % 8 != 0 || IC < 32 || st > 2 || g->R * g->S > TC_MAX_TAPS) return 0;      // TMA needs a 16-byte channel pitch
     if (OH % ost != 0 || OW % ost != 0) return 0;
     if (tr && st == 2 && ((g->R % 2) || (g->S % 2))) return 0;      // parity classes with unequal tap counts
     return 1;
@@ -396,7 +395,7 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     const int IH = tr ? g->P : g->H, IW = tr ? g->Q : g->W, IC = tr ? g->K : g->C;
     const int OH = tr ? g->H : g->P, OW = tr ? g->W : g->Q, OC = tr ? g->C : g->K;
     const int st = g->stride;
-    if (IC % 64 != 0 || st > 2 || g->R * g->S > TC_MAX_TAPS) return -1;
+    if (IC % 8 != 0 || IC < 32 || st > 2 || g->R * g->S > TC_MAX_TAPS) return -1;
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wp)) & 15) return -1;
     const int ost = tr ? st : 1;
     if (OH % ost != 0 || OW % ost != 0) return -1;
@@ -411,7 +410,9 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     p.HT = pow2ceil(p.OHc) < 128 / p.WT ? pow2ceil(p.OHc) : 128 / p.WT;
     p.NT = 128 / (p.WT * p.HT);
     p.tiles_w = (int)cdiv(p.OWc, p.WT); p.tiles_h = (int)cdiv(p.OHc, p.HT); p.tiles_n = (int)cdiv(g->N, p.NT);
-    p.IC = IC; p.kchunks = IC / 64;
+    // a trailing partial 64-channel chunk reads zeros for the input (TMA out-of-bounds fill), so whatever the weight
+    // box picks up beyond this tap's IC columns (the next tap's weights, or zeros past the matrix) is multiplied by 0
+    p.IC = IC; p.kchunks = (int)cdiv(IC, 64);
     p.in_sh = p.in_sw = tr ? 1 : st;
     p.act = g->act; p.has_bias = bias != nullptr;
     int classes = ost * ost, ntaps = -1;
@@ -448,8 +449,8 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(A) failed: %d", (int)r);
     }
-    const int BN = OC % 128 == 0 ? 128 : 64;
-    p.partial = (OC % BN != 0) || (reinterpret_cast<uintptr_t>(out) & 15) ? 1 : 0;
+    const int BN = (OC % 128 == 0 || OC >= 512) ? 128 : 64;
+    p.partial = (OC % 8 != 0) || (reinterpret_cast<uintptr_t>(out) & 15) ? 1 : 0;      // rows not 16-byte aligned
     {
         cuuint64_t dims[2] = {(cuuint64_t)g->R * g->S * IC, (cuuint64_t)OC};
         cuuint64_t strides[1] = {(cuuint64_t)g->R * g->S * IC * 2};
@@ -462,7 +463,7 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     }
     // statistics are fused into the epilogue when every 128-pixel tile lies inside one BatchNorm group
     p.n_per_group = g->N / g->groups;
-    const bool fuse_stats = stats != nullptr && !p.partial && (p.n_per_group % p.NT) == 0;
+    const bool fuse_stats = stats != nullptr && (p.n_per_group % p.NT) == 0;
     int rc = BN == 128 ? launch_tc<128, 3>(ma, mb, p, bias, out, classes, fuse_stats ? stats : nullptr, stream)
                        : launch_tc<64, 4>(ma, mb, p, bias, out, classes, fuse_stats ? stats : nullptr, stream);
     if (rc) return rc;
@@ -591,8 +592,11 @@ __global__ void __launch_bounds__(192, 2) tc_wgrad_kernel(const __grid_constant_
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             float* dst = dw + ((long long)k * p.C + ct * BN + c0) * RS + tap;
+            if (k < p.K) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) atomicAdd(dst + (long long)c * RS, __uint_as_float(v[c]));
+                for (int c = 0; c < 32; ++c)
+                    if (ct * BN + c0 + c < p.C) atomicAdd(dst + (long long)c * RS, __uint_as_float(v[c]));
+            }
         }
         tc_fence_before();
     }
@@ -620,7 +624,7 @@ static int launch_tc_wgrad(const CUtensorMap& ms, const CUtensorMap& mb, const T
 
 int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream) {
     if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || tc_disabled()) return -1;
-    if (g->K % 128 != 0 || g->C % 64 != 0 || g->stride > 2) return -1;
+    if (g->K % 8 != 0 || g->C % 8 != 0 || g->K < 64 || g->stride > 2) return -1;   // TMA: 16-byte channel pitch
     if ((reinterpret_cast<uintptr_t>(small_) | reinterpret_cast<uintptr_t>(big)) & 15) return -1;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return -1;
@@ -635,8 +639,8 @@ int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, fl
     if (g->Q % p.WT != 0 || g->P % p.HT != 0) return -1;
     p.tiles_w = g->Q / p.WT; p.tiles_h = g->P / p.HT; p.tiles_n = (int)cdiv(g->N, p.NT);
     p.total_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int BN = g->C % 128 == 0 ? 128 : 64;
-    p.k_tiles = g->K / 128; p.c_tiles = g->C / BN;
+    const int BN = (g->C % 128 == 0 || g->C >= 512) ? 128 : 64;
+    p.k_tiles = (int)cdiv(g->K, 128); p.c_tiles = (int)cdiv(g->C, BN);
     const long long base = (long long)p.k_tiles * p.c_tiles * g->R * g->S;
     long long splits = cdiv(4LL * num_sms(), base);
     if (splits > p.total_ptiles) splits = p.total_ptiles;

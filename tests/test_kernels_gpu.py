@@ -119,6 +119,11 @@ TC_CASES = [
     (130, 8, 8, 64, 64, 4, 2, 1, 2),
     (3, 64, 64, 64, 64, 3, 1, 1, 1),
     (5, 4, 4, 64, 128, 3, 1, 1, 1),
+    # channel counts that are only multiples of 8: partial 64-channel chunks and tail tiles in the output channels
+    (4, 16, 16, 72, 96, 3, 1, 1, 2),
+    (8, 8, 8, 40, 200, 4, 2, 1, 1),
+    (64, 1, 1, 1200, 1200, 1, 1, 0, 2),      # the 1200-wide linear layers of the WaveEq MLP configuration
+    (6, 1, 1, 20480, 1200, 1, 1, 0, 2),      # its first encoder layer
 ]
 
 
