@@ -47,6 +47,9 @@ int conv_forward_thin(const vs_conv_geom* g, int mode, const void* in, const voi
 int conv_wgrad_thin(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream);
 int conv_wgrad_simt(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream);
 // tensor-core paths: 0 = done, -1 = geometry not eligible (fall back to the CUDA-core kernels), >0 = error
+int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
+                        double* stats, cudaStream_t stream);
+int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream);
 int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                     double* stats, cudaStream_t stream);
 
@@ -80,6 +83,8 @@ extern "C" int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* 
     if (mode == VS_CONV_TRANSPOSED && g->C == 1 && g->K == 64 && g->R == 4 && g->stride == 2)
         rc = conv_forward_thin(g, mode, in, wp, bias, out, stats, as_stream(stream));
     if (rc >= 0) return rc;
+    rc = conv_forward_im2col(g, mode, in, wp, bias, out, stats, as_stream(stream));
+    if (rc >= 0) return rc;
     rc = conv_forward_tc(g, mode, in, wp, bias, out, stats, as_stream(stream));
     if (rc >= 0) return rc;
     rc = conv_forward_thin(g, mode, in, wp, bias, out, stats, as_stream(stream));
@@ -88,14 +93,17 @@ extern "C" int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* 
 }
 
 // which kernel family vs_conv_forward dispatches this geometry to: 0 = CUDA-core gather GEMM, 1 = tcgen05 tap GEMM,
-// 2 = thin streaming kernel.  Pure host logic (no launch); mirrors the dispatch order above.
+// 2 = thin streaming kernel, 3 = tcgen05 GEMM over a CTA-built im2col tile.  Pure host logic (no launch); mirrors the
+// dispatch order above.
 namespace vs {
+int conv_forward_im2col_eligible(const vs_conv_geom* g, int mode);
 int conv_forward_tc_eligible(const vs_conv_geom* g, int mode);
 int conv_forward_thin_eligible(const vs_conv_geom* g, int mode);
 }
 extern "C" int vs_conv_forward_path(const vs_conv_geom* g, int32_t mode) {
     if (check_geom(g)) return -1;
     if (mode == VS_CONV_TRANSPOSED && g->C == 1 && g->K == 64 && g->R == 4 && g->stride == 2 && conv_forward_thin_eligible(g, mode)) return 2;
+    if (conv_forward_im2col_eligible(g, mode)) return 3;
     if (conv_forward_tc_eligible(g, mode)) return 1;
     if (conv_forward_thin_eligible(g, mode)) return 2;
     return 0;
@@ -103,7 +111,9 @@ extern "C" int vs_conv_forward_path(const vs_conv_geom* g, int32_t mode) {
 
 extern "C" int vs_conv_wgrad(const vs_conv_geom* g, const void* small_, const void* big, float* dw, void* stream) {
     if (int rc = check_geom(g)) return rc;
-    int rc = conv_wgrad_thin(g, small_, big, dw, as_stream(stream));
+    int rc = conv_wgrad_im2col(g, small_, big, dw, as_stream(stream));
+    if (rc >= 0) return rc;
+    rc = conv_wgrad_thin(g, small_, big, dw, as_stream(stream));
     if (rc >= 0) return rc;
     rc = conv_wgrad_tc(g, small_, big, dw, as_stream(stream));
     if (rc >= 0) return rc;

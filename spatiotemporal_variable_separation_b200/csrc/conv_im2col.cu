@@ -1,0 +1,509 @@
+// tcgen05 convolutions for layers with a handful of channels on the image side (bf16 operands, fp32 accumulation).
+//
+// The first encoder convolution (nt_cond*nc = 5 input channels, /root/reference/var_sep/networks/conv.py:119-123) and
+// the backward of the last decoder up-convolution (nc = 1 output channel, conv.py:258-263) have R*S*C <= 128: one
+// 128-byte row of shared memory holds a pixel's whole receptive field.  A TMA box cannot express that gather
+// (C*2 bytes is not a multiple of 16), so the CTA builds the im2col tile itself, directly in the 128-byte-swizzled
+// layout tcgen05.mma reads, and the image-side tensor is streamed from HBM exactly once:
+//   forward : out[pix][k]      = sum_kk xcol[pix][kk] * w[k][kk]          (K-major A built by 4 warps, B resident)
+//   wgrad   : dw[k][c][tap]   += sum_pix xcol[pix][(tap,c)] * small[pix][k] (MN-major A built, B = TMA boxes of `small`)
+// with kk = (r*S + s)*C + c and xcol[pix][kk] = big[n][p*stride-pad+r][q*stride-pad+s][c] (zero outside the image).
+// The shared-memory image of a tile is the same in both cases: row = pixel, 128 bytes = 64 kk values, the 16-byte
+// chunk index XORed with (row & 7).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace vs {
+
+constexpr int IM_MAX_KK = 128;
+
+struct Im2colParams {
+    int N, H, W, C, P, Q, K, R, S, stride, pad;
+    int KK, nchunk16;            // R*S*C and the number of 16-byte chunks per pixel row that hold data
+    int WT, HT, NT;              // pixel box over the small grid (powers of two)
+    int wt_shift, ht_shift;
+    int tiles_w, tiles_h, tiles_n, total_tiles;
+    int ptiles_per_split;        // wgrad
+    int act, has_bias, partial, n_per_group;
+};
+
+// one 16-byte chunk (8 consecutive kk) of pixel (n, p, q)'s receptive field
+__device__ __forceinline__ uint4 im2col_chunk(const Im2colParams& p, const unsigned short* __restrict__ big, const uint32_t* tab,
+                                              int j, bool ok, int n, int pp, int qq) {
+    unsigned short v[8];
+    const int h0 = pp * p.stride - p.pad, w0 = qq * p.stride - p.pad;
+    const unsigned short* img = big + (long long)n * p.H * p.W * p.C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int kk = j * 8 + e;
+        const uint32_t t = tab[kk];                       // r | s << 8 | c << 16 (entries past KK decode to r = 255)
+        const int h = h0 + (int)(t & 255u), w = w0 + (int)((t >> 8) & 255u), c = (int)(t >> 16);
+        const bool in = ok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+        v[e] = in ? __ldg(img + ((long long)h * p.W + w) * p.C + c) : (unsigned short)0;
+    }
+    return make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16), v[4] | ((uint32_t)v[5] << 16),
+                      v[6] | ((uint32_t)v[7] << 16));
+}
+
+__device__ __forceinline__ void im2col_table(const Im2colParams& p, uint32_t* tab) {
+    for (int kk = threadIdx.x; kk < IM_MAX_KK; kk += blockDim.x) {
+        uint32_t t = 255u;                                // r = 255: always outside the image
+        if (kk < p.KK) {
+            const int tap = kk / p.C, c = kk - tap * p.C;
+            t = (uint32_t)(tap / p.S) | ((uint32_t)(tap % p.S) << 8) | ((uint32_t)c << 16);
+        }
+        tab[kk] = t;
+    }
+}
+
+// =================================================================================================== forward
+// warps: 0 = spare (weights are staged by everyone at start), 1 = TMEM allocator + MMA issuer, 2..5 = im2col builders,
+// 6..9 = epilogue.  Persistent over 128-pixel tiles; KC = number of 64-wide kk chunks (1 or 2).
+constexpr int IMF_THREADS = 320;
+
+template <int BN, int KC, int STAGES>
+struct ImfSmem {
+    static constexpr int A_BYTES = KC * TC_BM * 128, B_BYTES = KC * BN * 128;
+    static constexpr int BAR_OFF = STAGES * A_BYTES + B_BYTES;
+    static constexpr int TAB_OFF = BAR_OFF + 256, STAT_OFF = TAB_OFF + IM_MAX_KK * 4;
+    static constexpr int TOTAL = STAT_OFF + BN * 2 * 4 + 1024;
+    static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
+};
+
+template <int BN, int KC, int STAGES>
+__global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid_constant__ Im2colParams p,
+                                                                   const unsigned short* __restrict__ big,
+                                                                   const unsigned short* __restrict__ wp,
+                                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                                   double* __restrict__ stats) {
+    using S = ImfSmem<BN, KC, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* b_smem = smem + STAGES * S::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + S::TAB_OFF);
+    float* sstat = reinterpret_cast<float*>(smem + S::STAT_OFF);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = p.total_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+    im2col_table(p, tab);
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.f;
+    // A stages: zero once (chunks past nchunk16 are never written again); B: the packed weights [K][KK], zero padded
+    for (int i = threadIdx.x; i < STAGES * S::A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < BN * KC * 8; i += blockDim.x) {
+        const int oc = i / (KC * 8), jj = i % (KC * 8);            // jj: 16-byte chunk along kk
+        unsigned short v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int kk = jj * 8 + e;
+            v[e] = (oc < p.K && kk < p.KK) ? __ldg(wp + (long long)oc * p.KK + kk) : (unsigned short)0;
+        }
+        const int chunk = jj >> 3, j = jj & 7;
+        *reinterpret_cast<uint4*>(b_smem + chunk * (BN * 128) + oc * 128 + ((j ^ (oc & 7)) << 4)) =
+            make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16), v[4] | ((uint32_t)v[5] << 16),
+                       v[6] | ((uint32_t)v[7] << 16));
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+#define VS_IM_DECODE(idx)                                       \
+    int t_ = (idx);                                             \
+    const int tw = t_ % p.tiles_w; t_ /= p.tiles_w;             \
+    const int th = t_ % p.tiles_h;                              \
+    const int tn = t_ / p.tiles_h;                              \
+    const int j0 = tw * p.WT, i0 = th * p.HT, b0 = tn * p.NT;
+
+    if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16_f32(BN);
+            const int ksteps = (p.KK + 15) >> 4;
+            int lt = 0;
+            for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+                const int acc = lt & 1, s = lt % STAGES;
+                mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+                mbar_wait(&full[s], (lt / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * S::A_BYTES), b_addr = smem_u32(b_smem);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t ao = (uint32_t)((k >> 2) * (TC_BM * 128) + (k & 3) * 32);
+                    const uint32_t bo = (uint32_t)((k >> 2) * (BN * 128) + (k & 3) * 32);
+                    umma_bf16(tmem_d, kmajor_sw128_desc(a_addr + ao), kmajor_sw128_desc(b_addr + bo), idesc, k != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else if (warp >= 2 && warp < 6) {
+        // ===== im2col builders: thread = pixel row of the tile =====
+        const int m = threadIdx.x - 64;
+        const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
+        int lt = 0;
+        for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+            VS_IM_DECODE(idx)
+            const int s = lt % STAGES;
+            const int pp = i0 + h, qq = j0 + w, nn = b0 + n;
+            const bool ok = pp < p.P && qq < p.Q && nn < p.N;
+            uint8_t* a_row = smem + s * S::A_BYTES + m * 128;
+            // gather first (loads in flight while waiting for the slot), then store
+            uint4 first = im2col_chunk(p, big, tab, 0, ok, nn, pp, qq);
+            mbar_wait(&empty[s], ((lt / STAGES) & 1) ^ 1);
+            *reinterpret_cast<uint4*>(a_row + ((0 ^ (m & 7)) << 4)) = first;
+            for (int j = 1; j < p.nchunk16; ++j) {
+                const uint4 v = im2col_chunk(p, big, tab, j, ok, nn, pp, qq);
+                *reinterpret_cast<uint4*>(a_row + (j >> 3) * (TC_BM * 128) + (((j & 7) ^ (m & 7)) << 4)) = v;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+    } else if (warp >= 6) {
+        // ===== epilogue: one warp per TMEM lane quarter =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
+        int lt = 0;
+        for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+            VS_IM_DECODE(idx)
+            const int acc = lt & 1;
+            const int pp = i0 + h, qq = j0 + w, nn = b0 + n;
+            const bool ok = pp < p.P && qq < p.Q && nn < p.N;
+            __nv_bfloat16* dst = out + (((long long)nn * p.P + pp) * p.Q + qq) * p.K;
+            mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                const float bias_l = (p.has_bias && c0 + lane < p.K) ? __ldg(bias + c0 + lane) : 0.f;
+                float xs[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                if (p.partial || BN > p.K) {
+                    if (ok) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (c0 + c < p.K) dst[c0 + c] = __float2bfloat16_rn(act_fwd(xs[c], p.act));
+                    }
+                } else if (ok) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = v * 8 + e * 2;
+                            __nv_bfloat162 b2 = p.act == VS_ACT_NONE ? __floats2bfloat162_rn(xs[c], xs[c + 1])
+                                                                     : __floats2bfloat162_rn(act_fwd(xs[c], p.act), act_fwd(xs[c + 1], p.act));
+                            pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                        }
+                        *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                if (stats != nullptr) {
+                    float wk[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] : 0.f;
+                    const float s1 = warp_transpose_sum32(wk, lane);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] * xs[c] : 0.f;
+                    const float s2 = warp_transpose_sum32(wk, lane);
+                    atomicAdd(&sstat[(c0 + lane) * 2], s1);
+                    atomicAdd(&sstat[(c0 + lane) * 2 + 1], s2);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (stats != nullptr) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int g = b0 / p.n_per_group;
+                const int t = threadIdx.x - 192;
+                for (int i = t; i < 2 * BN; i += 128) {
+                    const int col = i >> 1;
+                    if (col < p.K) atomicAdd(&stats[((long long)g * p.K + col) * 2 + (i & 1)], (double)sstat[i]);
+                    sstat[i] = 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem_base);
+    }
+}
+
+static void im2col_tiling(Im2colParams& p, int pixels) {
+    p.WT = pow2ceil(p.Q) < pixels ? pow2ceil(p.Q) : pixels;
+    p.HT = pow2ceil(p.P) < pixels / p.WT ? pow2ceil(p.P) : pixels / p.WT;
+    p.NT = pixels / (p.WT * p.HT);
+    p.wt_shift = 0; while ((1 << p.wt_shift) < p.WT) ++p.wt_shift;
+    p.ht_shift = 0; while ((1 << p.ht_shift) < p.HT) ++p.ht_shift;
+    p.tiles_w = (int)cdiv(p.Q, p.WT); p.tiles_h = (int)cdiv(p.P, p.HT); p.tiles_n = (int)cdiv(p.N, p.NT);
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+}
+
+static void im2col_params(Im2colParams& p, const vs_conv_geom* g) {
+    memset(&p, 0, sizeof(p));
+    p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
+    p.stride = g->stride; p.pad = g->pad;
+    p.KK = g->R * g->S * g->C;
+    p.nchunk16 = (p.KK + 7) / 8;
+}
+
+static bool im2col_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VARSEP_DISABLE_IM2COL"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1 || tc_disabled();
+}
+
+int conv_forward_im2col_eligible(const vs_conv_geom* g, int mode) {
+    if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || im2col_disabled()) return 0;
+    if (mode != VS_CONV_DIRECT) return 0;
+    if (g->C >= 32 || g->R * g->S * g->C > IM_MAX_KK || g->K > 128 || g->K < 16 || g->R > 16 || g->S > 16) return 0;
+    if ((long long)g->N * g->P * g->Q < 4096) return 0;        // launch-bound sizes: the streaming kernels are fine
+    return 1;
+}
+
+template <int BN, int KC, int STAGES>
+static int launch_imf(const Im2colParams& p, const void* big, const void* wp, const float* bias, void* out, double* stats,
+                      cudaStream_t stream) {
+    using S = ImfSmem<BN, KC, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(im2col_fwd_kernel<BN, KC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return fail("im2col_fwd_kernel smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int resident = 2 * num_sms();
+    const int grid = p.total_tiles < resident ? p.total_tiles : resident;
+    im2col_fwd_kernel<BN, KC, STAGES><<<grid, IMF_THREADS, S::TOTAL, stream>>>(
+        p, (const unsigned short*)big, (const unsigned short*)wp, bias, (__nv_bfloat16*)out, stats);
+    return launched("im2col_fwd_kernel");
+}
+
+// returns 0 = done, -1 = geometry not eligible, >0 = error
+int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
+                        double* stats, cudaStream_t stream) {
+    if (!conv_forward_im2col_eligible(g, mode)) return -1;
+    Im2colParams p;
+    im2col_params(p, g);
+    im2col_tiling(p, 128);
+    p.act = g->act; p.has_bias = bias != nullptr;
+    p.partial = (g->K % 8 != 0) || (reinterpret_cast<uintptr_t>(out) & 15) ? 1 : 0;
+    p.n_per_group = g->N / g->groups;
+    const bool fuse_stats = stats != nullptr && (p.n_per_group % p.NT) == 0;
+    double* st = fuse_stats ? stats : nullptr;
+    const int KC = p.KK > 64 ? 2 : 1;
+    int rc;
+    if (g->K <= 64) rc = KC == 1 ? launch_imf<64, 1, 4>(p, in, wp, bias, out, st, stream) : launch_imf<64, 2, 2>(p, in, wp, bias, out, st, stream);
+    else            rc = KC == 1 ? launch_imf<128, 1, 4>(p, in, wp, bias, out, st, stream) : launch_imf<128, 2, 2>(p, in, wp, bias, out, st, stream);
+    if (rc) return rc;
+    if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * g->P * g->Q, g->K, stats, stream);
+    return 0;
+}
+
+// =================================================================================================== weight gradient
+// D[kk][k] += sum over 64-pixel blocks; warps: 0 = TMA producer (boxes of `small`), 1 = MMA issuer, 2..5 = im2col
+// builders during the reduction, then the epilogue (fp32 reductions into the torch-layout gradient).
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_constant__ CUtensorMap map_small,
+                                                              const __grid_constant__ Im2colParams p,
+                                                              const unsigned short* __restrict__ big, float* __restrict__ dw) {
+    constexpr int PIX = 64, CHUNK = 64 * PIX * 2;
+    constexpr int A_BYTES = 2 * CHUNK, B_BYTES = BN * PIX * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kt = blockIdx.x;
+    const int pt0 = blockIdx.z * p.ptiles_per_split;
+    int pt1 = pt0 + p.ptiles_per_split;
+    if (pt1 > p.total_tiles) pt1 = p.total_tiles;
+    const int nkb = pt1 - pt0;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_small);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }     // TMA expect + 4 builder warps
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    im2col_table(p, tab);
+    for (int s = 0; s < STAGES; ++s)
+        for (int i = threadIdx.x; i < A_BYTES / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(smem + s * STAGE_BYTES)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (nkb <= 0) {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc<BN>(tmem_base);
+        return;
+    }
+
+#define VS_IMW_DECODE(t)                                        \
+    int t_ = (t);                                               \
+    const int tw = t_ % p.tiles_w; t_ /= p.tiles_w;             \
+    const int th = t_ % p.tiles_h;                              \
+    const int tn = t_ / p.tiles_h;                              \
+    const int q0 = tw * p.WT, p0 = th * p.HT, b0 = tn * p.NT;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES;
+                mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
+                VS_IMW_DECODE(pt0 + kb)
+                uint8_t* b_dst = smem + st * STAGE_BYTES + A_BYTES;
+                mbar_expect_tx(&full[st], B_BYTES);
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) tma_load_4d(b_dst + j * CHUNK, &map_small, &full[st], kt * BN + j * 64, q0, p0, b0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16_f32(BN) | (1u << 15) | (1u << 16);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES;
+                mbar_wait(&full[st], (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + st * STAGE_BYTES);
+                const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < PIX / 16; ++k)
+                    umma_bf16(tmem_base, mnmajor_sw128_desc(a_addr + k * 2048, CHUNK), mnmajor_sw128_desc(b_addr + k * 2048, CHUNK),
+                              idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_commit(&empty[st]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // ===== builders: items = (16-byte chunk j, pixel m), m fastest =====
+        const int t = threadIdx.x - 64;                   // 0..127
+        const int items = p.nchunk16 * PIX;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % STAGES;
+            VS_IMW_DECODE(pt0 + kb)
+            uint8_t* a_dst = smem + st * STAGE_BYTES;
+            bool waited = false;
+            for (int it = t; it < items || !waited; it += 128) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                int m = 0, j = 0;
+                const bool live = it < items;
+                if (live) {
+                    m = it & (PIX - 1); j = it >> 6;
+                    const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
+                    const int pp = p0 + h, qq = q0 + w, nn = b0 + n;
+                    v = im2col_chunk(p, big, tab, j, pp < p.P && qq < p.Q && nn < p.N, nn, pp, qq);
+                }
+                if (!waited) { mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1); waited = true; }
+                if (live) *reinterpret_cast<uint4*>(a_dst + (j >> 3) * CHUNK + m * 128 + (((j & 7) ^ (m & 7)) << 4)) = v;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[st]);
+        }
+        // ===== epilogue: TMEM lane = kk, column = channel of `small` =====
+        const int q = warp & 3;
+        const int kk = q * 32 + lane;
+        const int RS = p.R * p.S;
+        const int tap = kk / p.C, c = kk - tap * p.C;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (kk < p.KK) {
+                float* dst = dw + ((long long)(kt * BN + c0) * p.C + c) * RS + tap;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (kt * BN + c0 + i < p.K) atomicAdd(dst + (long long)i * p.C * RS, __uint_as_float(v[i]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_imw(const CUtensorMap& ms, const Im2colParams& p, const void* big, float* dw, int k_tiles, int splits,
+                      cudaStream_t stream) {
+    constexpr int SMEM = STAGES * (2 * 64 * 64 * 2 + BN * 64 * 2) + 1024 + 256 + IM_MAX_KK * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(im2col_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return fail("im2col_wgrad_kernel smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid((unsigned)k_tiles, 1, (unsigned)splits);
+    im2col_wgrad_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(ms, p, (const unsigned short*)big, dw);
+    return launched("im2col_wgrad_kernel");
+}
+
+int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream) {
+    if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || im2col_disabled()) return -1;
+    if (g->C >= 32 || g->R * g->S * g->C > IM_MAX_KK || g->R > 16 || g->S > 16) return -1;
+    if (g->K % 8 != 0 || g->K < 32) return -1;                         // TMA: 16-byte channel pitch of `small`
+    if ((long long)g->N * g->P * g->Q < 4096) return -1;
+    if (reinterpret_cast<uintptr_t>(small_) & 15) return -1;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return -1;
+    Im2colParams p;
+    im2col_params(p, g);
+    im2col_tiling(p, 64);
+    // partial boxes in W/H would shift the pixel order inside the TMA box relative to the builder's decode
+    if (g->Q % p.WT != 0 || g->P % p.HT != 0) return -1;
+    const int BN = g->K > 64 ? 128 : 64;
+    const int k_tiles = (int)cdiv(g->K, BN);
+    long long splits = cdiv(4LL * num_sms(), k_tiles);
+    if (splits > p.total_tiles) splits = p.total_tiles;
+    if (splits > 65535) splits = 65535;
+    p.ptiles_per_split = (int)cdiv(p.total_tiles, splits);
+    splits = cdiv(p.total_tiles, p.ptiles_per_split);
+    CUtensorMap ms;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g->K, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)g->K * 2, (cuuint64_t)g->K * g->Q * 2, (cuuint64_t)g->K * g->Q * g->P * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.WT, (cuuint32_t)p.HT, (cuuint32_t)p.NT};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult rc = enc(&ms, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(small_), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(small) failed: %d", (int)rc);
+    }
+    return BN == 128 ? launch_imw<128, 3>(ms, p, big, dw, k_tiles, (int)splits, stream)
+                     : launch_imw<64, 4>(ms, p, big, dw, k_tiles, (int)splits, stream);
+}
+
+}  // namespace vs

@@ -61,12 +61,41 @@ def packed_weight(w, K, C, RS, swap, dtype):
 # every (parameter, layout) pair that has ever been packed; lets the optimizer refresh all of them in one launch
 _pack_registry = []
 _pack_table = {}
+# (parameter, zero-padded shadow) pairs, see ``padded_rows``
+_pad_registry = []
+
+
+def padded_rows(w, Kp):
+    """fp32 copy of parameter ``w`` with dim 0 zero-padded to ``Kp`` rows (a persistent shadow, refreshed when the
+    parameter changes).  TMA needs a 16-byte channel pitch, so a transposed convolution whose input channel count
+    is not a multiple of 8 (the decoder's first up-convolution reads the 148-channel [S|T] code) runs on the
+    tensor cores with zero input channels appended; the packed copies are made from this shadow."""
+    hit = w.__dict__.get('_vs_padrows')
+    tag = (w._version, w.data_ptr(), _pack_epoch)
+    if hit is not None and hit[0].shape[0] == Kp:
+        if hit[1] != tag:
+            hit[0][:w.shape[0]].copy_(w.detach())
+            w.__dict__['_vs_padrows'] = (hit[0], tag)
+        return hit[0]
+    shadow = torch.zeros((Kp,) + tuple(w.shape[1:]), device=w.device, dtype=torch.float32)
+    shadow[:w.shape[0]].copy_(w.detach())
+    w.__dict__['_vs_padrows'] = (shadow, tag)
+    _pad_registry.append((w, shadow))
+    return shadow
+
+
+def _refresh_padded():
+    for w, shadow in _pad_registry:
+        if w.is_cuda and shadow.device == w.device:
+            shadow[:w.shape[0]].copy_(w.detach())
+            w.__dict__['_vs_padrows'] = (shadow, (w._version, w.data_ptr(), _pack_epoch))
 
 
 def repack_all():
     """Refresh every known packed copy with ONE kernel (called by FusedAdam.step after the arena update) and mark
     them current, so the next step's forward / backward find cache hits instead of ~30 small pack launches."""
     import struct
+    _refresh_padded()
     live = [(w, key, out) for (w, key, out) in _pack_registry if w.is_cuda]
     if not live:
         return
@@ -120,10 +149,18 @@ class ConvBlockFn(torch.autograd.Function):
             out_shape, OC, mode = (N, H, W, cfg.C), cfg.C, L.TRANSPOSED
         dt = x.dtype
         act = L.ACT[cfg.act]
-        wp = packed_weight(weight, cfg.K, cfg.C, cfg.R * cfg.S, mode == L.TRANSPOSED, dt)
+        ctx.cfg_fwd = cfg
+        wsrc = weight
+        if mode == L.TRANSPOSED and dt == torch.bfloat16 and cfg.K % 8 != 0 and cfg.K >= 32 and cfg.C % 8 == 0:
+            # input channels padded with zeros to a 16-byte pitch so that the layer runs on the tensor cores
+            Kp = (cfg.K + 7) // 8 * 8
+            xp = torch.zeros((N, P, Q, Kp), device=x.device, dtype=dt)
+            L.call('vs_copy_channels', ptr(x), cfg.K, N * P * Q, ptr(xp), Kp, 0, N * P * Q, L.dtype_code(xp), L.stream())
+            x, wsrc, cfg = xp, padded_rows(weight, Kp), cfg._replace(K=Kp)
+        wp = packed_weight(wsrc, cfg.K, cfg.C, cfg.R * cfg.S, mode == L.TRANSPOSED, dt)
         y = torch.empty(out_shape, device=x.device, dtype=dt)
         rows = y.numel() // OC
-        ctx.cfg, ctx.dims, ctx.mode = cfg, (N, H, W, P, Q, OC), mode
+        ctx.cfg, ctx.dims, ctx.mode = cfg, (N, H, W, P, Q, OC), mode      # cfg: geometry of the launches (K padded)
         if cfg.has_bn:
             G = cfg.groups if cfg.training else 1
             mean = torch.empty(G * OC, device=x.device, dtype=torch.float32)
@@ -181,17 +218,26 @@ class ConvBlockFn(torch.autograd.Function):
             else:
                 dy = dout
         g = _geom(cfg, dt, N, H, W, P, Q, 0, 1)
+        cfg0 = ctx.cfg_fwd                      # the layer's own geometry (differs from cfg when K was padded)
+        padded = cfg0.K != cfg.K
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
+            g0 = _geom(cfg0, dt, N, H, W, P, Q, 0, 1)
+            dx = torch.empty(x.shape[:-1] + (cfg0.K,), device=x.device, dtype=dt) if padded else torch.empty_like(x)
             back_mode = L.TRANSPOSED if mode == L.DIRECT else L.DIRECT
-            wp = packed_weight(weight, cfg.K, cfg.C, cfg.R * cfg.S, back_mode == L.TRANSPOSED, dt)
-            L.call('vs_conv_forward', g, back_mode, ptr(dy), ptr(wp), None, ptr(dx), None, L.stream())
+            wp = packed_weight(weight, cfg0.K, cfg0.C, cfg0.R * cfg0.S, back_mode == L.TRANSPOSED, dt)
+            L.call('vs_conv_forward', g0, back_mode, ptr(dy), ptr(wp), None, ptr(dx), None, L.stream())
         dw = db = None
         if ctx.needs_input_grad[1]:
             dw = _grad_buffer(p_weight)
             small, big = (dy, x) if cfg.kind == 'conv' else (x, dy)
-            L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dw[0]), L.stream())
+            if padded:
+                # gradient of the zero-padded weight; its first K rows are the layer's gradient
+                dwp = torch.zeros((cfg.K,) + tuple(weight.shape[1:]), device=x.device, dtype=torch.float32)
+                L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dwp), L.stream())
+                dw[0].add_(dwp[:cfg0.K].view_as(dw[0]))
+            else:
+                L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dw[0]), L.stream())
         if p_bias is not None and ctx.needs_input_grad[2]:
             db = _grad_buffer(p_bias)
             if not (cfg.has_bn and cfg.training):

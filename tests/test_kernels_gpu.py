@@ -65,6 +65,10 @@ CONV_CASES = [
     (4, 64, 64, 3, 64, 4, 2, 1, 1),       # same for nc=3 (chairs)
     (8, 64, 64, 5, 64, 4, 2, 1, 2),       # first DCGAN encoder layer (nt_cond*nc = 5)
     (6, 32, 32, 2, 64, 3, 1, 1, 2),       # last VGG decoder layer (ConvT 64->2, k3 s1 p1)
+    # tcgen05 over a CTA-built im2col tile: partial pixel boxes, K below / above one 64-channel tile, two kk chunks
+    (12, 40, 40, 3, 48, 4, 2, 1, 2),
+    (8, 32, 32, 6, 128, 4, 2, 1, 2),
+    (20, 16, 16, 7, 72, 3, 1, 1, 1),
     (33, 1, 1, 148, 24, 4, 1, 0, 3),      # placeholder geometry replaced below
 ]
 # first_upconv: ConvTranspose k4 s1 p0 of a 1x1 input (big side 4x4, small side 1x1)
