@@ -83,7 +83,7 @@ int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* in, const v
 
 /* Which kernel family vs_conv_forward would use for this geometry: 0 = CUDA-core gather GEMM, 1 = tcgen05/TMA tap
  * GEMM, 2 = thin streaming kernel, 3 = tcgen05 GEMM over an im2col tile the CTA builds itself (few image-side
- * channels), -1 = invalid geometry.  Host-only (no launch); used by bench.py to attribute
+ * channels), 4 = tcgen05 GEMM + col2im (last decoder up-convolution), -1 = invalid geometry.  Host-only (no launch); used by bench.py to attribute
  * the measured launch times to the tensor-core kernel for the roofline. */
 int vs_conv_forward_path(const vs_conv_geom* g, int32_t mode);
 

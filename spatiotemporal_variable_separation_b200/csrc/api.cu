@@ -49,6 +49,8 @@ int conv_wgrad_simt(const vs_conv_geom* g, const void* small_, const void* big, 
 // tensor-core paths: 0 = done, -1 = geometry not eligible (fall back to the CUDA-core kernels), >0 = error
 int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                         double* stats, cudaStream_t stream);
+int conv_forward_col2im(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
+                        double* stats, cudaStream_t stream);
 int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream);
 int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                     double* stats, cudaStream_t stream);
@@ -77,7 +79,9 @@ extern "C" int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* 
     if (int rc = check_geom(g)) return rc;
     VS_REQUIRE(mode == VS_CONV_DIRECT || mode == VS_CONV_TRANSPOSED, "bad mode %d", mode);
     VS_REQUIRE(stats == nullptr || g->act == VS_ACT_NONE, "statistics are taken of the pre-activation: act must be NONE");
-    int rc = -1;
+    // last decoder up-convolution (k4 s2 p1 to one or two channels): GEMM + col2im, the input is read once
+    int rc = conv_forward_col2im(g, mode, in, wp, bias, out, stats, as_stream(stream));
+    if (rc >= 0) return rc;
     // 64 -> 1 channel transposed convolution: the dedicated streaming kernel reads the input once (the tensor-core
     // tap GEMM would fetch it 16 times to fill 1 of 64 accumulator columns)
     if (mode == VS_CONV_TRANSPOSED && g->C == 1 && g->K == 64 && g->R == 4 && g->stride == 2)
@@ -93,15 +97,17 @@ extern "C" int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* 
 }
 
 // which kernel family vs_conv_forward dispatches this geometry to: 0 = CUDA-core gather GEMM, 1 = tcgen05 tap GEMM,
-// 2 = thin streaming kernel, 3 = tcgen05 GEMM over a CTA-built im2col tile.  Pure host logic (no launch); mirrors the
-// dispatch order above.
+// 2 = thin streaming kernel, 3 = tcgen05 GEMM over a CTA-built im2col tile, 4 = tcgen05 GEMM + col2im.  Pure host logic
+// (no launch, assumes no fused statistics); mirrors the dispatch order above.
 namespace vs {
+int conv_forward_col2im_eligible(const vs_conv_geom* g, int mode);
 int conv_forward_im2col_eligible(const vs_conv_geom* g, int mode);
 int conv_forward_tc_eligible(const vs_conv_geom* g, int mode);
 int conv_forward_thin_eligible(const vs_conv_geom* g, int mode);
 }
 extern "C" int vs_conv_forward_path(const vs_conv_geom* g, int32_t mode) {
     if (check_geom(g)) return -1;
+    if (conv_forward_col2im_eligible(g, mode)) return 4;
     if (mode == VS_CONV_TRANSPOSED && g->C == 1 && g->K == 64 && g->R == 4 && g->stride == 2 && conv_forward_thin_eligible(g, mode)) return 2;
     if (conv_forward_im2col_eligible(g, mode)) return 3;
     if (conv_forward_tc_eligible(g, mode)) return 1;

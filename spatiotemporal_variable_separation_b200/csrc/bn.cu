@@ -166,8 +166,12 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int G, int
 // 16-byte coalesced accesses.  Eligible when C*sizeof(T)/16 divides 256.
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Vec;
+constexpr int COL_ROWS_IN_FLIGHT = 4;     // 16-byte loads per operand a thread issues before it consumes any of them
 template <> struct Vec<float> {
     static constexpr int W = 4;
+    static __device__ __forceinline__ void unpack(const uint4& u, float* v) {
+        v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    }
     static __device__ __forceinline__ void load(const float* p, float* v) {
         const float4 a = *reinterpret_cast<const float4*>(p);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -178,6 +182,14 @@ template <> struct Vec<float> {
 };
 template <> struct Vec<__nv_bfloat16> {
     static constexpr int W = 8;
+    static __device__ __forceinline__ void unpack(const uint4& u, float* v) {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
     static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
         const uint4 u = *reinterpret_cast<const uint4*>(p);
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -206,6 +218,9 @@ struct ColPlan {
 };
 
 template <typename T>
+__device__ __forceinline__ uint4 raw16(const T* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+template <typename T>
 static bool col_plan(long long rows, int C, int G, ColPlan& pl, int blocks_per_sm = 8) {
     constexpr int W = Vec<T>::W;
     if (C % W != 0) return false;
@@ -214,7 +229,7 @@ static bool col_plan(long long rows, int C, int G, ColPlan& pl, int blocks_per_s
     pl.rows_per_iter = 256 / pl.tpr;
     pl.rpg = rows / G;
     long long chunks = cdiv((long long)blocks_per_sm * num_sms(), G);
-    const long long max_chunks = cdiv(pl.rpg, 4LL * pl.rows_per_iter);
+    const long long max_chunks = cdiv(pl.rpg, 2LL * COL_ROWS_IN_FLIGHT * pl.rows_per_iter);
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     pl.per = cdiv(cdiv(pl.rpg, chunks), pl.rows_per_iter) * pl.rows_per_iter;
@@ -238,20 +253,26 @@ __global__ void __launch_bounds__(256) bn_act_fwd_col_kernel(const T* __restrict
     float mu[W], is[W], ga[W], be[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
-    // two independent rows in flight per thread
-    for (long long r = r0 + rl; r < r1; r += 2 * pl.rows_per_iter) {
-        const long long rb = r + pl.rows_per_iter;
-        const bool has_b = rb < r1;
-        float v[W], v2[W];
-        Vec<T>::load(y + r * C + c, v);
-        if (has_b) Vec<T>::load(y + rb * C + c, v2);
+    // several independent rows in flight per thread (raw 16-byte loads first, conversion afterwards): the kernel is
+    // bound by the bytes in flight per SM, not by arithmetic
+    constexpr int U = COL_ROWS_IN_FLIGHT;
+    for (long long r = r0 + rl; r < r1; r += (long long)U * pl.rows_per_iter) {
+        uint4 raw[U];
 #pragma unroll
-        for (int k = 0; k < W; ++k) v[k] = act_fwd(ga[k] * ((v[k] - mu[k]) * is[k]) + be[k], act);
-        Vec<T>::store(out + r * C + c, v);
-        if (has_b) {
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + (long long)u * pl.rows_per_iter;
+            if (rr < r1) raw[u] = raw16(y + rr * C + c);
+        }
 #pragma unroll
-            for (int k = 0; k < W; ++k) v2[k] = act_fwd(ga[k] * ((v2[k] - mu[k]) * is[k]) + be[k], act);
-            Vec<T>::store(out + rb * C + c, v2);
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + (long long)u * pl.rows_per_iter;
+            if (rr < r1) {
+                float v[W];
+                Vec<T>::unpack(raw[u], v);
+#pragma unroll
+                for (int k = 0; k < W; ++k) v[k] = act_fwd(ga[k] * ((v[k] - mu[k]) * is[k]) + be[k], act);
+                Vec<T>::store(out + rr * C + c, v);
+            }
         }
     }
 }
@@ -271,28 +292,29 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_col_kernel(const T* __restri
         m1[k] = train ? (float)sums[((long long)g * C + c + k) * 2] * inv_count : 0.f;
         m2[k] = train ? (float)sums[((long long)g * C + c + k) * 2 + 1] * inv_count : 0.f;
     }
-    for (long long r = r0 + rl; r < r1; r += 2 * pl.rows_per_iter) {
-        const long long rb = r + pl.rows_per_iter;
-        const bool has_b = rb < r1;
-        float v[W], d[W], v2[W], d2[W];
-        Vec<T>::load(y + r * C + c, v);
-        Vec<T>::load(dout + r * C + c, d);
-        if (has_b) { Vec<T>::load(y + rb * C + c, v2); Vec<T>::load(dout + rb * C + c, d2); }
+    constexpr int U = COL_ROWS_IN_FLIGHT;
+    for (long long r = r0 + rl; r < r1; r += (long long)U * pl.rows_per_iter) {
+        uint4 ry[U], rd[U];
 #pragma unroll
-        for (int k = 0; k < W; ++k) {
-            const float xh = (v[k] - mu[k]) * is[k];
-            const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
-            d[k] = ga[k] * is[k] * (dz - m1[k] - xh * m2[k]);
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + (long long)u * pl.rows_per_iter;
+            if (rr < r1) { ry[u] = raw16(y + rr * C + c); rd[u] = raw16(dout + rr * C + c); }
         }
-        Vec<T>::store(dy + r * C + c, d);
-        if (has_b) {
 #pragma unroll
-            for (int k = 0; k < W; ++k) {
-                const float xh = (v2[k] - mu[k]) * is[k];
-                const float dz = d2[k] * act_grad_from_in(ga[k] * xh + be[k], act);
-                d2[k] = ga[k] * is[k] * (dz - m1[k] - xh * m2[k]);
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + (long long)u * pl.rows_per_iter;
+            if (rr < r1) {
+                float v[W], d[W];
+                Vec<T>::unpack(ry[u], v);
+                Vec<T>::unpack(rd[u], d);
+#pragma unroll
+                for (int k = 0; k < W; ++k) {
+                    const float xh = (v[k] - mu[k]) * is[k];
+                    const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
+                    d[k] = ga[k] * is[k] * (dz - m1[k] - xh * m2[k]);
+                }
+                Vec<T>::store(dy + rr * C + c, d);
             }
-            Vec<T>::store(dy + rb * C + c, d2);
         }
     }
 }
@@ -311,36 +333,36 @@ __global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict_
         s1[k] = 0.f; s2[k] = 0.f;
         if (MODE == 0) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
     }
-    // two independent rows in flight per thread (the loop is latency-, not bandwidth-limited otherwise)
-    for (long long r = r0 + rl; r < r1; r += 2 * pl.rows_per_iter) {
-        const long long rb = r + pl.rows_per_iter;
-        const bool has_b = rb < r1;
-        float v[W], d[W], v2[W], d2[W];
-        Vec<T>::load(y + r * C + c, v);
-        if (has_b) Vec<T>::load(y + rb * C + c, v2);
-        if (MODE == 0) {
-            Vec<T>::load(dout + r * C + c, d);
-            if (has_b) Vec<T>::load(dout + rb * C + c, d2);
+    constexpr int U = COL_ROWS_IN_FLIGHT;
+    for (long long r = r0 + rl; r < r1; r += (long long)U * pl.rows_per_iter) {
+        uint4 ry[U], rd[U];
 #pragma unroll
-            for (int k = 0; k < W; ++k) {
-                const float xh = (v[k] - mu[k]) * is[k];
-                const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
-                s1[k] += dz; s2[k] += dz * xh;
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + (long long)u * pl.rows_per_iter;
+            if (rr < r1) {
+                ry[u] = raw16(y + rr * C + c);
+                if (MODE == 0) rd[u] = raw16(dout + rr * C + c);
             }
-            if (has_b) {
+        }
 #pragma unroll
-                for (int k = 0; k < W; ++k) {
-                    const float xh = (v2[k] - mu[k]) * is[k];
-                    const float dz = d2[k] * act_grad_from_in(ga[k] * xh + be[k], act);
-                    s1[k] += dz; s2[k] += dz * xh;
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + (long long)u * pl.rows_per_iter;
+            if (rr < r1) {
+                float v[W];
+                Vec<T>::unpack(ry[u], v);
+                if (MODE == 0) {
+                    float d[W];
+                    Vec<T>::unpack(rd[u], d);
+#pragma unroll
+                    for (int k = 0; k < W; ++k) {
+                        const float xh = (v[k] - mu[k]) * is[k];
+                        const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
+                        s1[k] += dz; s2[k] += dz * xh;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < W; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
                 }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < W; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
-            if (has_b) {
-#pragma unroll
-                for (int k = 0; k < W; ++k) { s1[k] += v2[k]; s2[k] = fmaf(v2[k], v2[k], s2[k]); }
             }
         }
     }

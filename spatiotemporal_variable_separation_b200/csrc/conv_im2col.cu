@@ -24,37 +24,65 @@ struct Im2colParams {
     int wt_shift, ht_shift;
     int tiles_w, tiles_h, tiles_n, total_tiles;
     int ptiles_per_split;        // wgrad
+    int PH, PW, PWC, pelems;     // input patch of one pixel box: rows, columns, columns*C, elements (all NT images)
     int act, has_bias, partial, n_per_group;
 };
 
-// one 16-byte chunk (8 consecutive kk) of pixel (n, p, q)'s receptive field
-__device__ __forceinline__ uint4 im2col_chunk(const Im2colParams& p, const unsigned short* __restrict__ big, const uint32_t* tab,
-                                              int j, bool ok, int n, int pp, int qq) {
+constexpr int IM_PATCH_REGS = 32, IM_BUILDERS = 128, IM_PATCH_MAX = IM_PATCH_REGS * IM_BUILDERS;   // elements
+
+// The input patch a pixel box needs ((HT-1)*stride+R rows x (WT-1)*stride+S columns x C channels per image) is
+// fetched once with coalesced loads -- element e of the flat patch by builder thread e % 128 -- and parked in
+// registers while the previous tile is being built, then written to a double-buffered shared-memory copy (zeros
+// outside the image); the im2col rows are assembled from that copy, not from global memory.
+__device__ __forceinline__ void patch_fetch(const Im2colParams& p, const unsigned short* __restrict__ big, int t, int j0, int i0,
+                                            int b0, unsigned short (&regs)[IM_PATCH_REGS]) {
+    const int hbase = i0 * p.stride - p.pad, xbase = (j0 * p.stride - p.pad) * p.C, WC = p.W * p.C;
+#pragma unroll
+    for (int i = 0; i < IM_PATCH_REGS; ++i) {
+        const int e = i * IM_BUILDERS + t;
+        unsigned short v = 0;
+        if (e < p.pelems) {
+            const int row = e / p.PWC, x = e - row * p.PWC;
+            const int nl = row / p.PH, rr = row - nl * p.PH;
+            const int h = hbase + rr, gx = xbase + x, nn = b0 + nl;
+            if ((unsigned)h < (unsigned)p.H && (unsigned)gx < (unsigned)WC && nn < p.N)
+                v = __ldg(big + ((long long)nn * p.H + h) * WC + gx);
+        }
+        regs[i] = v;
+    }
+}
+__device__ __forceinline__ void patch_store(const Im2colParams& p, int t, const unsigned short (&regs)[IM_PATCH_REGS],
+                                            unsigned short* pbuf) {
+#pragma unroll
+    for (int i = 0; i < IM_PATCH_REGS; ++i) {
+        const int e = i * IM_BUILDERS + t;
+        if (e < p.pelems) pbuf[e] = regs[i];
+    }
+}
+// one 16-byte chunk (8 consecutive kk) of the receptive field whose top-left element sits at pbuf[base]
+__device__ __forceinline__ uint4 im2col_chunk(const Im2colParams& p, const unsigned short* pbuf, const uint32_t* tab, int base, int j) {
     unsigned short v[8];
-    const int h0 = pp * p.stride - p.pad, w0 = qq * p.stride - p.pad;
-    const unsigned short* img = big + (long long)n * p.H * p.W * p.C;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int kk = j * 8 + e;
-        const uint32_t t = tab[kk];                       // r | s << 8 | c << 16 (entries past KK decode to r = 255)
-        const int h = h0 + (int)(t & 255u), w = w0 + (int)((t >> 8) & 255u), c = (int)(t >> 16);
-        const bool in = ok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
-        v[e] = in ? __ldg(img + ((long long)h * p.W + w) * p.C + c) : (unsigned short)0;
+        v[e] = kk < p.KK ? pbuf[base + (int)tab[kk]] : (unsigned short)0;
     }
     return make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16), v[4] | ((uint32_t)v[5] << 16),
                       v[6] | ((uint32_t)v[7] << 16));
 }
 
+// tab[kk] = offset of (r, s, c) inside the patch relative to the receptive field's top-left element
 __device__ __forceinline__ void im2col_table(const Im2colParams& p, uint32_t* tab) {
     for (int kk = threadIdx.x; kk < IM_MAX_KK; kk += blockDim.x) {
-        uint32_t t = 255u;                                // r = 255: always outside the image
+        uint32_t t = 0;
         if (kk < p.KK) {
             const int tap = kk / p.C, c = kk - tap * p.C;
-            t = (uint32_t)(tap / p.S) | ((uint32_t)(tap % p.S) << 8) | ((uint32_t)c << 16);
+            t = (uint32_t)(((tap / p.S) * p.PW + (tap % p.S)) * p.C + c);
         }
         tab[kk] = t;
     }
 }
+__device__ __forceinline__ void builders_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
 // =================================================================================================== forward
 // warps: 0 = spare (weights are staged by everyone at start), 1 = TMEM allocator + MMA issuer, 2..5 = im2col builders,
@@ -66,7 +94,8 @@ struct ImfSmem {
     static constexpr int A_BYTES = KC * TC_BM * 128, B_BYTES = KC * BN * 128;
     static constexpr int BAR_OFF = STAGES * A_BYTES + B_BYTES;
     static constexpr int TAB_OFF = BAR_OFF + 256, STAT_OFF = TAB_OFF + IM_MAX_KK * 4;
-    static constexpr int TOTAL = STAT_OFF + BN * 2 * 4 + 1024;
+    static constexpr int PATCH_OFF = STAT_OFF + BN * 2 * 4;
+    static constexpr int TOTAL = PATCH_OFF + 2 * IM_PATCH_MAX * 2 + 1024;
     static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
 };
 
@@ -88,6 +117,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem + S::TAB_OFF);
     float* sstat = reinterpret_cast<float*>(smem + S::STAT_OFF);
+    unsigned short* pbuf = reinterpret_cast<unsigned short*>(smem + S::PATCH_OFF);      // [2][IM_PATCH_MAX]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.total_tiles;
@@ -154,24 +184,34 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
         // ===== im2col builders: thread = pixel row of the tile =====
         const int m = threadIdx.x - 64;
         const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
+        const int base = ((n * p.PH + h * p.stride) * p.PW + w * p.stride) * p.C;
+        unsigned short regs[IM_PATCH_REGS];
+        {
+            VS_IM_DECODE(blockIdx.x)
+            patch_fetch(p, big, m, j0, i0, b0, regs);
+            patch_store(p, m, regs, pbuf);
+        }
+        builders_sync();
         int lt = 0;
         for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
-            VS_IM_DECODE(idx)
             const int s = lt % STAGES;
-            const int pp = i0 + h, qq = j0 + w, nn = b0 + n;
-            const bool ok = pp < p.P && qq < p.Q && nn < p.N;
+            const int next = idx + gridDim.x;
+            if (next < total) {                      // loads of the next patch stay in flight while this tile is built
+                VS_IM_DECODE(next)
+                patch_fetch(p, big, m, j0, i0, b0, regs);
+            }
+            const unsigned short* pb = pbuf + (lt & 1) * IM_PATCH_MAX;
             uint8_t* a_row = smem + s * S::A_BYTES + m * 128;
-            // gather first (loads in flight while waiting for the slot), then store
-            uint4 first = im2col_chunk(p, big, tab, 0, ok, nn, pp, qq);
             mbar_wait(&empty[s], ((lt / STAGES) & 1) ^ 1);
-            *reinterpret_cast<uint4*>(a_row + ((0 ^ (m & 7)) << 4)) = first;
-            for (int j = 1; j < p.nchunk16; ++j) {
-                const uint4 v = im2col_chunk(p, big, tab, j, ok, nn, pp, qq);
+            for (int j = 0; j < p.nchunk16; ++j) {
+                const uint4 v = im2col_chunk(p, pb, tab, base, j);
                 *reinterpret_cast<uint4*>(a_row + (j >> 3) * (TC_BM * 128) + (((j & 7) ^ (m & 7)) << 4)) = v;
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
+            if (next < total) patch_store(p, m, regs, pbuf + ((lt + 1) & 1) * IM_PATCH_MAX);
+            builders_sync();
         }
     } else if (warp >= 6) {
         // ===== epilogue: one warp per TMEM lane quarter =====
@@ -258,6 +298,8 @@ static void im2col_tiling(Im2colParams& p, int pixels) {
     p.ht_shift = 0; while ((1 << p.ht_shift) < p.HT) ++p.ht_shift;
     p.tiles_w = (int)cdiv(p.Q, p.WT); p.tiles_h = (int)cdiv(p.P, p.HT); p.tiles_n = (int)cdiv(p.N, p.NT);
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.PH = (p.HT - 1) * p.stride + p.R; p.PW = (p.WT - 1) * p.stride + p.S;
+    p.PWC = p.PW * p.C; p.pelems = p.NT * p.PH * p.PWC;
 }
 
 static void im2col_params(Im2colParams& p, const vs_conv_geom* g) {
@@ -278,7 +320,7 @@ int conv_forward_im2col_eligible(const vs_conv_geom* g, int mode) {
     if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || im2col_disabled()) return 0;
     if (mode != VS_CONV_DIRECT) return 0;
     if (g->C >= 32 || g->R * g->S * g->C > IM_MAX_KK || g->K > 128 || g->K < 16 || g->R > 16 || g->S > 16) return 0;
-    if ((long long)g->N * g->P * g->Q < 4096) return 0;        // launch-bound sizes: the streaming kernels are fine
+    if (g->P * g->Q < 256) return 0;       // per-image size only: the choice of kernel must not depend on the batch
     return 1;
 }
 
@@ -306,6 +348,7 @@ int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const v
     Im2colParams p;
     im2col_params(p, g);
     im2col_tiling(p, 128);
+    if (p.pelems > IM_PATCH_MAX) return -1;
     p.act = g->act; p.has_bias = bias != nullptr;
     p.partial = (g->K % 8 != 0) || (reinterpret_cast<uintptr_t>(out) & 15) ? 1 : 0;
     p.n_per_group = g->N / g->groups;
@@ -337,6 +380,7 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256);
+    unsigned short* pbuf = reinterpret_cast<unsigned short*>(smem + STAGES * STAGE_BYTES + 256 + IM_MAX_KK * 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kt = blockIdx.x;
@@ -407,27 +451,34 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
         // ===== builders: items = (16-byte chunk j, pixel m), m fastest =====
         const int t = threadIdx.x - 64;                   // 0..127
         const int items = p.nchunk16 * PIX;
+        unsigned short regs[IM_PATCH_REGS];
+        {
+            VS_IMW_DECODE(pt0)
+            patch_fetch(p, big, t, q0, p0, b0, regs);
+            patch_store(p, t, regs, pbuf);
+        }
+        builders_sync();
         for (int kb = 0; kb < nkb; ++kb) {
             const int st = kb % STAGES;
-            VS_IMW_DECODE(pt0 + kb)
+            if (kb + 1 < nkb) {
+                VS_IMW_DECODE(pt0 + kb + 1)
+                patch_fetch(p, big, t, q0, p0, b0, regs);
+            }
+            const unsigned short* pb = pbuf + (kb & 1) * IM_PATCH_MAX;
             uint8_t* a_dst = smem + st * STAGE_BYTES;
-            bool waited = false;
-            for (int it = t; it < items || !waited; it += 128) {
-                uint4 v = make_uint4(0, 0, 0, 0);
-                int m = 0, j = 0;
-                const bool live = it < items;
-                if (live) {
-                    m = it & (PIX - 1); j = it >> 6;
-                    const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
-                    const int pp = p0 + h, qq = q0 + w, nn = b0 + n;
-                    v = im2col_chunk(p, big, tab, j, pp < p.P && qq < p.Q && nn < p.N, nn, pp, qq);
-                }
-                if (!waited) { mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1); waited = true; }
-                if (live) *reinterpret_cast<uint4*>(a_dst + (j >> 3) * CHUNK + m * 128 + (((j & 7) ^ (m & 7)) << 4)) = v;
+            mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
+            for (int it = t; it < items; it += 128) {
+                const int m = it & (PIX - 1), j = it >> 6;
+                const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
+                const int base = ((n * p.PH + h * p.stride) * p.PW + w * p.stride) * p.C;
+                const uint4 v = im2col_chunk(p, pb, tab, base, j);
+                *reinterpret_cast<uint4*>(a_dst + (j >> 3) * CHUNK + m * 128 + (((j & 7) ^ (m & 7)) << 4)) = v;
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[st]);
+            if (kb + 1 < nkb) patch_store(p, t, regs, pbuf + ((kb + 1) & 1) * IM_PATCH_MAX);
+            builders_sync();
         }
         // ===== epilogue: TMEM lane = kk, column = channel of `small` =====
         const int q = warp & 3;
@@ -459,7 +510,7 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
 template <int BN, int STAGES>
 static int launch_imw(const CUtensorMap& ms, const Im2colParams& p, const void* big, float* dw, int k_tiles, int splits,
                       cudaStream_t stream) {
-    constexpr int SMEM = STAGES * (2 * 64 * 64 * 2 + BN * 64 * 2) + 1024 + 256 + IM_MAX_KK * 4;
+    constexpr int SMEM = STAGES * (2 * 64 * 64 * 2 + BN * 64 * 2) + 1024 + 256 + IM_MAX_KK * 4 + 2 * IM_PATCH_MAX * 2;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(im2col_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -475,7 +526,7 @@ int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big
     if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || im2col_disabled()) return -1;
     if (g->C >= 32 || g->R * g->S * g->C > IM_MAX_KK || g->R > 16 || g->S > 16) return -1;
     if (g->K % 8 != 0 || g->K < 32) return -1;                         // TMA: 16-byte channel pitch of `small`
-    if ((long long)g->N * g->P * g->Q < 4096) return -1;
+    if (g->P * g->Q < 256) return -1;
     if (reinterpret_cast<uintptr_t>(small_) & 15) return -1;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return -1;
@@ -483,7 +534,7 @@ int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big
     im2col_params(p, g);
     im2col_tiling(p, 64);
     // partial boxes in W/H would shift the pixel order inside the TMA box relative to the builder's decode
-    if (g->Q % p.WT != 0 || g->P % p.HT != 0) return -1;
+    if (g->Q % p.WT != 0 || g->P % p.HT != 0 || p.pelems > IM_PATCH_MAX) return -1;
     const int BN = g->K > 64 ? 128 : 64;
     const int k_tiles = (int)cdiv(g->K, BN);
     long long splits = cdiv(4LL * num_sms(), k_tiles);

@@ -69,6 +69,9 @@ CONV_CASES = [
     (12, 40, 40, 3, 48, 4, 2, 1, 2),
     (8, 32, 32, 6, 128, 4, 2, 1, 2),
     (20, 16, 16, 7, 72, 3, 1, 1, 1),
+    # transposed direction of these: GEMM + col2im kernel (nc = 2, two 64-channel chunks, non-square image)
+    (6, 32, 32, 2, 128, 4, 2, 1, 1),
+    (5, 16, 64, 1, 64, 4, 2, 1, 1),
     (33, 1, 1, 148, 24, 4, 1, 0, 3),      # placeholder geometry replaced below
 ]
 # first_upconv: ConvTranspose k4 s1 p0 of a 1x1 input (big side 4x4, small side 1x1)
