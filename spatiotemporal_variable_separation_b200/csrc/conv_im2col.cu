@@ -9,7 +9,9 @@
 //   wgrad   : dw[k][c][tap]   += sum_pix xcol[pix][(tap,c)] * small[pix][k] (MN-major A built, B = TMA boxes of `small`)
 // with kk = (r*S + s)*C + c and xcol[pix][kk] = big[n][p*stride-pad+r][q*stride-pad+s][c] (zero outside the image).
 // The shared-memory image of a tile is the same in both cases: row = pixel, 128 bytes = 64 kk values, the 16-byte
-// chunk index XORed with (row & 7).
+// chunk index XORed with (row & 7).  The input patch a pixel box needs ((HT-1)*stride+R rows of ((WT-1)*stride+S)*C
+// contiguous values) is itself a TMA box of the image viewed as [N][H][W*C] (zero-filled outside), prefetched several
+// tiles ahead, so the builders never wait on global memory.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -24,41 +26,18 @@ struct Im2colParams {
     int wt_shift, ht_shift;
     int tiles_w, tiles_h, tiles_n, total_tiles;
     int ptiles_per_split;        // wgrad
-    int PH, PW, PWC, pelems;     // input patch of one pixel box: rows, columns, columns*C, elements (all NT images)
+    int PH, PWCp, patch_bytes;   // input patch of one pixel box: rows, row pitch in elements (multiple of 8), bytes
     int act, has_bias, partial, n_per_group;
 };
 
-constexpr int IM_PATCH_REGS = 32, IM_BUILDERS = 128, IM_PATCH_MAX = IM_PATCH_REGS * IM_BUILDERS;   // elements
+constexpr int IM_PATCH_STAGE = 8192, IM_PATCH_STAGE_W = 4096, IM_PST = 3;   // bytes per patch stage (forward, wgrad), stages
 
-// The input patch a pixel box needs ((HT-1)*stride+R rows x (WT-1)*stride+S columns x C channels per image) is
-// fetched once with coalesced loads -- element e of the flat patch by builder thread e % 128 -- and parked in
-// registers while the previous tile is being built, then written to a double-buffered shared-memory copy (zeros
-// outside the image); the im2col rows are assembled from that copy, not from global memory.
-__device__ __forceinline__ void patch_fetch(const Im2colParams& p, const unsigned short* __restrict__ big, int t, int j0, int i0,
-                                            int b0, unsigned short (&regs)[IM_PATCH_REGS]) {
-    const int hbase = i0 * p.stride - p.pad, xbase = (j0 * p.stride - p.pad) * p.C, WC = p.W * p.C;
-#pragma unroll
-    for (int i = 0; i < IM_PATCH_REGS; ++i) {
-        const int e = i * IM_BUILDERS + t;
-        unsigned short v = 0;
-        if (e < p.pelems) {
-            const int row = e / p.PWC, x = e - row * p.PWC;
-            const int nl = row / p.PH, rr = row - nl * p.PH;
-            const int h = hbase + rr, gx = xbase + x, nn = b0 + nl;
-            if ((unsigned)h < (unsigned)p.H && (unsigned)gx < (unsigned)WC && nn < p.N)
-                v = __ldg(big + ((long long)nn * p.H + h) * WC + gx);
-        }
-        regs[i] = v;
-    }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void patch_store(const Im2colParams& p, int t, const unsigned short (&regs)[IM_PATCH_REGS],
-                                            unsigned short* pbuf) {
-#pragma unroll
-    for (int i = 0; i < IM_PATCH_REGS; ++i) {
-        const int e = i * IM_BUILDERS + t;
-        if (e < p.pelems) pbuf[e] = regs[i];
-    }
-}
+
 // one 16-byte chunk (8 consecutive kk) of the receptive field whose top-left element sits at pbuf[base]
 __device__ __forceinline__ uint4 im2col_chunk(const Im2colParams& p, const unsigned short* pbuf, const uint32_t* tab, int base, int j) {
     unsigned short v[8];
@@ -77,13 +56,11 @@ __device__ __forceinline__ void im2col_table(const Im2colParams& p, uint32_t* ta
         uint32_t t = 0;
         if (kk < p.KK) {
             const int tap = kk / p.C, c = kk - tap * p.C;
-            t = (uint32_t)(((tap / p.S) * p.PW + (tap % p.S)) * p.C + c);
+            t = (uint32_t)((tap / p.S) * p.PWCp + (tap % p.S) * p.C + c);
         }
         tab[kk] = t;
     }
 }
-__device__ __forceinline__ void builders_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-
 // =================================================================================================== forward
 // warps: 0 = spare (weights are staged by everyone at start), 1 = TMEM allocator + MMA issuer, 2..5 = im2col builders,
 // 6..9 = epilogue.  Persistent over 128-pixel tiles; KC = number of 64-wide kk chunks (1 or 2).
@@ -94,14 +71,14 @@ struct ImfSmem {
     static constexpr int A_BYTES = KC * TC_BM * 128, B_BYTES = KC * BN * 128;
     static constexpr int BAR_OFF = STAGES * A_BYTES + B_BYTES;
     static constexpr int TAB_OFF = BAR_OFF + 256, STAT_OFF = TAB_OFF + IM_MAX_KK * 4;
-    static constexpr int PATCH_OFF = STAT_OFF + BN * 2 * 4;
-    static constexpr int TOTAL = PATCH_OFF + 2 * IM_PATCH_MAX * 2 + 1024;
-    static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
+    static constexpr int PATCH_OFF = (STAT_OFF + BN * 2 * 4 + 127) / 128 * 128;
+    static constexpr int TOTAL = PATCH_OFF + IM_PST * IM_PATCH_STAGE + 1024;
+    static_assert((2 * STAGES + 2 * IM_PST + 5) * 8 <= 256, "barrier area");
 };
 
 template <int BN, int KC, int STAGES>
-__global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid_constant__ Im2colParams p,
-                                                                   const unsigned short* __restrict__ big,
+__global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid_constant__ CUtensorMap map_big,
+                                                                   const __grid_constant__ Im2colParams p,
                                                                    const unsigned short* __restrict__ wp,
                                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                                    double* __restrict__ stats) {
@@ -114,17 +91,21 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
     uint64_t* empty = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* pready = bars + 2 * STAGES + 4;        // [IM_PST] patch landed
+    uint64_t* pempty = pready + IM_PST;              // [IM_PST] patch consumed by the four builder warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + IM_PST);
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem + S::TAB_OFF);
     float* sstat = reinterpret_cast<float*>(smem + S::STAT_OFF);
-    unsigned short* pbuf = reinterpret_cast<unsigned short*>(smem + S::PATCH_OFF);      // [2][IM_PATCH_MAX]
+    uint8_t* pbuf = smem + S::PATCH_OFF;             // [IM_PST][IM_PATCH_STAGE]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.total_tiles;
 
     if (threadIdx.x == 0) {
+        prefetch_tmap(&map_big);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int s = 0; s < IM_PST; ++s) { mbar_init(&pready[s], 1); mbar_init(&pempty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -158,7 +139,19 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
     const int tn = t_ / p.tiles_h;                              \
     const int j0 = tw * p.WT, i0 = th * p.HT, b0 = tn * p.NT;
 
-    if (warp == 1) {
+    if (warp == 0) {
+        // ===== TMA producer: the input patch of every tile, IM_PST tiles ahead =====
+        if (lane == 0) {
+            int lt = 0;
+            for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+                VS_IM_DECODE(idx)
+                const int ps = lt % IM_PST;
+                mbar_wait(&pempty[ps], ((lt / IM_PST) & 1) ^ 1);
+                mbar_expect_tx(&pready[ps], (uint32_t)p.patch_bytes);
+                tma_load_3d(pbuf + ps * IM_PATCH_STAGE, &map_big, &pready[ps], ((j0 * p.stride - p.pad) * p.C) & ~7, i0 * p.stride - p.pad, b0);
+            }
+        }
+    } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_bf16_f32(BN);
@@ -183,25 +176,16 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
     } else if (warp >= 2 && warp < 6) {
         // ===== im2col builders: thread = pixel row of the tile =====
         const int m = threadIdx.x - 64;
-        const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
-        const int base = ((n * p.PH + h * p.stride) * p.PW + w * p.stride) * p.C;
-        unsigned short regs[IM_PATCH_REGS];
-        {
-            VS_IM_DECODE(blockIdx.x)
-            patch_fetch(p, big, m, j0, i0, b0, regs);
-            patch_store(p, m, regs, pbuf);
-        }
-        builders_sync();
+        const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1);
+        const int base = h * p.stride * p.PWCp + w * p.stride * p.C;
         int lt = 0;
         for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
-            const int s = lt % STAGES;
-            const int next = idx + gridDim.x;
-            if (next < total) {                      // loads of the next patch stay in flight while this tile is built
-                VS_IM_DECODE(next)
-                patch_fetch(p, big, m, j0, i0, b0, regs);
-            }
-            const unsigned short* pb = pbuf + (lt & 1) * IM_PATCH_MAX;
+            const int s = lt % STAGES, ps = lt % IM_PST;
+            const int j0 = (idx % p.tiles_w) * p.WT;
+            // the box starts at the 16-byte boundary below the patch's first element
+            const unsigned short* pb = reinterpret_cast<const unsigned short*>(pbuf + ps * IM_PATCH_STAGE) + (((j0 * p.stride - p.pad) * p.C) & 7);
             uint8_t* a_row = smem + s * S::A_BYTES + m * 128;
+            mbar_wait(&pready[ps], (lt / IM_PST) & 1);
             mbar_wait(&empty[s], ((lt / STAGES) & 1) ^ 1);
             for (int j = 0; j < p.nchunk16; ++j) {
                 const uint4 v = im2col_chunk(p, pb, tab, base, j);
@@ -209,9 +193,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-            if (next < total) patch_store(p, m, regs, pbuf + ((lt + 1) & 1) * IM_PATCH_MAX);
-            builders_sync();
+            if (lane == 0) { mbar_arrive(&full[s]); mbar_arrive(&pempty[ps]); }
         }
     } else if (warp >= 6) {
         // ===== epilogue: one warp per TMEM lane quarter =====
@@ -290,24 +272,44 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
     }
 }
 
-static void im2col_tiling(Im2colParams& p, int pixels) {
-    p.WT = pow2ceil(p.Q) < pixels ? pow2ceil(p.Q) : pixels;
-    p.HT = pow2ceil(p.P) < pixels / p.WT ? pow2ceil(p.P) : pixels / p.WT;
-    p.NT = pixels / (p.WT * p.HT);
-    p.wt_shift = 0; while ((1 << p.wt_shift) < p.WT) ++p.wt_shift;
-    p.ht_shift = 0; while ((1 << p.ht_shift) < p.HT) ++p.ht_shift;
-    p.tiles_w = (int)cdiv(p.Q, p.WT); p.tiles_h = (int)cdiv(p.P, p.HT); p.tiles_n = (int)cdiv(p.N, p.NT);
-    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    p.PH = (p.HT - 1) * p.stride + p.R; p.PW = (p.WT - 1) * p.stride + p.S;
-    p.PWC = p.PW * p.C; p.pelems = p.NT * p.PH * p.PWC;
-}
-
-static void im2col_params(Im2colParams& p, const vs_conv_geom* g) {
+// geometry, pixel box and input patch of one tile; false if the layer does not fit this kernel family
+static bool im2col_plan(Im2colParams& p, const vs_conv_geom* g, int pixels, int max_patch_bytes) {
     memset(&p, 0, sizeof(p));
     p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
     p.stride = g->stride; p.pad = g->pad;
     p.KK = g->R * g->S * g->C;
     p.nchunk16 = (p.KK + 7) / 8;
+    if (g->C >= 32 || p.KK > IM_MAX_KK || g->R > 16 || g->S > 16) return false;
+    if (g->P * g->Q < 256) return false;       // per-image size only: the choice of kernel must not depend on the batch
+    if (((long long)g->W * g->C * 2) % 16 != 0) return false;      // TMA row pitch of the [N][H][W*C] view
+    // widest pixel box whose patch rows still fit one TMA box (<= 256 elements)
+    p.WT = pow2ceil(p.Q) < pixels ? pow2ceil(p.Q) : pixels;
+    // (the box starts at a multiple of 8 elements -- TMA needs a 16-byte aligned innermost coordinate -- hence +7)
+    while (p.WT > 1 && (((p.WT - 1) * p.stride + p.S) * p.C + 7 + 7) / 8 * 8 > 256) p.WT >>= 1;
+    p.HT = pow2ceil(p.P) < pixels / p.WT ? pow2ceil(p.P) : pixels / p.WT;
+    p.NT = pixels / (p.WT * p.HT);
+    if (p.NT != 1) return false;
+    p.wt_shift = 0; while ((1 << p.wt_shift) < p.WT) ++p.wt_shift;
+    p.ht_shift = 0; while ((1 << p.ht_shift) < p.HT) ++p.ht_shift;
+    p.tiles_w = (int)cdiv(p.Q, p.WT); p.tiles_h = (int)cdiv(p.P, p.HT); p.tiles_n = p.N;
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.PH = (p.HT - 1) * p.stride + p.R;
+    p.PWCp = (((p.WT - 1) * p.stride + p.S) * p.C + 7 + 7) / 8 * 8;
+    p.patch_bytes = p.PH * p.PWCp * 2;
+    return p.PH <= 256 && p.PWCp <= 256 && p.patch_bytes <= max_patch_bytes;
+}
+
+static int im2col_big_map(CUtensorMap& mb, const Im2colParams& p, const void* big) {
+    EncodeTiledFn enc = encode_fn();
+    cuuint64_t dims[3] = {(cuuint64_t)p.W * p.C, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t strides[2] = {(cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)p.PWCp, (cuuint32_t)p.PH, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(big), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(im2col patch) failed: %d", (int)rc);
+    return 0;
 }
 
 static bool im2col_disabled() {
@@ -318,14 +320,13 @@ static bool im2col_disabled() {
 
 int conv_forward_im2col_eligible(const vs_conv_geom* g, int mode) {
     if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || im2col_disabled()) return 0;
-    if (mode != VS_CONV_DIRECT) return 0;
-    if (g->C >= 32 || g->R * g->S * g->C > IM_MAX_KK || g->K > 128 || g->K < 16 || g->R > 16 || g->S > 16) return 0;
-    if (g->P * g->Q < 256) return 0;       // per-image size only: the choice of kernel must not depend on the batch
-    return 1;
+    if (mode != VS_CONV_DIRECT || g->K > 128 || g->K < 16) return 0;
+    Im2colParams p;
+    return im2col_plan(p, g, 128, IM_PATCH_STAGE) ? 1 : 0;
 }
 
 template <int BN, int KC, int STAGES>
-static int launch_imf(const Im2colParams& p, const void* big, const void* wp, const float* bias, void* out, double* stats,
+static int launch_imf(const CUtensorMap& mb, const Im2colParams& p, const void* wp, const float* bias, void* out, double* stats,
                       cudaStream_t stream) {
     using S = ImfSmem<BN, KC, STAGES>;
     static bool configured = false;
@@ -337,7 +338,7 @@ static int launch_imf(const Im2colParams& p, const void* big, const void* wp, co
     const int resident = 2 * num_sms();
     const int grid = p.total_tiles < resident ? p.total_tiles : resident;
     im2col_fwd_kernel<BN, KC, STAGES><<<grid, IMF_THREADS, S::TOTAL, stream>>>(
-        p, (const unsigned short*)big, (const unsigned short*)wp, bias, (__nv_bfloat16*)out, stats);
+        mb, p, (const unsigned short*)wp, bias, (__nv_bfloat16*)out, stats);
     return launched("im2col_fwd_kernel");
 }
 
@@ -345,10 +346,12 @@ static int launch_imf(const Im2colParams& p, const void* big, const void* wp, co
 int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                         double* stats, cudaStream_t stream) {
     if (!conv_forward_im2col_eligible(g, mode)) return -1;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return -1;
+    if (!encode_fn()) return -1;
     Im2colParams p;
-    im2col_params(p, g);
-    im2col_tiling(p, 128);
-    if (p.pelems > IM_PATCH_MAX) return -1;
+    if (!im2col_plan(p, g, 128, IM_PATCH_STAGE)) return -1;
+    CUtensorMap mb;
+    if (int rc = im2col_big_map(mb, p, in)) return rc;
     p.act = g->act; p.has_bias = bias != nullptr;
     p.partial = (g->K % 8 != 0) || (reinterpret_cast<uintptr_t>(out) & 15) ? 1 : 0;
     p.n_per_group = g->N / g->groups;
@@ -356,8 +359,8 @@ int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const v
     double* st = fuse_stats ? stats : nullptr;
     const int KC = p.KK > 64 ? 2 : 1;
     int rc;
-    if (g->K <= 64) rc = KC == 1 ? launch_imf<64, 1, 4>(p, in, wp, bias, out, st, stream) : launch_imf<64, 2, 2>(p, in, wp, bias, out, st, stream);
-    else            rc = KC == 1 ? launch_imf<128, 1, 4>(p, in, wp, bias, out, st, stream) : launch_imf<128, 2, 2>(p, in, wp, bias, out, st, stream);
+    if (g->K <= 64) rc = KC == 1 ? launch_imf<64, 1, 4>(mb, p, wp, bias, out, st, stream) : launch_imf<64, 2, 2>(mb, p, wp, bias, out, st, stream);
+    else            rc = KC == 1 ? launch_imf<128, 1, 4>(mb, p, wp, bias, out, st, stream) : launch_imf<128, 2, 2>(mb, p, wp, bias, out, st, stream);
     if (rc) return rc;
     if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * g->P * g->Q, g->K, stats, stream);
     return 0;
@@ -368,8 +371,8 @@ int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const v
 // builders during the reduction, then the epilogue (fp32 reductions into the torch-layout gradient).
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_constant__ CUtensorMap map_small,
-                                                              const __grid_constant__ Im2colParams p,
-                                                              const unsigned short* __restrict__ big, float* __restrict__ dw) {
+                                                              const __grid_constant__ CUtensorMap map_big,
+                                                              const __grid_constant__ Im2colParams p, float* __restrict__ dw) {
     constexpr int PIX = 64, CHUNK = 64 * PIX * 2;
     constexpr int A_BYTES = 2 * CHUNK, B_BYTES = BN * PIX * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -378,9 +381,11 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint64_t* pready = bars + 2 * STAGES + 1;
+    uint64_t* pempty = pready + IM_PST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + IM_PST);
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256);
-    unsigned short* pbuf = reinterpret_cast<unsigned short*>(smem + STAGES * STAGE_BYTES + 256 + IM_MAX_KK * 4);
+    uint8_t* pbuf = smem + STAGES * STAGE_BYTES + 256 + IM_MAX_KK * 4;       // [IM_PST][IM_PATCH_STAGE_W], 128-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kt = blockIdx.x;
@@ -391,7 +396,9 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_small);
+        prefetch_tmap(&map_big);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }     // TMA expect + 4 builder warps
+        for (int i = 0; i < IM_PST; ++i) { mbar_init(&pready[i], 1); mbar_init(&pempty[i], 4); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -421,9 +428,12 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
     if (warp == 0) {
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % STAGES;
-                mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
+                const int st = kb % STAGES, ps = kb % IM_PST;
                 VS_IMW_DECODE(pt0 + kb)
+                mbar_wait(&pempty[ps], ((kb / IM_PST) & 1) ^ 1);
+                mbar_expect_tx(&pready[ps], (uint32_t)p.patch_bytes);
+                tma_load_3d(pbuf + ps * IM_PATCH_STAGE_W, &map_big, &pready[ps], ((q0 * p.stride - p.pad) * p.C) & ~7, p0 * p.stride - p.pad, b0);
+                mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
                 uint8_t* b_dst = smem + st * STAGE_BYTES + A_BYTES;
                 mbar_expect_tx(&full[st], B_BYTES);
 #pragma unroll
@@ -451,34 +461,23 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
         // ===== builders: items = (16-byte chunk j, pixel m), m fastest =====
         const int t = threadIdx.x - 64;                   // 0..127
         const int items = p.nchunk16 * PIX;
-        unsigned short regs[IM_PATCH_REGS];
-        {
-            VS_IMW_DECODE(pt0)
-            patch_fetch(p, big, t, q0, p0, b0, regs);
-            patch_store(p, t, regs, pbuf);
-        }
-        builders_sync();
         for (int kb = 0; kb < nkb; ++kb) {
-            const int st = kb % STAGES;
-            if (kb + 1 < nkb) {
-                VS_IMW_DECODE(pt0 + kb + 1)
-                patch_fetch(p, big, t, q0, p0, b0, regs);
-            }
-            const unsigned short* pb = pbuf + (kb & 1) * IM_PATCH_MAX;
+            const int st = kb % STAGES, ps = kb % IM_PST;
+            const int q0 = ((pt0 + kb) % p.tiles_w) * p.WT;
+            const unsigned short* pb = reinterpret_cast<const unsigned short*>(pbuf + ps * IM_PATCH_STAGE_W) + (((q0 * p.stride - p.pad) * p.C) & 7);
             uint8_t* a_dst = smem + st * STAGE_BYTES;
+            mbar_wait(&pready[ps], (kb / IM_PST) & 1);
             mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
             for (int it = t; it < items; it += 128) {
                 const int m = it & (PIX - 1), j = it >> 6;
-                const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
-                const int base = ((n * p.PH + h * p.stride) * p.PW + w * p.stride) * p.C;
+                const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1);
+                const int base = h * p.stride * p.PWCp + w * p.stride * p.C;
                 const uint4 v = im2col_chunk(p, pb, tab, base, j);
                 *reinterpret_cast<uint4*>(a_dst + (j >> 3) * CHUNK + m * 128 + (((j & 7) ^ (m & 7)) << 4)) = v;
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[st]);
-            if (kb + 1 < nkb) patch_store(p, t, regs, pbuf + ((kb + 1) & 1) * IM_PATCH_MAX);
-            builders_sync();
+            if (lane == 0) { mbar_arrive(&full[st]); mbar_arrive(&pempty[ps]); }
         }
         // ===== epilogue: TMEM lane = kk, column = channel of `small` =====
         const int q = warp & 3;
@@ -508,9 +507,10 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
 }
 
 template <int BN, int STAGES>
-static int launch_imw(const CUtensorMap& ms, const Im2colParams& p, const void* big, float* dw, int k_tiles, int splits,
+static int launch_imw(const CUtensorMap& ms, const CUtensorMap& mb, const Im2colParams& p, float* dw, int k_tiles, int splits,
                       cudaStream_t stream) {
-    constexpr int SMEM = STAGES * (2 * 64 * 64 * 2 + BN * 64 * 2) + 1024 + 256 + IM_MAX_KK * 4 + 2 * IM_PATCH_MAX * 2;
+    constexpr int SMEM = STAGES * (2 * 64 * 64 * 2 + BN * 64 * 2) + 1024 + 256 + IM_MAX_KK * 4 + IM_PST * IM_PATCH_STAGE_W;
+    static_assert((2 * STAGES + 2 * IM_PST + 2) * 8 <= 256, "barrier area");
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(im2col_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -518,26 +518,25 @@ static int launch_imw(const CUtensorMap& ms, const Im2colParams& p, const void* 
         configured = true;
     }
     dim3 grid((unsigned)k_tiles, 1, (unsigned)splits);
-    im2col_wgrad_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(ms, p, (const unsigned short*)big, dw);
+    im2col_wgrad_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(ms, mb, p, dw);
     return launched("im2col_wgrad_kernel");
 }
 
 int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream) {
     if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || im2col_disabled()) return -1;
-    if (g->C >= 32 || g->R * g->S * g->C > IM_MAX_KK || g->R > 16 || g->S > 16) return -1;
     if (g->K % 8 != 0 || g->K < 32) return -1;                         // TMA: 16-byte channel pitch of `small`
-    if (g->P * g->Q < 256) return -1;
-    if (reinterpret_cast<uintptr_t>(small_) & 15) return -1;
+    if ((reinterpret_cast<uintptr_t>(small_) | reinterpret_cast<uintptr_t>(big)) & 15) return -1;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return -1;
     Im2colParams p;
-    im2col_params(p, g);
-    im2col_tiling(p, 64);
+    if (!im2col_plan(p, g, 64, IM_PATCH_STAGE_W)) return -1;
     // partial boxes in W/H would shift the pixel order inside the TMA box relative to the builder's decode
-    if (g->Q % p.WT != 0 || g->P % p.HT != 0 || p.pelems > IM_PATCH_MAX) return -1;
+    if (g->Q % p.WT != 0 || g->P % p.HT != 0) return -1;
+    CUtensorMap mb;
+    if (int rc = im2col_big_map(mb, p, big)) return rc;
     const int BN = g->K > 64 ? 128 : 64;
     const int k_tiles = (int)cdiv(g->K, BN);
-    long long splits = cdiv(4LL * num_sms(), k_tiles);
+    long long splits = cdiv(2LL * num_sms(), k_tiles);       // two CTAs per SM; fewer CTAs = fewer colliding atomics
     if (splits > p.total_tiles) splits = p.total_tiles;
     if (splits > 65535) splits = 65535;
     p.ptiles_per_split = (int)cdiv(p.total_tiles, splits);
@@ -553,8 +552,8 @@ int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(small) failed: %d", (int)rc);
     }
-    return BN == 128 ? launch_imw<128, 3>(ms, p, big, dw, k_tiles, (int)splits, stream)
-                     : launch_imw<64, 4>(ms, p, big, dw, k_tiles, (int)splits, stream);
+    return BN == 128 ? launch_imw<128, 3>(ms, mb, p, dw, k_tiles, (int)splits, stream)
+                     : launch_imw<64, 4>(ms, mb, p, dw, k_tiles, (int)splits, stream);
 }
 
 }  // namespace vs
