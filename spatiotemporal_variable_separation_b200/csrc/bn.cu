@@ -210,6 +210,15 @@ template <> struct Vec<__nv_bfloat16> {
     }
 };
 
+// compile-time activation for the common cases (the identity, ReLU, LeakyReLU(0.2)), runtime switch otherwise
+#define VS_DISPATCH_ACT(act, A, ...)                                              \
+    switch (act) {                                                                \
+        case VS_ACT_NONE: { constexpr int A = VS_ACT_NONE; __VA_ARGS__ } break;   \
+        case VS_ACT_RELU: { constexpr int A = VS_ACT_RELU; __VA_ARGS__ } break;   \
+        case VS_ACT_LEAKY: { constexpr int A = VS_ACT_LEAKY; __VA_ARGS__ } break; \
+        default: { constexpr int A = -1; __VA_ARGS__ } break;                     \
+    }
+
 struct ColPlan {
     int tpr;             // threads per row = C / W
     int rows_per_iter;   // 256 / tpr
@@ -245,44 +254,51 @@ static bool col_plan(long long rows, int C, int G, ColPlan& pl, int blocks_per_s
     long long r1 = r0 + pl.per;                                                           \
     if (r1 > (long long)(g + 1) * pl.rpg) r1 = (long long)(g + 1) * pl.rpg;
 
-template <typename T>
+// ACT >= 0: activation known at compile time (no per-element switch); ACT < 0: use the runtime argument
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bn_act_fwd_col_kernel(const T* __restrict__ y, T* __restrict__ out, int C, ColPlan pl,
                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int act) {
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int act_rt) {
+    const int act = ACT >= 0 ? ACT : act_rt;
     VS_COL_SETUP
     float mu[W], is[W], ga[W], be[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
-    // several independent rows in flight per thread (raw 16-byte loads first, conversion afterwards): the kernel is
-    // bound by the bytes in flight per SM, not by arithmetic
+    // several independent rows in flight per thread (all raw 16-byte loads of a group are issued before any is
+    // consumed; the group loop is branch-free so that the compiler keeps them back to back): the kernel is bound by
+    // the bytes in flight per SM, not by arithmetic
     constexpr int U = COL_ROWS_IN_FLIGHT;
-    for (long long r = r0 + rl; r < r1; r += (long long)U * pl.rows_per_iter) {
+    const long long step = pl.rows_per_iter;
+    long long r = r0 + rl;
+    for (; r + (U - 1) * step < r1; r += U * step) {
         uint4 raw[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long rr = r + (long long)u * pl.rows_per_iter;
-            if (rr < r1) raw[u] = raw16(y + rr * C + c);
-        }
+        for (int u = 0; u < U; ++u) raw[u] = raw16(y + (r + u * step) * C + c);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long rr = r + (long long)u * pl.rows_per_iter;
-            if (rr < r1) {
-                float v[W];
-                Vec<T>::unpack(raw[u], v);
+            float v[W];
+            Vec<T>::unpack(raw[u], v);
 #pragma unroll
-                for (int k = 0; k < W; ++k) v[k] = act_fwd(ga[k] * ((v[k] - mu[k]) * is[k]) + be[k], act);
-                Vec<T>::store(out + rr * C + c, v);
-            }
+            for (int k = 0; k < W; ++k) v[k] = act_fwd(ga[k] * ((v[k] - mu[k]) * is[k]) + be[k], act);
+            Vec<T>::store(out + (r + u * step) * C + c, v);
         }
+    }
+    for (; r < r1; r += step) {
+        float v[W];
+        Vec<T>::unpack(raw16(y + r * C + c), v);
+#pragma unroll
+        for (int k = 0; k < W; ++k) v[k] = act_fwd(ga[k] * ((v[k] - mu[k]) * is[k]) + be[k], act);
+        Vec<T>::store(out + r * C + c, v);
     }
 }
 
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bn_bwd_apply_col_kernel(const T* __restrict__ dout, const T* __restrict__ y, T* __restrict__ dy,
                                                                int C, ColPlan pl, const float* __restrict__ mean,
                                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, int act,
+                                                               const float* __restrict__ beta, int act_rt,
                                                                const double* __restrict__ sums, int train) {
+    const int act = ACT >= 0 ? ACT : act_rt;
     VS_COL_SETUP
     float mu[W], is[W], ga[W], be[W], m1[W], m2[W];
     const float inv_count = 1.f / (float)pl.rpg;
@@ -293,38 +309,37 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_col_kernel(const T* __restri
         m2[k] = train ? (float)sums[((long long)g * C + c + k) * 2 + 1] * inv_count : 0.f;
     }
     constexpr int U = COL_ROWS_IN_FLIGHT;
-    for (long long r = r0 + rl; r < r1; r += (long long)U * pl.rows_per_iter) {
+    const long long step = pl.rows_per_iter;
+    auto apply = [&](const uint4& qy, const uint4& qd, long long rr) {
+        float v[W], d[W];
+        Vec<T>::unpack(qy, v);
+        Vec<T>::unpack(qd, d);
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const float xh = (v[k] - mu[k]) * is[k];
+            const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
+            d[k] = ga[k] * is[k] * (dz - m1[k] - xh * m2[k]);
+        }
+        Vec<T>::store(dy + rr * C + c, d);
+    };
+    long long r = r0 + rl;
+    for (; r + (U - 1) * step < r1; r += U * step) {
         uint4 ry[U], rd[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long rr = r + (long long)u * pl.rows_per_iter;
-            if (rr < r1) { ry[u] = raw16(y + rr * C + c); rd[u] = raw16(dout + rr * C + c); }
-        }
+        for (int u = 0; u < U; ++u) { ry[u] = raw16(y + (r + u * step) * C + c); rd[u] = raw16(dout + (r + u * step) * C + c); }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long rr = r + (long long)u * pl.rows_per_iter;
-            if (rr < r1) {
-                float v[W], d[W];
-                Vec<T>::unpack(ry[u], v);
-                Vec<T>::unpack(rd[u], d);
-#pragma unroll
-                for (int k = 0; k < W; ++k) {
-                    const float xh = (v[k] - mu[k]) * is[k];
-                    const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
-                    d[k] = ga[k] * is[k] * (dz - m1[k] - xh * m2[k]);
-                }
-                Vec<T>::store(dy + rr * C + c, d);
-            }
-        }
+        for (int u = 0; u < U; ++u) apply(ry[u], rd[u], r + u * step);
     }
+    for (; r < r1; r += step) apply(raw16(y + r * C + c), raw16(dout + r * C + c), r);
 }
 
 // MODE 0: BatchNorm backward sums {sum dz, sum dz*xhat};  MODE 1: forward statistics {sum y, sum y^2}
-template <typename T, int MODE>
+template <typename T, int MODE, int ACT>
 __global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict__ dout, const T* __restrict__ y, int C, ColPlan pl,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int act_rt,
                                                             double* __restrict__ sums) {
+    const int act = ACT >= 0 ? ACT : act_rt;
     VS_COL_SETUP
     __shared__ float red[2][256 * 8];
     float mu[W], is[W], ga[W], be[W], s1[W], s2[W];
@@ -334,38 +349,36 @@ __global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict_
         if (MODE == 0) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
     }
     constexpr int U = COL_ROWS_IN_FLIGHT;
-    for (long long r = r0 + rl; r < r1; r += (long long)U * pl.rows_per_iter) {
+    const long long step = pl.rows_per_iter;
+    auto accumulate = [&](const uint4& qy, const uint4& qd) {
+        float v[W];
+        Vec<T>::unpack(qy, v);
+        if (MODE == 0) {
+            float d[W];
+            Vec<T>::unpack(qd, d);
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                const float xh = (v[k] - mu[k]) * is[k];
+                const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
+                s1[k] += dz; s2[k] += dz * xh;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < W; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
+        }
+    };
+    long long r = r0 + rl;
+    for (; r + (U - 1) * step < r1; r += U * step) {
         uint4 ry[U], rd[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long rr = r + (long long)u * pl.rows_per_iter;
-            if (rr < r1) {
-                ry[u] = raw16(y + rr * C + c);
-                if (MODE == 0) rd[u] = raw16(dout + rr * C + c);
-            }
+            ry[u] = raw16(y + (r + u * step) * C + c);
+            rd[u] = MODE == 0 ? raw16(dout + (r + u * step) * C + c) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long rr = r + (long long)u * pl.rows_per_iter;
-            if (rr < r1) {
-                float v[W];
-                Vec<T>::unpack(ry[u], v);
-                if (MODE == 0) {
-                    float d[W];
-                    Vec<T>::unpack(rd[u], d);
-#pragma unroll
-                    for (int k = 0; k < W; ++k) {
-                        const float xh = (v[k] - mu[k]) * is[k];
-                        const float dz = d[k] * act_grad_from_in(ga[k] * xh + be[k], act);
-                        s1[k] += dz; s2[k] += dz * xh;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < W; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
-                }
-            }
-        }
+        for (int u = 0; u < U; ++u) accumulate(ry[u], rd[u]);
     }
+    for (; r < r1; r += step) accumulate(raw16(y + r * C + c), MODE == 0 ? raw16(dout + r * C + c) : make_uint4(0, 0, 0, 0));
     // reduce the row lanes of the block (threads with equal threadIdx.x % tpr), then fp64 atomics
 #pragma unroll
     for (int k = 0; k < W; ++k) { red[0][threadIdx.x * W + k] = s1[k]; red[1][threadIdx.x * W + k] = s2[k]; }
@@ -390,7 +403,7 @@ int column_stats(const void* y, int dtype, long long rows, int C, int G, double*
     VS_DISPATCH_DTYPE(dtype, T, {
         ColPlan pl;
         if (!col_plan<T>(rows, C, G, pl, 8)) return -1;
-        bn_reduce_col_kernel<T, 1><<<(unsigned)(G * pl.chunks), 256, 0, stream>>>(nullptr, (const T*)y, C, pl, nullptr, nullptr,
+        bn_reduce_col_kernel<T, 1, 0><<<(unsigned)(G * pl.chunks), 256, 0, stream>>>(nullptr, (const T*)y, C, pl, nullptr, nullptr,
                                                                                    nullptr, nullptr, 0, stats);
     });
     return launched("bn_reduce_col_kernel");
@@ -432,7 +445,9 @@ extern "C" int vs_bn_act_forward(const void* y, void* out, int32_t dtype, int64_
     VS_DISPATCH_DTYPE(dtype, T, {
         ColPlan pl;
         if (col_plan<T>(rows, C, G, pl)) {
-            bn_act_fwd_col_kernel<T><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)y, (T*)out, C, pl, mean, invstd, gamma, beta, act);
+            VS_DISPATCH_ACT(act, A, {
+                bn_act_fwd_col_kernel<T, A><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)y, (T*)out, C, pl, mean, invstd, gamma, beta, act);
+            });
             return launched("bn_act_fwd_col_kernel");
         }
     });
@@ -454,7 +469,9 @@ extern "C" int vs_bn_act_backward_reduce(const void* dout, const void* y, int32_
     VS_DISPATCH_DTYPE(dtype, T, {
         ColPlan pl;
         if (col_plan<T>(rows, C, G, pl, 8)) {
-            bn_reduce_col_kernel<T, 0><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, C, pl, mean, invstd, gamma, beta, act, sums);
+            VS_DISPATCH_ACT(act, A, {
+                bn_reduce_col_kernel<T, 0, A><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, C, pl, mean, invstd, gamma, beta, act, sums);
+            });
             return launched("bn_reduce_col_kernel");
         }
     });
@@ -480,7 +497,9 @@ extern "C" int vs_bn_act_backward_apply(const void* dout, const void* y, void* d
     VS_DISPATCH_DTYPE(dtype, T, {
         ColPlan pl;
         if (col_plan<T>(rows, C, G, pl)) {
-            bn_bwd_apply_col_kernel<T><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, C, pl, mean, invstd, gamma, beta, act, sums, train);
+            VS_DISPATCH_ACT(act, A, {
+                bn_bwd_apply_col_kernel<T, A><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, C, pl, mean, invstd, gamma, beta, act, sums, train);
+            });
             done = true;
         }
     });

@@ -27,6 +27,7 @@ struct Im2colParams {
     int tiles_w, tiles_h, tiles_n, total_tiles;
     int ptiles_per_split;        // wgrad
     int PH, PWCp, patch_bytes;   // input patch of one pixel box: rows, row pitch in elements (multiple of 8), bytes
+    int patch_stage;             // bytes between patch stages (patch_bytes rounded up to 128)
     int act, has_bias, partial, n_per_group;
 };
 
@@ -66,26 +67,31 @@ __device__ __forceinline__ void im2col_table(const Im2colParams& p, uint32_t* ta
 // 6..9 = epilogue.  Persistent over 128-pixel tiles; KC = number of 64-wide kk chunks (1 or 2).
 constexpr int IMF_THREADS = 320;
 
-template <int BN, int KC, int STAGES>
+template <int BN, int KC, int STAGES, bool TS>
 struct ImfSmem {
     static constexpr int A_BYTES = KC * TC_BM * 128, B_BYTES = KC * BN * 128;
-    static constexpr int BAR_OFF = STAGES * A_BYTES + B_BYTES;
+    static constexpr int OUT_OFF = STAGES * A_BYTES + B_BYTES;
+    static constexpr int OUT_BYTES = TS ? 2 * TC_BM * 128 : 0;       // two staged bf16 output tiles (BN = 64)
+    static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
     static constexpr int TAB_OFF = BAR_OFF + 256, STAT_OFF = TAB_OFF + IM_MAX_KK * 4;
     static constexpr int PATCH_OFF = (STAT_OFF + BN * 2 * 4 + 127) / 128 * 128;
-    static constexpr int TOTAL = PATCH_OFF + IM_PST * IM_PATCH_STAGE + 1024;
+    static constexpr int total(int patch_stage) { return PATCH_OFF + IM_PST * patch_stage + 1024; }
     static_assert((2 * STAGES + 2 * IM_PST + 5) * 8 <= 256, "barrier area");
+    static_assert(!TS || BN == 64, "the staged epilogue handles one 128-byte row per pixel");
 };
 
-template <int BN, int KC, int STAGES>
+template <int BN, int KC, int STAGES, bool TS>
 __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid_constant__ CUtensorMap map_big,
+                                                                   const __grid_constant__ CUtensorMap map_out,
                                                                    const __grid_constant__ Im2colParams p,
                                                                    const unsigned short* __restrict__ wp,
                                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                                    double* __restrict__ stats) {
-    using S = ImfSmem<BN, KC, STAGES>;
+    using S = ImfSmem<BN, KC, STAGES, TS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* b_smem = smem + STAGES * S::A_BYTES;
+    uint8_t* obuf = smem + S::OUT_OFF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + IM_PST);
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem + S::TAB_OFF);
     float* sstat = reinterpret_cast<float*>(smem + S::STAT_OFF);
-    uint8_t* pbuf = smem + S::PATCH_OFF;             // [IM_PST][IM_PATCH_STAGE]
+    uint8_t* pbuf = smem + S::PATCH_OFF;             // [IM_PST][p.patch_stage]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.total_tiles;
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
                 const int ps = lt % IM_PST;
                 mbar_wait(&pempty[ps], ((lt / IM_PST) & 1) ^ 1);
                 mbar_expect_tx(&pready[ps], (uint32_t)p.patch_bytes);
-                tma_load_3d(pbuf + ps * IM_PATCH_STAGE, &map_big, &pready[ps], ((j0 * p.stride - p.pad) * p.C) & ~7, i0 * p.stride - p.pad, b0);
+                tma_load_3d(pbuf + ps * p.patch_stage, &map_big, &pready[ps], ((j0 * p.stride - p.pad) * p.C) & ~7, i0 * p.stride - p.pad, b0);
             }
         }
     } else if (warp == 1) {
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
             const int s = lt % STAGES, ps = lt % IM_PST;
             const int j0 = (idx % p.tiles_w) * p.WT;
             // the box starts at the 16-byte boundary below the patch's first element
-            const unsigned short* pb = reinterpret_cast<const unsigned short*>(pbuf + ps * IM_PATCH_STAGE) + (((j0 * p.stride - p.pad) * p.C) & 7);
+            const unsigned short* pb = reinterpret_cast<const unsigned short*>(pbuf + ps * p.patch_stage) + (((j0 * p.stride - p.pad) * p.C) & 7);
             uint8_t* a_row = smem + s * S::A_BYTES + m * 128;
             mbar_wait(&pready[ps], (lt / IM_PST) & 1);
             mbar_wait(&empty[s], ((lt / STAGES) & 1) ^ 1);
@@ -217,7 +223,9 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
                 float xs[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
-                if (p.partial || BN > p.K) {
+                if (TS) {
+                    stage_row32(obuf + (lt & 1) * (TC_BM * 128), m, c0, xs, p.act);
+                } else if (p.partial || BN > p.K) {
                     if (ok) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
@@ -252,8 +260,19 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            if (stats != nullptr) {
+            if (TS) {
+                // staged tile complete -> one TMA store (clipped at the tensor edges); the previous tile's store is drained
+                // first so that its buffer can be refilled by the next tile
+                fence_proxy_async();
+                if (threadIdx.x == 192) tma_store_wait_read();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 192) {
+                    tma_store_4d(&map_out, obuf + (lt & 1) * (TC_BM * 128), 0, j0, i0, b0);
+                    tma_store_commit();
+                }
+            }
+            if (stats != nullptr) {
+                if (!TS) asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int g = b0 / p.n_per_group;
                 const int t = threadIdx.x - 192;
                 for (int i = t; i < 2 * BN; i += 128) {
@@ -264,6 +283,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
         }
+        if (TS && threadIdx.x == 192) tma_store_wait_all();
     }
     __syncthreads();
     if (warp == 1) {
@@ -296,6 +316,7 @@ static bool im2col_plan(Im2colParams& p, const vs_conv_geom* g, int pixels, int 
     p.PH = (p.HT - 1) * p.stride + p.R;
     p.PWCp = (((p.WT - 1) * p.stride + p.S) * p.C + 7 + 7) / 8 * 8;
     p.patch_bytes = p.PH * p.PWCp * 2;
+    p.patch_stage = (p.patch_bytes + 127) / 128 * 128;
     return p.PH <= 256 && p.PWCp <= 256 && p.patch_bytes <= max_patch_bytes;
 }
 
@@ -325,20 +346,21 @@ int conv_forward_im2col_eligible(const vs_conv_geom* g, int mode) {
     return im2col_plan(p, g, 128, IM_PATCH_STAGE) ? 1 : 0;
 }
 
-template <int BN, int KC, int STAGES>
-static int launch_imf(const CUtensorMap& mb, const Im2colParams& p, const void* wp, const float* bias, void* out, double* stats,
-                      cudaStream_t stream) {
-    using S = ImfSmem<BN, KC, STAGES>;
+template <int BN, int KC, int STAGES, bool TS>
+static int launch_imf(const CUtensorMap& mb, const CUtensorMap& mo, const Im2colParams& p, const void* wp, const float* bias,
+                      void* out, double* stats, cudaStream_t stream) {
+    using S = ImfSmem<BN, KC, STAGES, TS>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(im2col_fwd_kernel<BN, KC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(im2col_fwd_kernel<BN, KC, STAGES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             S::total(IM_PATCH_STAGE));
         if (e != cudaSuccess) return fail("im2col_fwd_kernel smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     const int resident = 2 * num_sms();
     const int grid = p.total_tiles < resident ? p.total_tiles : resident;
-    im2col_fwd_kernel<BN, KC, STAGES><<<grid, IMF_THREADS, S::TOTAL, stream>>>(
-        mb, p, (const unsigned short*)wp, bias, (__nv_bfloat16*)out, stats);
+    im2col_fwd_kernel<BN, KC, STAGES, TS><<<grid, IMF_THREADS, S::total(p.patch_stage), stream>>>(
+        mb, mo, p, (const unsigned short*)wp, bias, (__nv_bfloat16*)out, stats);
     return launched("im2col_fwd_kernel");
 }
 
@@ -358,9 +380,25 @@ int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const v
     const bool fuse_stats = stats != nullptr && (p.n_per_group % p.NT) == 0;
     double* st = fuse_stats ? stats : nullptr;
     const int KC = p.KK > 64 ? 2 : 1;
+    // staged epilogue + TMA store for one 64-channel tile with 16-byte aligned rows and a single kk chunk
+    CUtensorMap mo;
+    memset(&mo, 0, sizeof(mo));
+    const bool staged = g->K <= 64 && KC == 1 && !p.partial;
+    if (staged) {
+        cuuint64_t dims[4] = {(cuuint64_t)g->K, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)g->K * 2, (cuuint64_t)g->K * g->Q * 2, (cuuint64_t)g->K * g->Q * g->P * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.WT, (cuuint32_t)p.HT, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode_fn()(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(im2col out) failed: %d", (int)r);
+    }
     int rc;
-    if (g->K <= 64) rc = KC == 1 ? launch_imf<64, 1, 4>(mb, p, wp, bias, out, st, stream) : launch_imf<64, 2, 2>(mb, p, wp, bias, out, st, stream);
-    else            rc = KC == 1 ? launch_imf<128, 1, 4>(mb, p, wp, bias, out, st, stream) : launch_imf<128, 2, 2>(mb, p, wp, bias, out, st, stream);
+    if (staged)          rc = launch_imf<64, 1, 3, true>(mb, mo, p, wp, bias, out, st, stream);
+    else if (g->K <= 64) rc = KC == 1 ? launch_imf<64, 1, 4, false>(mb, mo, p, wp, bias, out, st, stream)
+                                      : launch_imf<64, 2, 2, false>(mb, mo, p, wp, bias, out, st, stream);
+    else                 rc = KC == 1 ? launch_imf<128, 1, 4, false>(mb, mo, p, wp, bias, out, st, stream)
+                                      : launch_imf<128, 2, 2, false>(mb, mo, p, wp, bias, out, st, stream);
     if (rc) return rc;
     if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * g->P * g->Q, g->K, stats, stream);
     return 0;

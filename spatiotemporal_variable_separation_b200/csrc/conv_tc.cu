@@ -36,33 +36,43 @@ struct TcParams {
     unsigned char ca[TC_MAX_CLASSES], cb[TC_MAX_CLASSES];
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TS>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 2 * 4 /*tile statistics*/;
+    static constexpr int OUT_BYTES = TS ? 2 * TC_BM * 128 : 0;       // two bf16 output tiles staged for TMA stores (BN = 64)
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 2 * 4 /*tile statistics*/;
     static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
+    static_assert(!TS || BN == 64, "the staged epilogue handles one 128-byte row per pixel");
 };
+
+// output tensor maps of the staged epilogue, one per output-parity class: [OC, OW/ost, OH/ost, N] views of the NHWC output
+struct TcOutMaps { CUtensorMap m[TC_MAX_CLASSES]; };
 
 // Persistent: every CTA walks a strided list of (pixel tile, output-channel tile, parity class) work items.
 // The TMA producer and the MMA issuer run ahead across tile boundaries (one smem ring for the whole kernel);
 // two TMEM accumulator stages let tile i+1's MMAs overlap tile i's epilogue.
-template <int BN, int STAGES>
+// TS: the epilogue stages the bf16 tile in shared memory and writes it with one TMA store (coalesced, clipped at the
+// tensor edges by the TMA unit) instead of 16-byte stores from every lane to 32 different lines.
+template <int BN, int STAGES, bool TS>
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_constant__ CUtensorMap map_a,
                                                          const __grid_constant__ CUtensorMap map_b,
+                                                         const __grid_constant__ TcOutMaps omaps,
                                                          const __grid_constant__ TcParams p,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                          double* __restrict__ stats) {
-    using S = TcSmem<BN, STAGES>;
+    using S = TcSmem<BN, STAGES, TS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint8_t* obuf = smem + STAGES * S::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;        // [2]
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* sstat = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);      // [BN][2] per-tile column sums
+    float* sstat = reinterpret_cast<float*>(smem + S::BAR_OFF + 256);      // [BN][2] per-tile column sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.ntaps * p.kchunks;
@@ -168,7 +178,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                 float xs[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
-                if (p.partial || n0 + BN > p.OC) {
+                if (TS) {
+                    stage_row32(obuf + (lt & 1) * (TC_BM * 128), m, c0, xs, p.act);
+                } else if (p.partial || n0 + BN > p.OC) {
                     // tail tile in OC, or rows not 16-byte aligned: predicated scalar stores
                     if (ok) {
 #pragma unroll
@@ -207,9 +219,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            if (stats != nullptr) {
-                // the four epilogue warps have added their 32-row partials: one fp64 atomic per column and tile
+            if (TS) {
+                // staged tile complete -> one TMA store.  The buffer written now was the source of the store issued two
+                // tiles ago; the store of the previous tile (other buffer) is drained here, before anyone refills it
+                fence_proxy_async();
+                if (threadIdx.x == 64) tma_store_wait_read();
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+                if (threadIdx.x == 64) {
+                    tma_store_4d(&omaps.m[cls], obuf + (lt & 1) * (TC_BM * 128), n0, j0, i0, b0);
+                    tma_store_commit();
+                }
+            }
+            if (stats != nullptr) {
+                // the epilogue warps have added their 32-row partials: one fp64 atomic per column and tile
+                if (!TS) asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
                 const int g = b0 / p.n_per_group;            // a tile never straddles BatchNorm groups (checked by the host)
                 const int t = threadIdx.x - 64;              // 0 .. 32*TC_EPI_WARPS-1
                 for (int i = t; i < 2 * BN; i += 32 * TC_EPI_WARPS) {
@@ -220,6 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
             }
         }
+        if (TS && threadIdx.x == 64) tma_store_wait_all();
     }
     __syncthreads();
     if (warp == 1) {
@@ -230,13 +254,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------ host
-template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const float* bias, void* out,
-                     int classes, double* stats, cudaStream_t stream) {
-    using S = TcSmem<BN, STAGES>;
+template <int BN, int STAGES, bool TS>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMaps& om, const TcParams& p, const float* bias,
+                     void* out, int classes, double* stats, cudaStream_t stream) {
+    using S = TcSmem<BN, STAGES, TS>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return fail("tc_conv_kernel smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
@@ -246,8 +270,14 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     q.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * q.n_tiles * classes;
     const int resident = 2 * num_sms();                     // __launch_bounds__(TC_THREADS, 2)
     const int grid = q.total_tiles < resident ? q.total_tiles : resident;
-    tc_conv_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, q, bias, (__nv_bfloat16*)out, stats);
+    tc_conv_kernel<BN, STAGES, TS><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, om, q, bias, (__nv_bfloat16*)out, stats);
     return launched("tc_conv_kernel");
+}
+
+static bool staged_epilogue_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VARSEP_DISABLE_STAGED_EPILOGUE"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
 }
 
 int conv_forward_tc_eligible(const vs_conv_geom* g, int mode) {
@@ -338,8 +368,28 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     // statistics are fused into the epilogue when every 128-pixel tile lies inside one BatchNorm group
     p.n_per_group = g->N / g->groups;
     const bool fuse_stats = stats != nullptr && (p.n_per_group % p.NT) == 0;
-    int rc = BN == 128 ? launch_tc<128, 3>(ma, mb, p, bias, out, classes, fuse_stats ? stats : nullptr, stream)
-                       : launch_tc<64, 4>(ma, mb, p, bias, out, classes, fuse_stats ? stats : nullptr, stream);
+    // staged epilogue + TMA stores for the 64-column tiles (16-byte aligned rows): one [OC, OW/ost, OH/ost, N] view per
+    // output-parity class, starting at that class's first pixel
+    TcOutMaps om;
+    memset(&om, 0, sizeof(om));
+    const bool staged = BN == 64 && !p.partial && !staged_epilogue_disabled();
+    if (staged) {
+        for (int cls = 0; cls < classes; ++cls) {
+            const char* base = reinterpret_cast<const char*>(out) + ((size_t)p.ca[cls] * OW + p.cb[cls]) * OC * 2;
+            cuuint64_t dims[4] = {(cuuint64_t)OC, (cuuint64_t)p.OWc, (cuuint64_t)p.OHc, (cuuint64_t)g->N};
+            cuuint64_t strides[3] = {(cuuint64_t)ost * OC * 2, (cuuint64_t)ost * OW * OC * 2, (cuuint64_t)OH * OW * OC * 2};
+            cuuint32_t box[4] = {64, (cuuint32_t)p.WT, (cuuint32_t)p.HT, (cuuint32_t)p.NT};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = enc(&om.m[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(out) failed: %d", (int)r);
+        }
+    }
+    double* stp = fuse_stats ? stats : nullptr;
+    int rc = BN == 128 ? launch_tc<128, 3, false>(ma, mb, om, p, bias, out, classes, stp, stream)
+             : staged  ? launch_tc<64, 3, true>(ma, mb, om, p, bias, out, classes, stp, stream)
+                       : launch_tc<64, 4, false>(ma, mb, om, p, bias, out, classes, stp, stream);
     if (rc) return rc;
     if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
     return rc;

@@ -115,6 +115,34 @@ __device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t saddr, uint32_t 
            (2ull << 61);
 }
 
+// TMA store of a shared-memory box (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 32 accumulator columns of one pixel row -> bf16 -> four 16-byte chunks of a [rows][128 B] staging tile in the
+// 128-byte-swizzled layout a TMA store box expects (chunk index XOR (row & 7)); col0 is 0 or 32
+__device__ __forceinline__ void stage_row32(uint8_t* tile, int row, int col0, const float* xs, int act) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = v * 8 + e * 2;
+            __nv_bfloat162 b2 = act == VS_ACT_NONE ? __floats2bfloat162_rn(xs[c], xs[c + 1])
+                                                   : __floats2bfloat162_rn(act_fwd(xs[c], act), act_fwd(xs[c + 1], act));
+            pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        const int chunk = (col0 >> 3) + v;
+        *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
