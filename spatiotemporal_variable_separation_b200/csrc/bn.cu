@@ -228,6 +228,20 @@ struct ColPlan {
 
 template <typename T>
 __device__ __forceinline__ uint4 raw16(const T* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// cp.async (LDGSTS) staging for the streaming loops: every thread copies its own 16-byte pieces of the next rows into
+// its own shared-memory slots and reads them back after cp.async.wait_group -- no registers are held by loads in flight
+// and the compiler cannot shrink the number of outstanding requests (it sinks plain loads next to their uses).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Empty asm that "uses" a loaded vector: placed after the load loop of a group it keeps every load of the group above
+// this point (the compiler otherwise sinks loads next to their uses and leaves two 16-byte requests in flight per
+// thread instead of eight).
+__device__ __forceinline__ void keep_loaded(uint4& v) { asm volatile("" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)); }
 
 template <typename T>
 static bool col_plan(long long rows, int C, int G, ColPlan& pl, int blocks_per_sm = 8) {
@@ -274,6 +288,8 @@ __global__ void __launch_bounds__(256) bn_act_fwd_col_kernel(const T* __restrict
         uint4 raw[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) raw[u] = raw16(y + (r + u * step) * C + c);
+#pragma unroll
+        for (int u = 0; u < U; ++u) keep_loaded(raw[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             float v[W];
@@ -328,6 +344,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_col_kernel(const T* __restri
 #pragma unroll
         for (int u = 0; u < U; ++u) { ry[u] = raw16(y + (r + u * step) * C + c); rd[u] = raw16(dout + (r + u * step) * C + c); }
 #pragma unroll
+        for (int u = 0; u < U; ++u) { keep_loaded(ry[u]); keep_loaded(rd[u]); }
+#pragma unroll
         for (int u = 0; u < U; ++u) apply(ry[u], rd[u], r + u * step);
     }
     for (; r < r1; r += step) apply(raw16(y + r * C + c), raw16(dout + r * C + c), r);
@@ -341,7 +359,10 @@ __global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict_
                                                             double* __restrict__ sums) {
     const int act = ACT >= 0 ? ACT : act_rt;
     VS_COL_SETUP
-    __shared__ float red[2][256 * 8];
+    // dynamic shared memory: staging slots [2 buffers][NT tensors][U rows][256 threads] x 16 bytes, reused as the
+    // block-reduction scratch [2][256 * W] floats at the end
+    extern __shared__ uint4 stage[];
+    constexpr int NT = MODE == 0 ? 2 : 1;
     float mu[W], is[W], ga[W], be[W], s1[W], s2[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) {
@@ -367,18 +388,31 @@ __global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict_
             for (int k = 0; k < W; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
         }
     };
-    long long r = r0 + rl;
-    for (; r + (U - 1) * step < r1; r += U * step) {
-        uint4 ry[U], rd[U];
+    // rows of this thread: r0 + rl + i * step; groups of U rows, group g+1 is in flight while group g is consumed
+    const long long nrows = r1 > r0 + rl ? (r1 - r0 - rl + step - 1) / step : 0;
+    const int ngroups = (int)((nrows + U - 1) / U);
+    auto slot = [&](int buf, int tensor, int u) -> uint4* { return stage + ((buf * NT + tensor) * U + u) * 256 + threadIdx.x; };
+    auto issue = [&](int grp) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            ry[u] = raw16(y + (r + u * step) * C + c);
-            rd[u] = MODE == 0 ? raw16(dout + (r + u * step) * C + c) : make_uint4(0, 0, 0, 0);
+            const long long i = (long long)grp * U + u;
+            if (i < nrows) {
+                const long long rr = r0 + rl + i * step;
+                cp_async16(slot(grp & 1, 0, u), y + rr * C + c);
+                if (MODE == 0) cp_async16(slot(grp & 1, 1, u), dout + rr * C + c);
+            }
         }
+        cp_async_commit();
+    };
+    if (ngroups > 0) issue(0);
+    for (int grp = 0; grp < ngroups; ++grp) {
+        if (grp + 1 < ngroups) { issue(grp + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
 #pragma unroll
-        for (int u = 0; u < U; ++u) accumulate(ry[u], rd[u]);
+        for (int u = 0; u < U; ++u)
+            if ((long long)grp * U + u < nrows) accumulate(*slot(grp & 1, 0, u), MODE == 0 ? *slot(grp & 1, 1, u) : make_uint4(0, 0, 0, 0));
     }
-    for (; r < r1; r += step) accumulate(raw16(y + r * C + c), MODE == 0 ? raw16(dout + r * C + c) : make_uint4(0, 0, 0, 0));
+    __syncthreads();        // staging memory becomes the reduction scratch
+    float (*red)[256 * W] = reinterpret_cast<float (*)[256 * W]>(stage);
     // reduce the row lanes of the block (threads with equal threadIdx.x % tpr), then fp64 atomics
 #pragma unroll
     for (int k = 0; k < W; ++k) { red[0][threadIdx.x * W + k] = s1[k]; red[1][threadIdx.x * W + k] = s2[k]; }
@@ -397,14 +431,25 @@ __global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict_
     }
 }
 
+// staging (2 buffers x 2 tensors x U rows x 256 threads x 16 B) is also large enough for the reduction scratch
+constexpr int REDUCE_SMEM = 2 * 2 * COL_ROWS_IN_FLIGHT * 256 * 16;
+static_assert(REDUCE_SMEM >= 2 * 256 * 8 * 4, "reduction scratch");
+template <typename K>
+static int reduce_smem_attr(K kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, REDUCE_SMEM);
+    if (e != cudaSuccess) return fail("bn_reduce_col_kernel smem attribute: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // per-(group, channel) sum / sum of squares of a stored [rows, C] tensor (second-pass BatchNorm statistics of
 // the tensor-core and thin convolution paths)
 int column_stats(const void* y, int dtype, long long rows, int C, int G, double* stats, cudaStream_t stream) {
     VS_DISPATCH_DTYPE(dtype, T, {
         ColPlan pl;
         if (!col_plan<T>(rows, C, G, pl, 8)) return -1;
-        bn_reduce_col_kernel<T, 1, 0><<<(unsigned)(G * pl.chunks), 256, 0, stream>>>(nullptr, (const T*)y, C, pl, nullptr, nullptr,
-                                                                                   nullptr, nullptr, 0, stats);
+        if (int rc = reduce_smem_attr(bn_reduce_col_kernel<T, 1, 0>)) return rc;
+        bn_reduce_col_kernel<T, 1, 0><<<(unsigned)(G * pl.chunks), 256, REDUCE_SMEM, stream>>>(nullptr, (const T*)y, C, pl, nullptr,
+                                                                                             nullptr, nullptr, nullptr, 0, stats);
     });
     return launched("bn_reduce_col_kernel");
 }
@@ -470,7 +515,8 @@ extern "C" int vs_bn_act_backward_reduce(const void* dout, const void* y, int32_
         ColPlan pl;
         if (col_plan<T>(rows, C, G, pl, 8)) {
             VS_DISPATCH_ACT(act, A, {
-                bn_reduce_col_kernel<T, 0, A><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, C, pl, mean, invstd, gamma, beta, act, sums);
+                if (int rc = reduce_smem_attr(bn_reduce_col_kernel<T, 0, A>)) return rc;
+                bn_reduce_col_kernel<T, 0, A><<<(unsigned)(G * pl.chunks), 256, REDUCE_SMEM, as_stream(stream)>>>((const T*)dout, (const T*)y, C, pl, mean, invstd, gamma, beta, act, sums);
             });
             return launched("bn_reduce_col_kernel");
         }

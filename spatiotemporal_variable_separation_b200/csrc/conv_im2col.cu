@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
     uint8_t* pbuf = smem + S::PATCH_OFF;             // [IM_PST][p.patch_stage]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total = p.total_tiles;
+    // one contiguous range of tiles per CTA (few BatchNorm groups per CTA: statistics are flushed once per group)
+    const int t_begin = (int)((long long)blockIdx.x * p.total_tiles / gridDim.x);
+    const int t_end = (int)((long long)(blockIdx.x + 1) * p.total_tiles / gridDim.x);
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_big);
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
         // ===== TMA producer: the input patch of every tile, IM_PST tiles ahead =====
         if (lane == 0) {
             int lt = 0;
-            for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+            for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
                 VS_IM_DECODE(idx)
                 const int ps = lt % IM_PST;
                 mbar_wait(&pempty[ps], ((lt / IM_PST) & 1) ^ 1);
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
             constexpr uint32_t idesc = idesc_bf16_f32(BN);
             const int ksteps = (p.KK + 15) >> 4;
             int lt = 0;
-            for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+            for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
                 const int acc = lt & 1, s = lt % STAGES;
                 mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
                 mbar_wait(&full[s], (lt / STAGES) & 1);
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
         const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1);
         const int base = h * p.stride * p.PWCp + w * p.stride * p.C;
         int lt = 0;
-        for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+        for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
             const int s = lt % STAGES, ps = lt % IM_PST;
             const int j0 = (idx % p.tiles_w) * p.WT;
             // the box starts at the 16-byte boundary below the patch's first element
@@ -207,7 +209,9 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
         const int m = q * 32 + lane;
         const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
         int lt = 0;
-        for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+        int stat_g = -1;
+        double stat_acc[2 * BN / 128] = {};
+        for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
             VS_IM_DECODE(idx)
             const int acc = lt & 1;
             const int pp = i0 + h, qq = j0 + w, nn = b0 + n;
@@ -272,15 +276,32 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
                 }
             }
             if (stats != nullptr) {
+                // running fp64 sums per thread (entries t and t + 128), flushed when the BatchNorm group changes
                 if (!TS) asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int g = b0 / p.n_per_group;
                 const int t = threadIdx.x - 192;
-                for (int i = t; i < 2 * BN; i += 128) {
-                    const int col = i >> 1;
-                    if (col < p.K) atomicAdd(&stats[((long long)g * p.K + col) * 2 + (i & 1)], (double)sstat[i]);
-                    sstat[i] = 0.f;
+                if (g != stat_g) {
+                    if (stat_g >= 0) {
+#pragma unroll
+                        for (int e = 0; e < 2 * BN / 128; ++e) {
+                            const int i = t + e * 128, col = i >> 1;
+                            if (col < p.K) atomicAdd(&stats[((long long)stat_g * p.K + col) * 2 + (i & 1)], stat_acc[e]);
+                            stat_acc[e] = 0.0;
+                        }
+                    }
+                    stat_g = g;
                 }
+#pragma unroll
+                for (int e = 0; e < 2 * BN / 128; ++e) { stat_acc[e] += (double)sstat[t + e * 128]; sstat[t + e * 128] = 0.f; }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+        if (stats != nullptr && stat_g >= 0) {
+            const int t = threadIdx.x - 192;
+#pragma unroll
+            for (int e = 0; e < 2 * BN / 128; ++e) {
+                const int i = t + e * 128, col = i >> 1;
+                if (col < p.K) atomicAdd(&stats[((long long)stat_g * p.K + col) * 2 + (i & 1)], stat_acc[e]);
             }
         }
         if (TS && threadIdx.x == 192) tma_store_wait_all();

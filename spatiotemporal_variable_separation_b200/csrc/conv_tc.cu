@@ -20,7 +20,7 @@
 
 namespace vs {
 
-constexpr int TC_MAX_TAPS = 25, TC_MAX_CLASSES = 4;
+constexpr int TC_MAX_TAPS = 25, TC_MAX_CLASSES = 16, TC_TABLE = 32, TC_MAX_OUT_MAPS = 4;   // classes * taps <= TC_TABLE
 constexpr int TC_EPI_WARPS = 8, TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 
 struct TcParams {
@@ -31,8 +31,8 @@ struct TcParams {
     int IC, kchunks, ntaps;
     int in_sh, in_sw;         // class-grid -> input coordinate multiplier
     int act, has_bias, partial, n_per_group;
-    signed char dh[TC_MAX_CLASSES][TC_MAX_TAPS], dw[TC_MAX_CLASSES][TC_MAX_TAPS];
-    unsigned char wtap[TC_MAX_CLASSES][TC_MAX_TAPS];
+    signed char dh[TC_TABLE], dw[TC_TABLE];          // [class * ntaps + tap]: input offset of the tap on the class grid
+    unsigned char wtap[TC_TABLE];                    // ... and its index r*S + s in the packed weights
     unsigned char ca[TC_MAX_CLASSES], cb[TC_MAX_CLASSES];
 };
 
@@ -48,7 +48,7 @@ struct TcSmem {
 };
 
 // output tensor maps of the staged epilogue, one per output-parity class: [OC, OW/ost, OH/ost, N] views of the NHWC output
-struct TcOutMaps { CUtensorMap m[TC_MAX_CLASSES]; };
+struct TcOutMaps { CUtensorMap m[TC_MAX_OUT_MAPS]; };
 
 // Persistent: every CTA walks a strided list of (pixel tile, output-channel tile, parity class) work items.
 // The TMA producer and the MMA issuer run ahead across tile boundaries (one smem ring for the whole kernel);
@@ -76,7 +76,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.ntaps * p.kchunks;
-    const int total = p.total_tiles;
+    // every CTA walks one contiguous range of work items: the parity classes / channel tiles of a pixel tile run back to
+    // back on the same SM (input tile re-read from L2), and a CTA sees few BatchNorm groups (statistics are flushed
+    // once per group and CTA, not once per tile)
+    const int t_begin = (int)((long long)blockIdx.x * p.total_tiles / gridDim.x);
+    const int t_end = (int)((long long)(blockIdx.x + 1) * p.total_tiles / gridDim.x);
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_a);
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
         // ===== TMA producer =====
         if (lane == 0) {
             int it = 0;
-            for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+            for (int idx = t_begin; idx < t_end; ++idx) {
                 VS_TC_DECODE(idx)
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -118,8 +122,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                     uint8_t* a_dst = smem + s * S::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + S::A_BYTES;
                     mbar_expect_tx(&full[s], S::STAGE_BYTES);
-                    tma_load_4d(a_dst, &map_a, &full[s], kc * TC_BK, j0 * p.in_sw + p.dw[cls][tap], i0 * p.in_sh + p.dh[cls][tap], b0);
-                    tma_load_2d(b_dst, &map_b, &full[s], p.wtap[cls][tap] * p.IC + kc * TC_BK, n0);
+                    tma_load_4d(a_dst, &map_a, &full[s], kc * TC_BK, j0 * p.in_sw + p.dw[cls * p.ntaps + tap], i0 * p.in_sh + p.dh[cls * p.ntaps + tap], b0);
+                    tma_load_2d(b_dst, &map_b, &full[s], p.wtap[cls * p.ntaps + tap] * p.IC + kc * TC_BK, n0);
                 }
             }
         }
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_bf16_f32(BN);
             int it = 0, lt = 0;
-            for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+            for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
                 const int acc = lt & 1;
                 mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 tc_fence_after();
@@ -159,7 +163,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
         const int m = q * 32 + lane;             // tile-local pixel (TMEM lane)
         const int w = m % p.WT, h = (m / p.WT) % p.HT, n = m / (p.WT * p.HT);
         int lt = 0;
-        for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++lt) {
+        int stat_key = -1;
+        double stat_acc = 0.0;
+        for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
             VS_TC_DECODE(idx)
             const int acc = lt & 1;
             const int i = i0 + h, j = j0 + w, nn = b0 + n;
@@ -231,17 +237,29 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                 }
             }
             if (stats != nullptr) {
-                // the epilogue warps have added their 32-row partials: one fp64 atomic per column and tile
+                // the epilogue warps have added their 32-row partials of this tile; thread i keeps the running fp64 sum of
+                // entry i (column n0 + i/2, sum or sum of squares) and flushes it when the (group, channel tile) changes
                 if (!TS) asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-                const int g = b0 / p.n_per_group;            // a tile never straddles BatchNorm groups (checked by the host)
                 const int t = threadIdx.x - 64;              // 0 .. 32*TC_EPI_WARPS-1
-                for (int i = t; i < 2 * BN; i += 32 * TC_EPI_WARPS) {
-                    const int col = n0 + (i >> 1);
-                    if (col < p.OC) atomicAdd(&stats[((long long)g * p.OC + col) * 2 + (i & 1)], (double)sstat[i]);
-                    sstat[i] = 0.f;
+                if (t < 2 * BN) {
+                    const int key = (b0 / p.n_per_group) * p.n_tiles + n0 / BN;      // a tile never straddles groups (host check)
+                    if (key != stat_key) {
+                        if (stat_key >= 0) {
+                            const int col = (stat_key % p.n_tiles) * BN + (t >> 1);
+                            if (col < p.OC) atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (t & 1)], stat_acc);
+                        }
+                        stat_key = key; stat_acc = 0.0;
+                    }
+                    stat_acc += (double)sstat[t];
+                    sstat[t] = 0.f;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
             }
+        }
+        if (stats != nullptr && stat_key >= 0) {
+            const int t = threadIdx.x - 64;
+            const int col = (stat_key % p.n_tiles) * BN + (t >> 1);
+            if (t < 2 * BN && col < p.OC) atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (t & 1)], stat_acc);
         }
         if (TS && threadIdx.x == 64) tma_store_wait_all();
     }
@@ -269,7 +287,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMa
     q.n_tiles = (int)cdiv(p.OC, BN);
     q.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * q.n_tiles * classes;
     const int resident = 2 * num_sms();                     // __launch_bounds__(TC_THREADS, 2)
-    const int grid = q.total_tiles < resident ? q.total_tiles : resident;
+    const int grid = q.total_tiles < resident ? q.total_tiles : resident;      // every CTA gets at least one work item
     tc_conv_kernel<BN, STAGES, TS><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, om, q, bias, (__nv_bfloat16*)out, stats);
     return launched("tc_conv_kernel");
 }
@@ -301,7 +319,11 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     const int st = g->stride;
     if (IC % 8 != 0 || IC < 32 || st > 2 || g->R * g->S > TC_MAX_TAPS) return -1;
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wp)) & 15) return -1;
-    const int ost = tr ? st : 1;
+    // A transposed convolution of a 1x1 input (the decoder's first up-convolution) has exactly one tap per output pixel:
+    // every output position is its own "parity class" (class stride R), so no structurally-zero tap is multiplied.
+    const bool one_px = tr && g->P == 1 && g->Q == 1 && g->pad == 0 && st == 1 && g->R == g->S && g->R * g->S <= TC_MAX_CLASSES;
+    const int cst = one_px ? g->R : st;          // stride between the pixels of one class
+    const int ost = tr ? cst : 1;
     if (OH % ost != 0 || OW % ost != 0) return -1;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return -1;
@@ -320,24 +342,32 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     p.in_sh = p.in_sw = tr ? 1 : st;
     p.act = g->act; p.has_bias = bias != nullptr;
     int classes = ost * ost, ntaps = -1;
+    if (classes > TC_MAX_CLASSES) return -1;
     for (int cls = 0; cls < classes; ++cls) {
         const int a = cls / ost, b = cls % ost;
         p.ca[cls] = (unsigned char)a; p.cb[cls] = (unsigned char)b;
-        int n = 0;
-        if (!tr) {
-            for (int r = 0; r < g->R; ++r)
-                for (int s = 0; s < g->S; ++s) { p.dh[cls][n] = (signed char)(r - g->pad); p.dw[cls][n] = (signed char)(s - g->pad); p.wtap[cls][n] = (unsigned char)(r * g->S + s); ++n; }
-        } else {
-            for (int r = (a + g->pad) % st; r < g->R; r += st)
-                for (int s = (b + g->pad) % st; s < g->S; s += st) {
-                    p.dh[cls][n] = (signed char)((a + g->pad - r) / st); p.dw[cls][n] = (signed char)((b + g->pad - s) / st);
-                    p.wtap[cls][n] = (unsigned char)(r * g->S + s); ++n;
-                }
+        // first pass counts the taps of this class, second pass fills the flat tables at [cls * ntaps + tap]
+        for (int pass = 0; pass < 2; ++pass) {
+            int n = 0;
+            if (!tr) {
+                for (int r = 0; r < g->R; ++r)
+                    for (int s = 0; s < g->S; ++s, ++n)
+                        if (pass) { p.dh[cls * ntaps + n] = (signed char)(r - g->pad); p.dw[cls * ntaps + n] = (signed char)(s - g->pad); p.wtap[cls * ntaps + n] = (unsigned char)(r * g->S + s); }
+            } else {
+                for (int r = (a + g->pad) % cst; r < g->R; r += cst)
+                    for (int s = (b + g->pad) % cst; s < g->S; s += cst, ++n)
+                        if (pass) {
+                            p.dh[cls * ntaps + n] = (signed char)((a + g->pad - r) / cst); p.dw[cls * ntaps + n] = (signed char)((b + g->pad - s) / cst);
+                            p.wtap[cls * ntaps + n] = (unsigned char)(r * g->S + s);
+                        }
+            }
+            if (!pass) {
+                if (ntaps >= 0 && n != ntaps) return -1;     // classes with unequal tap counts (odd filters, stride 2)
+                ntaps = n;
+                if (ntaps <= 0 || classes * ntaps > TC_TABLE) return -1;
+            }
         }
-        if (ntaps >= 0 && n != ntaps) return -1;     // classes with unequal tap counts (odd filters, stride 2)
-        ntaps = n;
     }
-    if (ntaps <= 0) return -1;
     p.ntaps = ntaps;
     if (p.WT * p.in_sw > 256 || p.HT * p.in_sh > 256) return -1;
 
@@ -372,7 +402,7 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     // output-parity class, starting at that class's first pixel
     TcOutMaps om;
     memset(&om, 0, sizeof(om));
-    const bool staged = BN == 64 && !p.partial && !staged_epilogue_disabled();
+    const bool staged = BN == 64 && !p.partial && classes <= TC_MAX_OUT_MAPS && !staged_epilogue_disabled();
     if (staged) {
         for (int cls = 0; cls < classes; ++cls) {
             const char* base = reinterpret_cast<const char*>(out) + ((size_t)p.ca[cls] * OW + p.cb[cls]) * OC * 2;
