@@ -238,6 +238,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// staging (2 buffers x 2 tensors x U rows x 256 threads x 16 B) is also large enough for the reduction scratch
+constexpr int REDUCE_SMEM = 2 * 2 * COL_ROWS_IN_FLIGHT * 256 * 16;
+static_assert(REDUCE_SMEM >= 2 * 256 * 8 * 4, "reduction scratch");
+template <typename K>
+static int reduce_smem_attr(K kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, REDUCE_SMEM);
+    if (e != cudaSuccess) return fail("bn_reduce_col_kernel smem attribute: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // Empty asm that "uses" a loaded vector: placed after the load loop of a group it keeps every load of the group above
 // this point (the compiler otherwise sinks loads next to their uses and leaves two 16-byte requests in flight per
 // thread instead of eight).
@@ -338,17 +348,32 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_col_kernel(const T* __restri
         }
         Vec<T>::store(dy + rr * C + c, d);
     };
-    long long r = r0 + rl;
-    for (; r + (U - 1) * step < r1; r += U * step) {
-        uint4 ry[U], rd[U];
+    // cp.async staging as in bn_reduce_col_kernel: [2 buffers][2 tensors][U rows][256 threads] x 16 bytes
+    extern __shared__ uint4 stage[];
+    const long long nrows = r1 > r0 + rl ? (r1 - r0 - rl + step - 1) / step : 0;
+    const int ngroups = (int)((nrows + U - 1) / U);
+    auto slot = [&](int buf, int tensor, int u) -> uint4* { return stage + ((buf * 2 + tensor) * U + u) * 256 + threadIdx.x; };
+    auto issue = [&](int grp) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) { ry[u] = raw16(y + (r + u * step) * C + c); rd[u] = raw16(dout + (r + u * step) * C + c); }
+        for (int u = 0; u < U; ++u) {
+            const long long i = (long long)grp * U + u;
+            if (i < nrows) {
+                const long long rr = r0 + rl + i * step;
+                cp_async16(slot(grp & 1, 0, u), y + rr * C + c);
+                cp_async16(slot(grp & 1, 1, u), dout + rr * C + c);
+            }
+        }
+        cp_async_commit();
+    };
+    if (ngroups > 0) issue(0);
+    for (int grp = 0; grp < ngroups; ++grp) {
+        if (grp + 1 < ngroups) { issue(grp + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
 #pragma unroll
-        for (int u = 0; u < U; ++u) { keep_loaded(ry[u]); keep_loaded(rd[u]); }
-#pragma unroll
-        for (int u = 0; u < U; ++u) apply(ry[u], rd[u], r + u * step);
+        for (int u = 0; u < U; ++u) {
+            const long long i = (long long)grp * U + u;
+            if (i < nrows) apply(*slot(grp & 1, 0, u), *slot(grp & 1, 1, u), r0 + rl + i * step);
+        }
     }
-    for (; r < r1; r += step) apply(raw16(y + r * C + c), raw16(dout + r * C + c), r);
 }
 
 // MODE 0: BatchNorm backward sums {sum dz, sum dz*xhat};  MODE 1: forward statistics {sum y, sum y^2}
@@ -429,16 +454,6 @@ __global__ void __launch_bounds__(256) bn_reduce_col_kernel(const T* __restrict_
             atomicAdd(&sums[((long long)g * C + c + k) * 2 + 1], t2);
         }
     }
-}
-
-// staging (2 buffers x 2 tensors x U rows x 256 threads x 16 B) is also large enough for the reduction scratch
-constexpr int REDUCE_SMEM = 2 * 2 * COL_ROWS_IN_FLIGHT * 256 * 16;
-static_assert(REDUCE_SMEM >= 2 * 256 * 8 * 4, "reduction scratch");
-template <typename K>
-static int reduce_smem_attr(K kernel) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, REDUCE_SMEM);
-    if (e != cudaSuccess) return fail("bn_reduce_col_kernel smem attribute: %s", cudaGetErrorString(e));
-    return 0;
 }
 
 // per-(group, channel) sum / sum of squares of a stored [rows, C] tensor (second-pass BatchNorm statistics of
@@ -544,7 +559,8 @@ extern "C" int vs_bn_act_backward_apply(const void* dout, const void* y, void* d
         ColPlan pl;
         if (col_plan<T>(rows, C, G, pl)) {
             VS_DISPATCH_ACT(act, A, {
-                bn_bwd_apply_col_kernel<T, A><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, C, pl, mean, invstd, gamma, beta, act, sums, train);
+                if (int rc = reduce_smem_attr(bn_bwd_apply_col_kernel<T, A>)) return rc;
+                bn_bwd_apply_col_kernel<T, A><<<(unsigned)(G * pl.chunks), 256, REDUCE_SMEM, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, C, pl, mean, invstd, gamma, beta, act, sums, train);
             });
             done = true;
         }

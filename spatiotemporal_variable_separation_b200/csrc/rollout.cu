@@ -10,6 +10,7 @@
 // gradients; the weight gradients are then three (T-1)*B-row GEMMs (one launch each, vs_conv_wgrad) instead of
 // 3*(T-1) small ones.  All arithmetic is fp32 (latent dynamics are precision-sensitive and tiny: 0.2 % of FLOPs).
 #include "common.cuh"
+#include "tc_ptx.cuh"      // warp_transpose_sum32
 
 namespace vs {
 
@@ -185,6 +186,224 @@ static int fill_weights(RolloutWeights& rw, const float* const* w_host, int nb) 
 
 }  // namespace vs
 
+// =================================================================================================
+// Weight-resident cluster variant (one block of 8 CTAs per 8 batch rows).
+//
+// The per-row kernels above stream every block's weights (h*h*4 bytes, ~1 MB) from L2 into each SM once per time step,
+// which bounds a step at the per-SM L2 ingest rate.  Here the hidden units are split over the 8 CTAs of a thread-block
+// cluster: CTA c keeps ITS rows of W1 and W2 and ITS columns of W3 in shared memory for the whole rollout (138 KB for
+// h = 512, d = 20) and the cluster exchanges activations through distributed shared memory:
+//   layer A (d -> h, slice of h per CTA)   -> all-gather of the slice into every CTA's copy of the h-vector
+//   layer B (h -> h, slice of h per CTA)   -> stays local
+//   layer C (h -> d, K-split over the slice) -> partial sums to every CTA, summed in rank order (deterministic)
+// with two cluster barriers per block and step.  Forward and adjoint recurrences have the same shape (the backward
+// takes the transposed weights), so one kernel template serves both.
+// =================================================================================================
+namespace vs {
+
+constexpr int RC_CS = 8;          // CTAs per cluster
+constexpr int RC_ROWS = 8;        // batch rows per cluster
+constexpr int RC_THREADS = 512;
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (a location in this CTA's shared memory) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void* p, uint32_t rank) {
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ void dsmem_store(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+struct RolloutClusterArgs {
+    float* codes;            // fwd: codes [T][B][d];   bwd: dcodes
+    const float* hidden;     // bwd: saved post-ReLU hiddens
+    float* hidden_out;       // fwd: hidden;            bwd: dhidden
+    float* xin;              // fwd only (may be null)
+    float* res;              // fwd: res (may be null); bwd: dres
+    int T, B, d, h, nb;
+};
+
+// shared memory (floats): per block j: WA[hs][d+1] | WB[hs][h] | WC[d][hs] | bA[hs] | bB[hs] | bC[d]
+//                         then x[RC_ROWS][d] | full[RC_ROWS][h] | outB[RC_ROWS][hs] | part[RC_CS][RC_ROWS][d]
+template <bool BWD>
+__global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const RolloutClusterArgs a, const RolloutWeights w) {
+    extern __shared__ float sm[];
+    const int T = a.T, B = a.B, d = a.d, h = a.h, nb = a.nb;
+    const int hs = h / RC_CS;
+    const int rank = (int)cluster_rank();
+    const int cluster_id = blockIdx.x / RC_CS;
+    const int row0 = cluster_id * RC_ROWS;
+    const int nrow = min(RC_ROWS, B - row0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wstride = (hs * (d + 1) + hs * h + d * hs + 2 * hs + d + 3) & ~3;      // multiple of 4 floats (float4 reads)
+    float* x = sm + (size_t)nb * wstride;
+    float* full = x + RC_ROWS * d;
+    float* outB = full + RC_ROWS * h;
+    float* part = outB + RC_ROWS * hs;
+#define hslot(j, which, t) ((((long long)(j) * 2 + (which)) * (T - 1)) + ((t) - 1))
+
+    // ---- resident weights.  Layer A = first layer applied (fwd: W1 [h][d]; bwd: W3^T [h][d]), B = middle, C = last
+    for (int j = 0; j < nb; ++j) {
+        float* WA = sm + (size_t)j * wstride; float* WB = WA + hs * (d + 1); float* WC = WB + hs * h;
+        float* bA = WC + d * hs; float* bB = bA + hs; float* bC = bB + hs;
+        const float* gA = BWD ? w.w3[j] : w.w1[j];
+        const float* gB = w.w2[j];
+        const float* gC = BWD ? w.w1[j] : w.w3[j];
+        for (int i = tid; i < hs * d; i += RC_THREADS) { const int o = i / d, k = i - o * d; WA[o * (d + 1) + k] = gA[(long long)(rank * hs + o) * d + k]; }
+        for (int i = tid; i < hs * h; i += RC_THREADS) WB[i] = gB[(long long)rank * hs * h + i];
+        for (int i = tid; i < d * hs; i += RC_THREADS) { const int n = i / hs, k = i - n * hs; WC[i] = gC[(long long)n * h + rank * hs + k]; }
+        for (int i = tid; i < hs; i += RC_THREADS) { bA[i] = BWD ? 0.f : w.b1[j][rank * hs + i]; bB[i] = BWD ? 0.f : w.b2[j][rank * hs + i]; }
+        for (int i = tid; i < d; i += RC_THREADS) bC[i] = BWD ? 0.f : w.b3[j][i];
+    }
+    // ---- initial state (every CTA of the cluster keeps a copy)
+    for (int i = tid; i < RC_ROWS * d; i += RC_THREADS) {
+        const int r = i / d, k = i - r * d;
+        x[i] = r < nrow ? a.codes[((long long)(BWD ? T - 1 : 0) * B + row0 + r) * d + k] : 0.f;
+    }
+    cluster_sync_all();          // also: every CTA of the cluster has started (DSMEM is valid from here on)
+
+    for (int step = 1; step < T; ++step) {
+        const int t = BWD ? T - step : step;
+        for (int jj = 0; jj < nb; ++jj) {
+            const int j = BWD ? nb - 1 - jj : jj;
+            const long long slot = (long long)j * (T - 1) + (t - 1);
+            float* WA = sm + (size_t)j * wstride; float* WB = WA + hs * (d + 1); float* WC = WB + hs * h;
+            float* bA = WC + d * hs; float* bB = bA + hs; float* bC = bB + hs;
+            if (rank == 0) {
+                // fwd: block input (for the W1 gradient);  bwd: gradient of the block's residual output
+                float* dst = BWD ? a.res : a.xin;
+                if (dst) for (int i = tid; i < nrow * d; i += RC_THREADS) dst[(slot * B + row0) * d + i] = x[i];
+            }
+            // ---- layer A: this CTA's hs hidden units for all rows, scattered into every CTA's `full`
+            for (int pI = tid; pI < hs * RC_ROWS; pI += RC_THREADS) {
+                const int o = pI % hs, r = pI / hs;
+                float acc = bA[o];
+                const float* wr = WA + o * (d + 1);
+                const float* xr = x + r * d;
+                for (int k = 0; k < d; ++k) acc = fmaf(wr[k], xr[k], acc);
+                const long long gi = (hslot(j, BWD ? 1 : 0, t) * B + row0 + r) * h + rank * hs + o;
+                if (BWD) {
+                    acc = (r < nrow && a.hidden[gi] > 0.f) ? acc : 0.f;
+                } else {
+                    acc = fmaxf(acc, 0.f);
+                }
+                if (r < nrow && a.hidden_out) a.hidden_out[gi] = acc;
+                float* loc = full + r * h + rank * hs + o;
+#pragma unroll
+                for (int c = 0; c < RC_CS; ++c) dsmem_store(dsmem_addr(loc, (uint32_t)c), acc);
+            }
+            cluster_sync_all();
+            // ---- layer B: warp = tile of 4 hidden units, lanes split k, 32 accumulators (4 units x 8 rows) per lane
+            for (int ot = warp; ot < hs / 4; ot += RC_THREADS / 32) {
+                float acc[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                for (int k = lane * 4; k < h; k += 128) {
+                    float4 wv[4];
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) wv[o] = *reinterpret_cast<const float4*>(WB + (ot * 4 + o) * h + k);
+#pragma unroll
+                    for (int r = 0; r < RC_ROWS; ++r) {
+                        const float4 xv = *reinterpret_cast<const float4*>(full + r * h + k);
+#pragma unroll
+                        for (int o = 0; o < 4; ++o)
+                            acc[o * 8 + r] += wv[o].x * xv.x + wv[o].y * xv.y + wv[o].z * xv.z + wv[o].w * xv.w;
+                    }
+                }
+                const float tot = warp_transpose_sum32(acc, lane);       // lane i: unit ot*4 + i/8, row i%8
+                const int o = ot * 4 + (lane >> 3), r = lane & 7;
+                float v = tot + bB[o];
+                const long long gi = (hslot(j, BWD ? 0 : 1, t) * B + row0 + r) * h + rank * hs + o;
+                if (BWD) {
+                    v = (r < nrow && a.hidden[gi] > 0.f) ? v : 0.f;
+                } else {
+                    v = fmaxf(v, 0.f);
+                }
+                if (r < nrow && a.hidden_out) a.hidden_out[gi] = v;
+                outB[r * hs + o] = v;
+            }
+            __syncthreads();
+            // ---- layer C: partial sums over this CTA's slice of the hidden units, sent to every CTA
+            for (int pI = tid; pI < d * RC_ROWS; pI += RC_THREADS) {
+                const int n = pI % d, r = pI / d;
+                float acc = 0.f;
+                const float* wr = WC + n * hs;
+                const float* vr = outB + r * hs;
+                for (int k = 0; k < hs; ++k) acc = fmaf(wr[k], vr[k], acc);
+                float* loc = part + (rank * RC_ROWS + r) * d + n;
+#pragma unroll
+                for (int c = 0; c < RC_CS; ++c) dsmem_store(dsmem_addr(loc, (uint32_t)c), acc);
+            }
+            cluster_sync_all();
+            // ---- residual update, identical in every CTA (fixed summation order over the ranks)
+            for (int pI = tid; pI < d * RC_ROWS; pI += RC_THREADS) {
+                const int n = pI % d, r = pI / d;
+                float rr = bC[n];
+#pragma unroll
+                for (int c = 0; c < RC_CS; ++c) rr += part[(c * RC_ROWS + r) * d + n];
+                if (!BWD && rank == 0 && r < nrow && a.res) a.res[(slot * B + row0 + r) * d + n] = rr;
+                x[r * d + n] += rr;
+            }
+            __syncthreads();
+        }
+        if (BWD) {
+            // the decoder's gradient w.r.t. codes[t-1] joins the chain
+            for (int i = tid; i < nrow * d; i += RC_THREADS) {
+                const long long o = ((long long)(t - 1) * B + row0) * d + i;
+                x[i] += a.codes[o];
+            }
+            __syncthreads();
+            if (t == 1 && rank == 0) for (int i = tid; i < nrow * d; i += RC_THREADS) a.codes[((long long)row0) * d + i] = x[i];
+        } else if (rank == 0) {
+            for (int i = tid; i < nrow * d; i += RC_THREADS) a.codes[((long long)t * B + row0) * d + i] = x[i];
+        }
+    }
+    cluster_sync_all();          // no CTA exits while a peer may still write into its shared memory
+#undef hslot
+}
+
+static size_t rollout_cluster_smem(int d, int h, int nb) {
+    const int hs = h / RC_CS;
+    const size_t wstride = ((size_t)hs * (d + 1) + (size_t)hs * h + (size_t)d * hs + 2 * hs + d + 3) & ~(size_t)3;
+    return (nb * wstride + (size_t)RC_ROWS * d + (size_t)RC_ROWS * h + (size_t)RC_ROWS * hs + (size_t)RC_CS * RC_ROWS * d) * sizeof(float);
+}
+
+static bool rollout_cluster_eligible(int d, int h, int nb) {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("VARSEP_DISABLE_ROLLOUT_CLUSTER"); off = (e && e[0] == '1') ? 1 : 0; }
+    if (off) return false;
+    if (h % (RC_CS * 4) != 0 || h < RC_CS * 4 || d < 1 || d > 256) return false;
+    return rollout_cluster_smem(d, h, nb) <= 220 * 1024;
+}
+
+template <bool BWD>
+static int launch_rollout_cluster(const RolloutClusterArgs& a, const RolloutWeights& rw, cudaStream_t stream) {
+    const size_t smem = rollout_cluster_smem(a.d, a.h, a.nb);
+    cudaError_t e = cudaFuncSetAttribute(rollout_cluster_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail("rollout_cluster_kernel smem attribute: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(cdiv(a.B, RC_ROWS) * RC_CS));
+    cfg.blockDim = dim3(RC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = RC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, rollout_cluster_kernel<BWD>, a, rw);
+    if (e != cudaSuccess) return fail("rollout_cluster_kernel launch: %s", cudaGetErrorString(e));
+    return launched("rollout_cluster_kernel");
+}
+
+}  // namespace vs
+
 using namespace vs;
 
 constexpr int RB = 2;
@@ -195,6 +414,10 @@ extern "C" int vs_latent_rollout_forward(float* codes, const float* const* w_hos
     if (T == 1) return 0;
     RolloutWeights rw;
     if (int rc = fill_weights(rw, w_host, n_blocks)) return rc;
+    if (rollout_cluster_eligible(d, h, n_blocks)) {
+        RolloutClusterArgs a = {codes, nullptr, hidden, xin, res, T, B, d, h, n_blocks};
+        return launch_rollout_cluster<false>(a, rw, as_stream(stream));
+    }
     const int smem = (2 * RB * d + 2 * RB * h) * (int)sizeof(float);
     VS_REQUIRE(smem <= 200 * 1024 && (h % 4) == 0, "latent rollout: hidden size %d not supported", h);
     if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_fwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -209,6 +432,10 @@ extern "C" int vs_latent_rollout_backward(float* dcodes, const float* const* w_h
     if (T == 1) return 0;
     RolloutWeights rw;
     if (int rc = fill_weights(rw, w_host, n_blocks)) return rc;
+    if (rollout_cluster_eligible(d, h, n_blocks)) {
+        RolloutClusterArgs a = {dcodes, hidden, dhidden, nullptr, dres, T, B, d, h, n_blocks};
+        return launch_rollout_cluster<true>(a, rw, as_stream(stream));
+    }
     const int smem = (2 * RB * d + 2 * RB * h) * (int)sizeof(float);
     VS_REQUIRE(smem <= 200 * 1024, "latent rollout: hidden size %d not supported", h);
     if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_bwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
