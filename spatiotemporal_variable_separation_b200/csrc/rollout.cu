@@ -229,7 +229,8 @@ struct RolloutClusterArgs {
     int T, B, d, h, nb;
 };
 
-// shared memory (floats): per block j: WA[hs][d+1] | WB[hs][h] | WC[d][hs] | bA[hs] | bB[hs] | bC[d]
+// shared memory (floats): per block j: WA[hs][d+1] | WB[hs][h] | WC[d][hs+1] | bA[hs] | bB[hs] | bC[d]
+//   (WA and WC rows padded by one float: conflict-free when lanes walk down a column)
 //                         then x[RC_ROWS][d] | full[RC_ROWS][h] | outB[RC_ROWS][hs] | part[RC_CS][RC_ROWS][d]
 template <bool BWD>
 __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const RolloutClusterArgs a, const RolloutWeights w) {
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const Ro
     const int row0 = cluster_id * RC_ROWS;
     const int nrow = min(RC_ROWS, B - row0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wstride = (hs * (d + 1) + hs * h + d * hs + 2 * hs + d + 3) & ~3;      // multiple of 4 floats (float4 reads)
+    const int wstride = (hs * (d + 1) + hs * h + d * (hs + 1) + 2 * hs + d + 3) & ~3;      // multiple of 4 floats (float4 reads)
     float* x = sm + (size_t)nb * wstride;
     float* full = x + RC_ROWS * d;
     float* outB = full + RC_ROWS * h;
@@ -251,13 +252,13 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const Ro
     // ---- resident weights.  Layer A = first layer applied (fwd: W1 [h][d]; bwd: W3^T [h][d]), B = middle, C = last
     for (int j = 0; j < nb; ++j) {
         float* WA = sm + (size_t)j * wstride; float* WB = WA + hs * (d + 1); float* WC = WB + hs * h;
-        float* bA = WC + d * hs; float* bB = bA + hs; float* bC = bB + hs;
+        float* bA = WC + d * (hs + 1); float* bB = bA + hs; float* bC = bB + hs;
         const float* gA = BWD ? w.w3[j] : w.w1[j];
         const float* gB = w.w2[j];
         const float* gC = BWD ? w.w1[j] : w.w3[j];
         for (int i = tid; i < hs * d; i += RC_THREADS) { const int o = i / d, k = i - o * d; WA[o * (d + 1) + k] = gA[(long long)(rank * hs + o) * d + k]; }
         for (int i = tid; i < hs * h; i += RC_THREADS) WB[i] = gB[(long long)rank * hs * h + i];
-        for (int i = tid; i < d * hs; i += RC_THREADS) { const int n = i / hs, k = i - n * hs; WC[i] = gC[(long long)n * h + rank * hs + k]; }
+        for (int i = tid; i < d * hs; i += RC_THREADS) { const int n = i / hs, k = i - n * hs; WC[n * (hs + 1) + k] = gC[(long long)n * h + rank * hs + k]; }
         for (int i = tid; i < hs; i += RC_THREADS) { bA[i] = BWD ? 0.f : w.b1[j][rank * hs + i]; bB[i] = BWD ? 0.f : w.b2[j][rank * hs + i]; }
         for (int i = tid; i < d; i += RC_THREADS) bC[i] = BWD ? 0.f : w.b3[j][i];
     }
@@ -268,46 +269,58 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const Ro
     }
     cluster_sync_all();          // also: every CTA of the cluster has started (DSMEM is valid from here on)
 
+    // one (unit, row) item per thread in layers A and B, one (output, row) item in layer C (host checks hs*8 <= 512, d*8 <= 512)
+    const bool itemA = tid < hs * RC_ROWS;
+    const int oA = tid % hs, rA = tid / hs;
+    const int otB = warp, oB = otB * 4 + (lane >> 3), rB = lane & 7;
+    const bool warpB = otB < hs / 4;
+    const bool itemC = tid < d * RC_ROWS;
+    const int nC = tid % d, rC = tid / d;
     for (int step = 1; step < T; ++step) {
         const int t = BWD ? T - step : step;
         for (int jj = 0; jj < nb; ++jj) {
             const int j = BWD ? nb - 1 - jj : jj;
             const long long slot = (long long)j * (T - 1) + (t - 1);
             float* WA = sm + (size_t)j * wstride; float* WB = WA + hs * (d + 1); float* WC = WB + hs * h;
-            float* bA = WC + d * hs; float* bB = bA + hs; float* bC = bB + hs;
+            float* bA = WC + d * (hs + 1); float* bB = bA + hs; float* bC = bB + hs;
+            const long long giA = (hslot(j, BWD ? 1 : 0, t) * B + row0 + rA) * h + rank * hs + oA;
+            const long long giB = (hslot(j, BWD ? 0 : 1, t) * B + row0 + rB) * h + rank * hs + oB;
+            // backward: the saved hiddens that gate this step's gradients are fetched now and consumed after the GEMVs
+            float gateA = 1.f, gateB = 1.f;
+            if (BWD) {
+                if (itemA && rA < nrow) gateA = a.hidden[giA];
+                if (warpB && rB < nrow) gateB = a.hidden[giB];
+            }
+            // ---- layer A: this CTA's hs hidden units for all rows, scattered into every CTA's `full`
+            float vA = 0.f;
+            if (itemA) {
+                float acc = bA[oA];
+                const float* wr = WA + oA * (d + 1);
+                const float* xr = x + rA * d;
+                for (int k = 0; k < d; ++k) acc = fmaf(wr[k], xr[k], acc);
+                vA = BWD ? ((rA < nrow && gateA > 0.f) ? acc : 0.f) : fmaxf(acc, 0.f);
+                float* loc = full + rA * h + rank * hs + oA;
+#pragma unroll
+                for (int c = 0; c < RC_CS; ++c) dsmem_store(dsmem_addr(loc, (uint32_t)c), vA);
+            }
+            cluster_sync_all();
+            // global stores are issued AFTER the barrier: its release semantics would otherwise wait for them to drain
+            if (itemA && rA < nrow && a.hidden_out) a.hidden_out[giA] = vA;
             if (rank == 0) {
                 // fwd: block input (for the W1 gradient);  bwd: gradient of the block's residual output
                 float* dst = BWD ? a.res : a.xin;
-                if (dst) for (int i = tid; i < nrow * d; i += RC_THREADS) dst[(slot * B + row0) * d + i] = x[i];
+                if (dst && tid < nrow * d) dst[(slot * B + row0) * d + tid] = x[tid];
             }
-            // ---- layer A: this CTA's hs hidden units for all rows, scattered into every CTA's `full`
-            for (int pI = tid; pI < hs * RC_ROWS; pI += RC_THREADS) {
-                const int o = pI % hs, r = pI / hs;
-                float acc = bA[o];
-                const float* wr = WA + o * (d + 1);
-                const float* xr = x + r * d;
-                for (int k = 0; k < d; ++k) acc = fmaf(wr[k], xr[k], acc);
-                const long long gi = (hslot(j, BWD ? 1 : 0, t) * B + row0 + r) * h + rank * hs + o;
-                if (BWD) {
-                    acc = (r < nrow && a.hidden[gi] > 0.f) ? acc : 0.f;
-                } else {
-                    acc = fmaxf(acc, 0.f);
-                }
-                if (r < nrow && a.hidden_out) a.hidden_out[gi] = acc;
-                float* loc = full + r * h + rank * hs + o;
-#pragma unroll
-                for (int c = 0; c < RC_CS; ++c) dsmem_store(dsmem_addr(loc, (uint32_t)c), acc);
-            }
-            cluster_sync_all();
             // ---- layer B: warp = tile of 4 hidden units, lanes split k, 32 accumulators (4 units x 8 rows) per lane
-            for (int ot = warp; ot < hs / 4; ot += RC_THREADS / 32) {
+            float vB = 0.f;
+            if (warpB) {
                 float acc[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) acc[i] = 0.f;
                 for (int k = lane * 4; k < h; k += 128) {
                     float4 wv[4];
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) wv[o] = *reinterpret_cast<const float4*>(WB + (ot * 4 + o) * h + k);
+                    for (int o = 0; o < 4; ++o) wv[o] = *reinterpret_cast<const float4*>(WB + (otB * 4 + o) * h + k);
 #pragma unroll
                     for (int r = 0; r < RC_ROWS; ++r) {
                         const float4 xv = *reinterpret_cast<const float4*>(full + r * h + k);
@@ -316,52 +329,43 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const Ro
                             acc[o * 8 + r] += wv[o].x * xv.x + wv[o].y * xv.y + wv[o].z * xv.z + wv[o].w * xv.w;
                     }
                 }
-                const float tot = warp_transpose_sum32(acc, lane);       // lane i: unit ot*4 + i/8, row i%8
-                const int o = ot * 4 + (lane >> 3), r = lane & 7;
-                float v = tot + bB[o];
-                const long long gi = (hslot(j, BWD ? 0 : 1, t) * B + row0 + r) * h + rank * hs + o;
-                if (BWD) {
-                    v = (r < nrow && a.hidden[gi] > 0.f) ? v : 0.f;
-                } else {
-                    v = fmaxf(v, 0.f);
-                }
-                if (r < nrow && a.hidden_out) a.hidden_out[gi] = v;
-                outB[r * hs + o] = v;
+                const float tot = warp_transpose_sum32(acc, lane) + bB[oB];       // lane i: unit otB*4 + i/8, row i%8
+                vB = BWD ? ((rB < nrow && gateB > 0.f) ? tot : 0.f) : fmaxf(tot, 0.f);
+                outB[rB * hs + oB] = vB;
             }
             __syncthreads();
             // ---- layer C: partial sums over this CTA's slice of the hidden units, sent to every CTA
-            for (int pI = tid; pI < d * RC_ROWS; pI += RC_THREADS) {
-                const int n = pI % d, r = pI / d;
+            if (itemC) {
                 float acc = 0.f;
-                const float* wr = WC + n * hs;
-                const float* vr = outB + r * hs;
+                const float* wr = WC + nC * (hs + 1);
+                const float* vr = outB + rC * hs;
                 for (int k = 0; k < hs; ++k) acc = fmaf(wr[k], vr[k], acc);
-                float* loc = part + (rank * RC_ROWS + r) * d + n;
+                float* loc = part + (rank * RC_ROWS + rC) * d + nC;
 #pragma unroll
                 for (int c = 0; c < RC_CS; ++c) dsmem_store(dsmem_addr(loc, (uint32_t)c), acc);
             }
             cluster_sync_all();
+            if (warpB && rB < nrow && a.hidden_out) a.hidden_out[giB] = vB;
             // ---- residual update, identical in every CTA (fixed summation order over the ranks)
-            for (int pI = tid; pI < d * RC_ROWS; pI += RC_THREADS) {
-                const int n = pI % d, r = pI / d;
-                float rr = bC[n];
+            if (itemC) {
+                float rr = bC[nC];
 #pragma unroll
-                for (int c = 0; c < RC_CS; ++c) rr += part[(c * RC_ROWS + r) * d + n];
-                if (!BWD && rank == 0 && r < nrow && a.res) a.res[(slot * B + row0 + r) * d + n] = rr;
-                x[r * d + n] += rr;
+                for (int c = 0; c < RC_CS; ++c) rr += part[(c * RC_ROWS + rC) * d + nC];
+                if (!BWD && rank == 0 && rC < nrow && a.res) a.res[(slot * B + row0 + rC) * d + nC] = rr;
+                x[rC * d + nC] += rr;
             }
             __syncthreads();
         }
         if (BWD) {
             // the decoder's gradient w.r.t. codes[t-1] joins the chain
-            for (int i = tid; i < nrow * d; i += RC_THREADS) {
-                const long long o = ((long long)(t - 1) * B + row0) * d + i;
-                x[i] += a.codes[o];
+            if (tid < nrow * d) {
+                const long long o = ((long long)(t - 1) * B + row0) * d + tid;
+                x[tid] += a.codes[o];
+                if (t == 1 && rank == 0) a.codes[o] = x[tid];
             }
             __syncthreads();
-            if (t == 1 && rank == 0) for (int i = tid; i < nrow * d; i += RC_THREADS) a.codes[((long long)row0) * d + i] = x[i];
         } else if (rank == 0) {
-            for (int i = tid; i < nrow * d; i += RC_THREADS) a.codes[((long long)t * B + row0) * d + i] = x[i];
+            if (tid < nrow * d) a.codes[((long long)t * B + row0) * d + tid] = x[tid];
         }
     }
     cluster_sync_all();          // no CTA exits while a peer may still write into its shared memory
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const Ro
 
 static size_t rollout_cluster_smem(int d, int h, int nb) {
     const int hs = h / RC_CS;
-    const size_t wstride = ((size_t)hs * (d + 1) + (size_t)hs * h + (size_t)d * hs + 2 * hs + d + 3) & ~(size_t)3;
+    const size_t wstride = ((size_t)hs * (d + 1) + (size_t)hs * h + (size_t)d * (hs + 1) + 2 * hs + d + 3) & ~(size_t)3;
     return (nb * wstride + (size_t)RC_ROWS * d + (size_t)RC_ROWS * h + (size_t)RC_ROWS * hs + (size_t)RC_CS * RC_ROWS * d) * sizeof(float);
 }
 
@@ -378,7 +382,8 @@ static bool rollout_cluster_eligible(int d, int h, int nb) {
     static int off = -1;
     if (off < 0) { const char* e = getenv("VARSEP_DISABLE_ROLLOUT_CLUSTER"); off = (e && e[0] == '1') ? 1 : 0; }
     if (off) return false;
-    if (h % (RC_CS * 4) != 0 || h < RC_CS * 4 || d < 1 || d > 256) return false;
+    // one (unit, row) / (output, row) item per thread
+    if (h % (RC_CS * 4) != 0 || h < RC_CS * 4 || (h / RC_CS) * RC_ROWS > RC_THREADS || d < 1 || d * RC_ROWS > RC_THREADS) return false;
     return rollout_cluster_smem(d, h, nb) <= 220 * 1024;
 }
 
