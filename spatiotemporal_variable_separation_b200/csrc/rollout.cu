@@ -201,9 +201,8 @@ static int fill_weights(RolloutWeights& rw, const float* const* w_host, int nb) 
 // =================================================================================================
 namespace vs {
 
-constexpr int RC_CS = 8;          // CTAs per cluster
-constexpr int RC_ROWS = 8;        // batch rows per cluster
 constexpr int RC_THREADS = 512;
+constexpr int RC_MAX_ITEMS = 2;   // (unit, row) items per thread in layer A, warp tasks per warp in layer B
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -229,24 +228,29 @@ struct RolloutClusterArgs {
     int T, B, d, h, nb;
 };
 
+// CS = CTAs per cluster (8 portable, 16 where the device can co-schedule it), R = batch rows per cluster (8 or 16).
+// The arithmetic of a row does not depend on R (rows never mix; every accumulator goes through the same lane
+// butterfly), so R may follow the batch size; CS changes the order of the layer-C partial sums and is therefore a
+// property of the device only (eval rollouts stay bit-identical across batch sizes).
 // shared memory (floats): per block j: WA[hs][d+1] | WB[hs][h] | WC[d][hs+1] | bA[hs] | bB[hs] | bC[d]
 //   (WA and WC rows padded by one float: conflict-free when lanes walk down a column)
-//                         then x[RC_ROWS][d] | full[RC_ROWS][h] | outB[RC_ROWS][hs] | part[RC_CS][RC_ROWS][d]
-template <bool BWD>
+//                         then x[R][d] | full[R][h] | outB[R][hs] | part[CS][R][d]
+template <bool BWD, int CS, int R>
 __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const RolloutClusterArgs a, const RolloutWeights w) {
+    constexpr int OUTS = 32 / R;      // hidden units per warp task in layer B (OUTS * R = 32 accumulators per lane)
     extern __shared__ float sm[];
     const int T = a.T, B = a.B, d = a.d, h = a.h, nb = a.nb;
-    const int hs = h / RC_CS;
+    const int hs = h / CS;
     const int rank = (int)cluster_rank();
-    const int cluster_id = blockIdx.x / RC_CS;
-    const int row0 = cluster_id * RC_ROWS;
-    const int nrow = min(RC_ROWS, B - row0);
+    const int cluster_id = blockIdx.x / CS;
+    const int row0 = cluster_id * R;
+    const int nrow = min(R, B - row0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wstride = (hs * (d + 1) + hs * h + d * (hs + 1) + 2 * hs + d + 3) & ~3;      // multiple of 4 floats (float4 reads)
     float* x = sm + (size_t)nb * wstride;
-    float* full = x + RC_ROWS * d;
-    float* outB = full + RC_ROWS * h;
-    float* part = outB + RC_ROWS * hs;
+    float* full = x + R * d;
+    float* outB = full + R * h;
+    float* part = outB + R * hs;
 #define hslot(j, which, t) ((((long long)(j) * 2 + (which)) * (T - 1)) + ((t) - 1))
 
     // ---- resident weights.  Layer A = first layer applied (fwd: W1 [h][d]; bwd: W3^T [h][d]), B = middle, C = last
@@ -263,18 +267,15 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const Ro
         for (int i = tid; i < d; i += RC_THREADS) bC[i] = BWD ? 0.f : w.b3[j][i];
     }
     // ---- initial state (every CTA of the cluster keeps a copy)
-    for (int i = tid; i < RC_ROWS * d; i += RC_THREADS) {
+    for (int i = tid; i < R * d; i += RC_THREADS) {
         const int r = i / d, k = i - r * d;
         x[i] = r < nrow ? a.codes[((long long)(BWD ? T - 1 : 0) * B + row0 + r) * d + k] : 0.f;
     }
     cluster_sync_all();          // also: every CTA of the cluster has started (DSMEM is valid from here on)
 
-    // one (unit, row) item per thread in layers A and B, one (output, row) item in layer C (host checks hs*8 <= 512, d*8 <= 512)
-    const bool itemA = tid < hs * RC_ROWS;
-    const int oA = tid % hs, rA = tid / hs;
-    const int otB = warp, oB = otB * 4 + (lane >> 3), rB = lane & 7;
-    const bool warpB = otB < hs / 4;
-    const bool itemC = tid < d * RC_ROWS;
+    // work items (host checks hs*R <= 2*512, hs/OUTS <= 2*16 warps, d*R <= 512)
+    const int nA = hs * R, nBt = hs / OUTS;
+    const bool itemC = tid < d * R;
     const int nC = tid % d, rC = tid / d;
     for (int step = 1; step < T; ++step) {
         const int t = BWD ? T - step : step;
@@ -283,55 +284,71 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const Ro
             const long long slot = (long long)j * (T - 1) + (t - 1);
             float* WA = sm + (size_t)j * wstride; float* WB = WA + hs * (d + 1); float* WC = WB + hs * h;
             float* bA = WC + d * (hs + 1); float* bB = bA + hs; float* bC = bB + hs;
-            const long long giA = (hslot(j, BWD ? 1 : 0, t) * B + row0 + rA) * h + rank * hs + oA;
-            const long long giB = (hslot(j, BWD ? 0 : 1, t) * B + row0 + rB) * h + rank * hs + oB;
+            const long long baseA = hslot(j, BWD ? 1 : 0, t) * B + row0, baseB = hslot(j, BWD ? 0 : 1, t) * B + row0;
             // backward: the saved hiddens that gate this step's gradients are fetched now and consumed after the GEMVs
-            float gateA = 1.f, gateB = 1.f;
-            if (BWD) {
-                if (itemA && rA < nrow) gateA = a.hidden[giA];
-                if (warpB && rB < nrow) gateB = a.hidden[giB];
+            float gateA[RC_MAX_ITEMS], gateB[RC_MAX_ITEMS], vA[RC_MAX_ITEMS], vB[RC_MAX_ITEMS];
+#pragma unroll
+            for (int ii = 0; ii < RC_MAX_ITEMS; ++ii) {
+                gateA[ii] = gateB[ii] = 1.f; vA[ii] = vB[ii] = 0.f;
+                if (BWD) {
+                    const int pA = tid + ii * RC_THREADS, oA = pA % hs, rA = pA / hs;
+                    if (pA < nA && rA < nrow) gateA[ii] = a.hidden[(baseA + rA) * h + rank * hs + oA];
+                    const int ot = warp + ii * (RC_THREADS / 32), oB = ot * OUTS + lane / R, rB = lane % R;
+                    if (ot < nBt && rB < nrow) gateB[ii] = a.hidden[(baseB + rB) * h + rank * hs + oB];
+                }
             }
             // ---- layer A: this CTA's hs hidden units for all rows, scattered into every CTA's `full`
-            float vA = 0.f;
-            if (itemA) {
-                float acc = bA[oA];
-                const float* wr = WA + oA * (d + 1);
-                const float* xr = x + rA * d;
-                for (int k = 0; k < d; ++k) acc = fmaf(wr[k], xr[k], acc);
-                vA = BWD ? ((rA < nrow && gateA > 0.f) ? acc : 0.f) : fmaxf(acc, 0.f);
-                float* loc = full + rA * h + rank * hs + oA;
 #pragma unroll
-                for (int c = 0; c < RC_CS; ++c) dsmem_store(dsmem_addr(loc, (uint32_t)c), vA);
+            for (int ii = 0; ii < RC_MAX_ITEMS; ++ii) {
+                const int pA = tid + ii * RC_THREADS, oA = pA % hs, rA = pA / hs;
+                if (pA < nA) {
+                    float acc = bA[oA];
+                    const float* wr = WA + oA * (d + 1);
+                    const float* xr = x + rA * d;
+                    for (int k = 0; k < d; ++k) acc = fmaf(wr[k], xr[k], acc);
+                    vA[ii] = BWD ? ((rA < nrow && gateA[ii] > 0.f) ? acc : 0.f) : fmaxf(acc, 0.f);
+                    float* loc = full + rA * h + rank * hs + oA;
+#pragma unroll
+                    for (int c = 0; c < CS; ++c) dsmem_store(dsmem_addr(loc, (uint32_t)c), vA[ii]);
+                }
             }
             cluster_sync_all();
-            // global stores are issued AFTER the barrier: its release semantics would otherwise wait for them to drain
-            if (itemA && rA < nrow && a.hidden_out) a.hidden_out[giA] = vA;
+            // global stores are issued after the barrier, next to the longest stretch of arithmetic
+#pragma unroll
+            for (int ii = 0; ii < RC_MAX_ITEMS; ++ii) {
+                const int pA = tid + ii * RC_THREADS, oA = pA % hs, rA = pA / hs;
+                if (pA < nA && rA < nrow && a.hidden_out) a.hidden_out[(baseA + rA) * h + rank * hs + oA] = vA[ii];
+            }
             if (rank == 0) {
                 // fwd: block input (for the W1 gradient);  bwd: gradient of the block's residual output
                 float* dst = BWD ? a.res : a.xin;
                 if (dst && tid < nrow * d) dst[(slot * B + row0) * d + tid] = x[tid];
             }
-            // ---- layer B: warp = tile of 4 hidden units, lanes split k, 32 accumulators (4 units x 8 rows) per lane
-            float vB = 0.f;
-            if (warpB) {
-                float acc[32];
+            // ---- layer B: warp task = OUTS hidden units x R rows, lanes split k, 32 accumulators per lane
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-                for (int k = lane * 4; k < h; k += 128) {
-                    float4 wv[4];
+            for (int ii = 0; ii < RC_MAX_ITEMS; ++ii) {
+                const int ot = warp + ii * (RC_THREADS / 32);
+                if (ot < nBt) {
+                    float acc[32];
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) wv[o] = *reinterpret_cast<const float4*>(WB + (otB * 4 + o) * h + k);
+                    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                    for (int k = lane * 4; k < h; k += 128) {
+                        float4 wv[OUTS];
 #pragma unroll
-                    for (int r = 0; r < RC_ROWS; ++r) {
-                        const float4 xv = *reinterpret_cast<const float4*>(full + r * h + k);
+                        for (int o = 0; o < OUTS; ++o) wv[o] = *reinterpret_cast<const float4*>(WB + (ot * OUTS + o) * h + k);
 #pragma unroll
-                        for (int o = 0; o < 4; ++o)
-                            acc[o * 8 + r] += wv[o].x * xv.x + wv[o].y * xv.y + wv[o].z * xv.z + wv[o].w * xv.w;
+                        for (int r = 0; r < R; ++r) {
+                            const float4 xv = *reinterpret_cast<const float4*>(full + r * h + k);
+#pragma unroll
+                            for (int o = 0; o < OUTS; ++o)
+                                acc[o * R + r] += wv[o].x * xv.x + wv[o].y * xv.y + wv[o].z * xv.z + wv[o].w * xv.w;
+                        }
                     }
+                    const int oB = ot * OUTS + lane / R, rB = lane % R;
+                    const float tot = warp_transpose_sum32(acc, lane) + bB[oB];       // lane i: unit ot*OUTS + i/R, row i%R
+                    vB[ii] = BWD ? ((rB < nrow && gateB[ii] > 0.f) ? tot : 0.f) : fmaxf(tot, 0.f);
+                    outB[rB * hs + oB] = vB[ii];
                 }
-                const float tot = warp_transpose_sum32(acc, lane) + bB[oB];       // lane i: unit otB*4 + i/8, row i%8
-                vB = BWD ? ((rB < nrow && gateB > 0.f) ? tot : 0.f) : fmaxf(tot, 0.f);
-                outB[rB * hs + oB] = vB;
             }
             __syncthreads();
             // ---- layer C: partial sums over this CTA's slice of the hidden units, sent to every CTA
@@ -340,17 +357,21 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const Ro
                 const float* wr = WC + nC * (hs + 1);
                 const float* vr = outB + rC * hs;
                 for (int k = 0; k < hs; ++k) acc = fmaf(wr[k], vr[k], acc);
-                float* loc = part + (rank * RC_ROWS + rC) * d + nC;
+                float* loc = part + (rank * R + rC) * d + nC;
 #pragma unroll
-                for (int c = 0; c < RC_CS; ++c) dsmem_store(dsmem_addr(loc, (uint32_t)c), acc);
+                for (int c = 0; c < CS; ++c) dsmem_store(dsmem_addr(loc, (uint32_t)c), acc);
             }
             cluster_sync_all();
-            if (warpB && rB < nrow && a.hidden_out) a.hidden_out[giB] = vB;
+#pragma unroll
+            for (int ii = 0; ii < RC_MAX_ITEMS; ++ii) {
+                const int ot = warp + ii * (RC_THREADS / 32), oB = ot * OUTS + lane / R, rB = lane % R;
+                if (ot < nBt && rB < nrow && a.hidden_out) a.hidden_out[(baseB + rB) * h + rank * hs + oB] = vB[ii];
+            }
             // ---- residual update, identical in every CTA (fixed summation order over the ranks)
             if (itemC) {
                 float rr = bC[nC];
 #pragma unroll
-                for (int c = 0; c < RC_CS; ++c) rr += part[(c * RC_ROWS + rC) * d + nC];
+                for (int c = 0; c < CS; ++c) rr += part[(c * R + rC) * d + nC];
                 if (!BWD && rank == 0 && rC < nrow && a.res) a.res[(slot * B + row0 + rC) * d + nC] = rr;
                 x[rC * d + nC] += rr;
             }
@@ -372,39 +393,102 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rollout_cluster_kernel(const Ro
 #undef hslot
 }
 
-static size_t rollout_cluster_smem(int d, int h, int nb) {
-    const int hs = h / RC_CS;
+static size_t rollout_cluster_smem(int d, int h, int nb, int CS, int R) {
+    const int hs = h / CS;
     const size_t wstride = ((size_t)hs * (d + 1) + (size_t)hs * h + (size_t)d * (hs + 1) + 2 * hs + d + 3) & ~(size_t)3;
-    return (nb * wstride + (size_t)RC_ROWS * d + (size_t)RC_ROWS * h + (size_t)RC_ROWS * hs + (size_t)RC_CS * RC_ROWS * d) * sizeof(float);
+    return (nb * wstride + (size_t)R * d + (size_t)R * h + (size_t)R * hs + (size_t)CS * R * d) * sizeof(float);
 }
 
-static bool rollout_cluster_eligible(int d, int h, int nb) {
-    static int off = -1;
-    if (off < 0) { const char* e = getenv("VARSEP_DISABLE_ROLLOUT_CLUSTER"); off = (e && e[0] == '1') ? 1 : 0; }
-    if (off) return false;
-    // one (unit, row) / (output, row) item per thread
-    if (h % (RC_CS * 4) != 0 || h < RC_CS * 4 || (h / RC_CS) * RC_ROWS > RC_THREADS || d < 1 || d * RC_ROWS > RC_THREADS) return false;
-    return rollout_cluster_smem(d, h, nb) <= 220 * 1024;
+static bool rollout_cluster_fits(int d, int h, int nb, int CS, int R) {
+    const int hs = h / CS, outs = 32 / R;
+    if (h % (CS * 4) != 0 || hs < 4 || hs % outs != 0) return false;
+    if (hs * R > RC_MAX_ITEMS * RC_THREADS || hs / outs > RC_MAX_ITEMS * (RC_THREADS / 32) || d < 1 || d * R > RC_THREADS) return false;
+    return rollout_cluster_smem(d, h, nb, CS, R) <= 220 * 1024;
 }
 
-template <bool BWD>
-static int launch_rollout_cluster(const RolloutClusterArgs& a, const RolloutWeights& rw, cudaStream_t stream) {
-    const size_t smem = rollout_cluster_smem(a.d, a.h, a.nb);
-    cudaError_t e = cudaFuncSetAttribute(rollout_cluster_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail("rollout_cluster_kernel smem attribute: %s", cudaGetErrorString(e));
+template <bool BWD, int CS, int R>
+static int rollout_cluster_max_active(int d, int h, int nb) {
+    // clusters of this shape the device can keep resident at once (0: cannot launch)
+    const size_t smem = rollout_cluster_smem(d, h, nb, CS, R);
+    if (cudaFuncSetAttribute(rollout_cluster_kernel<BWD, CS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (CS > 8 && cudaFuncSetAttribute(rollout_cluster_kernel<BWD, CS, R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(cdiv(a.B, RC_ROWS) * RC_CS));
+    cfg.gridDim = dim3((unsigned)(CS * 64));
+    cfg.blockDim = dim3(RC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, rollout_cluster_kernel<BWD, CS, R>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+template <bool BWD, int CS, int R>
+static int launch_rollout_cluster(const RolloutClusterArgs& a, const RolloutWeights& rw, cudaStream_t stream) {
+    const size_t smem = rollout_cluster_smem(a.d, a.h, a.nb, CS, R);
+    cudaError_t e = cudaFuncSetAttribute(rollout_cluster_kernel<BWD, CS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail("rollout_cluster_kernel smem attribute: %s", cudaGetErrorString(e));
+    if (CS > 8) {
+        e = cudaFuncSetAttribute(rollout_cluster_kernel<BWD, CS, R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return fail("rollout_cluster_kernel cluster attribute: %s", cudaGetErrorString(e));
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(cdiv(a.B, R) * CS));
     cfg.blockDim = dim3(RC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = RC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, rollout_cluster_kernel<BWD>, a, rw);
+    e = cudaLaunchKernelEx(&cfg, rollout_cluster_kernel<BWD, CS, R>, a, rw);
     if (e != cudaSuccess) return fail("rollout_cluster_kernel launch: %s", cudaGetErrorString(e));
     return launched("rollout_cluster_kernel");
+}
+
+// returns 0 = launched, -1 = this (d, h, n_blocks) does not fit the cluster kernel, >0 = error.
+// Cluster size: 16 if the device can keep at least 8 such clusters resident, else 8 (a device property, never the batch
+// size); rows per cluster: 8, or 16 when that avoids a second wave of clusters.
+template <bool BWD>
+static int rollout_cluster(const RolloutClusterArgs& a, const RolloutWeights& rw, cudaStream_t stream) {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("VARSEP_DISABLE_ROLLOUT_CLUSTER"); off = (e && e[0] == '1') ? 1 : 0; }
+    if (off) return -1;
+    struct Choice { int d, h, nb, cs, max8, max16; };
+    static Choice cache = {0, 0, 0, 0, 0, 0};
+    if (cache.d != a.d || cache.h != a.h || cache.nb != a.nb || cache.cs == 0) {
+        Choice c = {a.d, a.h, a.nb, -1, 0, 0};
+        if (rollout_cluster_fits(a.d, a.h, a.nb, 16, 8)) {
+            c.max8 = rollout_cluster_max_active<BWD, 16, 8>(a.d, a.h, a.nb);
+            if (c.max8 >= 8) {
+                c.cs = 16;
+                c.max16 = rollout_cluster_fits(a.d, a.h, a.nb, 16, 16) ? rollout_cluster_max_active<BWD, 16, 16>(a.d, a.h, a.nb) : 0;
+            }
+        }
+        if (c.cs < 0 && rollout_cluster_fits(a.d, a.h, a.nb, 8, 8)) {
+            c.max8 = rollout_cluster_max_active<BWD, 8, 8>(a.d, a.h, a.nb);
+            if (c.max8 >= 1) {
+                c.cs = 8;
+                c.max16 = rollout_cluster_fits(a.d, a.h, a.nb, 8, 16) ? rollout_cluster_max_active<BWD, 8, 16>(a.d, a.h, a.nb) : 0;
+            }
+        }
+        cache = c;
+    }
+    if (cache.cs < 0) return -1;
+    const long long need8 = cdiv(a.B, 8), need16 = cdiv(a.B, 16);
+    const bool rows16 = cache.max16 > 0 && cdiv(need8, cache.max8) > cdiv(need16, cache.max16);
+    if (cache.cs == 16) return rows16 ? launch_rollout_cluster<BWD, 16, 16>(a, rw, stream) : launch_rollout_cluster<BWD, 16, 8>(a, rw, stream);
+    return rows16 ? launch_rollout_cluster<BWD, 8, 16>(a, rw, stream) : launch_rollout_cluster<BWD, 8, 8>(a, rw, stream);
 }
 
 }  // namespace vs
@@ -419,9 +503,10 @@ extern "C" int vs_latent_rollout_forward(float* codes, const float* const* w_hos
     if (T == 1) return 0;
     RolloutWeights rw;
     if (int rc = fill_weights(rw, w_host, n_blocks)) return rc;
-    if (rollout_cluster_eligible(d, h, n_blocks)) {
+    {
         RolloutClusterArgs a = {codes, nullptr, hidden, xin, res, T, B, d, h, n_blocks};
-        return launch_rollout_cluster<false>(a, rw, as_stream(stream));
+        const int rc = rollout_cluster<false>(a, rw, as_stream(stream));
+        if (rc >= 0) return rc;
     }
     const int smem = (2 * RB * d + 2 * RB * h) * (int)sizeof(float);
     VS_REQUIRE(smem <= 200 * 1024 && (h % 4) == 0, "latent rollout: hidden size %d not supported", h);
@@ -437,9 +522,10 @@ extern "C" int vs_latent_rollout_backward(float* dcodes, const float* const* w_h
     if (T == 1) return 0;
     RolloutWeights rw;
     if (int rc = fill_weights(rw, w_host, n_blocks)) return rc;
-    if (rollout_cluster_eligible(d, h, n_blocks)) {
+    {
         RolloutClusterArgs a = {dcodes, hidden, dhidden, nullptr, dres, T, B, d, h, n_blocks};
-        return launch_rollout_cluster<true>(a, rw, as_stream(stream));
+        const int rc = rollout_cluster<true>(a, rw, as_stream(stream));
+        if (rc >= 0) return rc;
     }
     const int smem = (2 * RB * d + 2 * RB * h) * (int)sizeof(float);
     VS_REQUIRE(smem <= 200 * 1024, "latent rollout: hidden size %d not supported", h);
