@@ -2,7 +2,7 @@
 //
 // Replaces the cuDNN kernels behind nn.Conv2d / nn.ConvTranspose2d of the DCGAN / VGG / SST stacks
 // (/root/reference/var_sep/networks/conv.py:119-123,147-170,258-263,295-318) for the layers whose
-// channel counts are multiples of 64.  One kernel covers
+// input channel count is a multiple of 8 (16-byte TMA pitch).  One kernel covers
 //   - direct convolutions (any R x S, stride 1 or 2, zero padding),
 //   - transposed convolutions, decomposed into stride*stride output-parity classes so that no
 //     structurally-zero tap is ever multiplied (k4 s2 p1: four 2x2 stride-1 convolutions),
@@ -10,9 +10,9 @@
 // of the NHWC input (shifted by the tap offset, zero-filled outside the image by the TMA unit, strided
 // for stride-2 convolutions) is multiplied with a [BN x 64] slab of the packed weights.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
-// issuer, warps 2..5 = epilogue (TMEM -> registers -> bias / activation -> bf16 -> global).
-// Two CTAs are resident per SM so one tile's epilogue overlaps the other's main loop.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..9 = epilogue (TMEM -> registers -> bias / activation / BatchNorm sums -> bf16 -> global, directly or
+// through a staged shared-memory tile and a TMA store).  Persistent CTAs, two per SM, two TMEM accumulator stages.
 #include <cuda.h>
 
 #include "common.cuh"
