@@ -271,6 +271,223 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
 #undef VS_TC_DECODE
 }
 
+// ------------------------------------------------------------------------------------------ CTA pairs
+// cta_group::2 variant for the wide layers (OC a multiple of 128): the two CTAs of a cluster (one TPC) work on two
+// adjacent 128-pixel tiles and the SAME BN output channels.  Each CTA stages its own A box and only HALF of the weight
+// slab; one thread of the leader CTA issues tcgen05.mma.cta_group::2 (M = 256 over the pair, N = BN), which reads both
+// shared memories and writes both tensor memories.  Per 64-channel chunk a CTA stages 16 + BN/8 KB instead of
+// 16 + BN/4 KB for the same 128 x BN x 64 MACs: the L2 -> shared-memory fill that bounds the single-CTA kernel drops by
+// 25 % (BN = 128) to 33 % (BN = 256, which one CTA cannot hold with double-buffered accumulators).
+// One CTA per SM (both TMEM accumulator stages of BN = 256 take all 512 columns), deeper smem ring instead.
+template <int BN, int STAGES>
+struct TcPairSmem {
+    static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = (BN / 2) * TC_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 2 * 4 /*tile statistics*/;
+    static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                     const __grid_constant__ CUtensorMap map_b,
+                                                                     const __grid_constant__ TcParams p,
+                                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                                     double* __restrict__ stats) {
+    using S = TcPairSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* full = bars;                          // leader's: both CTAs' TMA bytes of a stage have landed
+    uint64_t* empty = bars + STAGES;                // each CTA's: the MMAs that read this stage have completed
+    uint64_t* tmem_full = bars + 2 * STAGES;        // [2] each CTA's: accumulator stage complete
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2] leader's: both CTAs' epilogues have drained the stage
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* sstat = reinterpret_cast<float*>(smem + S::BAR_OFF + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cl_rank();
+    const bool leader = rank == 0;
+    const int nkb = p.ntaps * p.kchunks;
+    // work items of the PAIR: (class, channel tile, pair of pixel tiles); contiguous range per pair
+    const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+    const int t_begin = (int)((long long)pair * p.total_tiles / npairs);
+    const int t_end = (int)((long long)(pair + 1) * p.total_tiles / npairs);
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.f;
+    __syncthreads();
+    if (warp == 1) tmem_alloc_pair<2 * BN>(tmem_slot);
+    tc_fence_before();
+    cl_sync();                 // barriers of both CTAs initialised, both tensor memories allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // this CTA's pixel tile = 2 * pair index + rank (an odd tile count leaves the last rank-1 tile beyond the batch:
+    // its TMA boxes are zero-filled and its epilogue rows are masked)
+#define VS_TCP_DECODE(idx)                                                  \
+    const int cls = (idx) % p.classes;                                      \
+    const int rest_ = (idx) / p.classes;                                    \
+    const int n0 = (rest_ % p.n_tiles) * BN;                                \
+    int t_ = (rest_ / p.n_tiles) * 2 + rank;                                \
+    const int tw = t_ % p.tiles_w; t_ /= p.tiles_w;                         \
+    const int th = t_ % p.tiles_h;                                          \
+    const int tn = t_ / p.tiles_h;                                          \
+    const int j0 = tw * p.WT, i0 = th * p.HT, b0 = tn * p.NT;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A box + own half of the weight slab, completion on the LEADER's barrier =====
+        if (lane == 0) {
+            int it = 0;
+            for (int idx = t_begin; idx < t_end; ++idx) {
+                VS_TCP_DECODE(idx)
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+                    uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + S::A_BYTES;
+                    if (leader) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);
+                    const uint32_t bar = cl_map(&full[s], 0);
+                    tma_load_4d_pair(a_dst, &map_a, bar, kc * TC_BK, j0 * p.in_sw + p.dw[cls * p.ntaps + tap],
+                                     i0 * p.in_sh + p.dh[cls * p.ntaps + tap], b0);
+                    tma_load_2d_pair(b_dst, &map_b, bar, p.wtap[cls * p.ntaps + tap] * p.IC + kc * TC_BK, n0 + rank * (BN / 2));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA =====
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16_f32_pair(BN);
+            int it = 0, lt = 0;
+            for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)
+                        umma_bf16_pair(tmem_d, kmajor_sw128_desc(a_addr + k * 32), kmajor_sw128_desc(b_addr + k * 32), idesc,
+                                       (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_pair(&empty[s]);
+                }
+                umma_commit_pair(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 pixel rows of the pair tile =====
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int COLS_PER_WARP = BN / (TC_EPI_WARPS / 4);
+        const int m = q * 32 + lane;
+        const int w = m % p.WT, h = (m / p.WT) % p.HT, n = m / (p.WT * p.HT);
+        int lt = 0;
+        int stat_key = -1;
+        double stat_acc[2 * BN / (32 * TC_EPI_WARPS)] = {};
+        for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
+            VS_TCP_DECODE(idx)
+            const int acc = lt & 1;
+            const int i = i0 + h, j = j0 + w, nn = b0 + n;
+            const bool ok = i < p.OHc && j < p.OWc && nn < p.N;
+            const long long pix = ((long long)nn * p.OH + (long long)i * p.ost + p.ca[cls]) * p.OW + (long long)j * p.ost + p.cb[cls];
+            __nv_bfloat16* dst = out + pix * p.OC + n0;
+            mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                const float bias_l = p.has_bias ? __ldg(bias + n0 + c0 + lane) : 0.f;
+                float xs[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                if (ok) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = v * 8 + e * 2;
+                            __nv_bfloat162 b2 = p.act == VS_ACT_NONE ? __floats2bfloat162_rn(xs[c], xs[c + 1])
+                                                                     : __floats2bfloat162_rn(act_fwd(xs[c], p.act), act_fwd(xs[c + 1], p.act));
+                            pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                        }
+                        *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                if (stats != nullptr) {
+                    float wk[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] : 0.f;
+                    const float s1 = warp_transpose_sum32(wk, lane);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] * xs[c] : 0.f;
+                    const float s2 = warp_transpose_sum32(wk, lane);
+                    atomicAdd(&sstat[(c0 + lane) * 2], s1);
+                    atomicAdd(&sstat[(c0 + lane) * 2 + 1], s2);
+                }
+            }
+            // hand the accumulator stage back to the leader's MMA issuer (its barrier counts the warps of both CTAs)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(cl_map(&tmem_empty[acc], 0));
+            if (stats != nullptr) {
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+                const int t = threadIdx.x - 64;
+                const int key = (b0 / p.n_per_group) * p.n_tiles + n0 / BN;
+                if (key != stat_key) {
+                    if (stat_key >= 0) {
+#pragma unroll
+                        for (int e = 0; e < 2 * BN / (32 * TC_EPI_WARPS); ++e) {
+                            const int ii = t + e * 32 * TC_EPI_WARPS, col = (stat_key % p.n_tiles) * BN + (ii >> 1);
+                            atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (ii & 1)], stat_acc[e]);
+                            stat_acc[e] = 0.0;
+                        }
+                    }
+                    stat_key = key;
+                }
+#pragma unroll
+                for (int e = 0; e < 2 * BN / (32 * TC_EPI_WARPS); ++e) {
+                    const int ii = t + e * 32 * TC_EPI_WARPS;
+                    stat_acc[e] += (double)sstat[ii];
+                    sstat[ii] = 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            }
+        }
+        if (stats != nullptr && stat_key >= 0) {
+            const int t = threadIdx.x - 64;
+#pragma unroll
+            for (int e = 0; e < 2 * BN / (32 * TC_EPI_WARPS); ++e) {
+                const int ii = t + e * 32 * TC_EPI_WARPS, col = (stat_key % p.n_tiles) * BN + (ii >> 1);
+                atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (ii & 1)], stat_acc[e]);
+            }
+        }
+    }
+    // the leader's MMAs read the peer's shared memory and write its tensor memory: nobody leaves before everybody is done
+    tc_fence_before();
+    cl_sync();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair<2 * BN>(tmem_base);
+    }
+#undef VS_TCP_DECODE
+}
+
 // ------------------------------------------------------------------------------------------ host
 template <int BN, int STAGES, bool TS>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMaps& om, const TcParams& p, const float* bias,
@@ -290,6 +507,44 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMa
     const int grid = q.total_tiles < resident ? q.total_tiles : resident;      // every CTA gets at least one work item
     tc_conv_kernel<BN, STAGES, TS><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, om, q, bias, (__nv_bfloat16*)out, stats);
     return launched("tc_conv_kernel");
+}
+
+static bool pair_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VARSEP_DISABLE_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+template <int BN, int STAGES>
+static int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const float* bias, void* out, int classes,
+                          double* stats, cudaStream_t stream) {
+    using S = TcPairSmem<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return fail("tc_conv_pair_kernel smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    TcParams q = p;
+    q.classes = classes;
+    q.n_tiles = p.OC / BN;
+    const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    q.total_tiles = ((ptiles + 1) / 2) * q.n_tiles * classes;          // work items of a PAIR
+    int pairs = num_sms() / 2;                                         // one CTA per SM
+    if (pairs > q.total_tiles) pairs = q.total_tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_pair_kernel<BN, STAGES>, ma, mb, q, bias, (__nv_bfloat16*)out, stats);
+    if (e != cudaSuccess) return fail("tc_conv_pair_kernel launch: %s", cudaGetErrorString(e));
+    return launched("tc_conv_pair_kernel");
 }
 
 static bool staged_epilogue_disabled() {
@@ -385,10 +640,15 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     }
     const int BN = (OC % 128 == 0 || OC >= 512) ? 128 : 64;
     p.partial = (OC % 8 != 0) || (reinterpret_cast<uintptr_t>(out) & 15) ? 1 : 0;      // rows not 16-byte aligned
+    // wide layers: CTA pairs (cta_group::2), BN = 256 when OC allows.  A property of the layer, never of the batch size.
+    // (measured: 256-column pair tiles reach 1.2-1.4 PFLOP/s on the decoder layers; 128-column pair tiles lose to two
+    // single CTAs per SM except for long reduction loops, where the deeper ring of the pair kernel hides the latency)
+    const int PBN = OC % 256 == 0 ? 256 : 128;
+    const bool pair = OC % 128 == 0 && IC >= 64 && !p.partial && !pair_disabled() && (PBN == 256 || p.ntaps * p.kchunks >= 64);
     {
         cuuint64_t dims[2] = {(cuuint64_t)g->R * g->S * IC, (cuuint64_t)OC};
         cuuint64_t strides[1] = {(cuuint64_t)g->R * g->S * IC * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)BN};
+        cuuint32_t box[2] = {64, (cuuint32_t)(pair ? PBN / 2 : BN)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -417,7 +677,9 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
         }
     }
     double* stp = fuse_stats ? stats : nullptr;
-    int rc = BN == 128 ? launch_tc<128, 3, false>(ma, mb, om, p, bias, out, classes, stp, stream)
+    int rc = pair ? (PBN == 256 ? launch_tc_pair<256, 6>(ma, mb, p, bias, out, classes, stp, stream)
+                                : launch_tc_pair<128, 8>(ma, mb, p, bias, out, classes, stp, stream))
+             : BN == 128 ? launch_tc<128, 3, false>(ma, mb, om, p, bias, out, classes, stp, stream)
              : staged  ? launch_tc<64, 3, true>(ma, mb, om, p, bias, out, classes, stp, stream)
                        : launch_tc<64, 4, false>(ma, mb, om, p, bias, out, classes, stp, stream);
     if (rc) return rc;
