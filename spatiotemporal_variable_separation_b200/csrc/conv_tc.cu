@@ -817,6 +817,144 @@ __global__ void __launch_bounds__(192, 2) tc_wgrad_kernel(const __grid_constant_
     }
 }
 
+// CTA-pair variant (cta_group::2): the pair owns 256 channels of `small` (128 per CTA) x BN channels of `big` (BN/2 per
+// CTA) for one tap and one pixel range; per 64-pixel block a CTA stages 16 + BN/16 KB for 128 x BN x 64 MACs
+// (128 FLOP per staged byte at BN = 256 instead of 64).
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 2) tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_small,
+                                                               const __grid_constant__ CUtensorMap map_big,
+                                                               const __grid_constant__ TcWgradParams p,
+                                                               float* __restrict__ dw) {
+    constexpr int PIX = 64, HB = BN / 2;
+    constexpr int A_BYTES = 128 * PIX * 2, B_BYTES = HB * PIX * 2, STAGE_BYTES = A_BYTES + B_BYTES, CHUNK = 64 * PIX * 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;                      // leader's
+    uint64_t* empty = bars + STAGES;            // each CTA's
+    uint64_t* tmem_full = bars + 2 * STAGES;    // each CTA's
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cl_rank();
+    const bool leader = rank == 0;
+    const int pairx = blockIdx.x >> 1;
+    const int kt = pairx % p.k_tiles, ct = pairx / p.k_tiles;          // k_tiles counts 256-channel tiles here
+    const int tap = blockIdx.y;
+    const int r = tap / p.S, s = tap % p.S;
+    const int pt0 = blockIdx.z * p.ptiles_per_split;
+    int pt1 = pt0 + p.ptiles_per_split;
+    if (pt1 > p.total_ptiles) pt1 = p.total_ptiles;
+    const int nkb = pt1 - pt0;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_small);
+        prefetch_tmap(&map_big);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) tmem_alloc_pair<BN>(tmem_slot);
+    tc_fence_before();
+    cl_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (nkb > 0) {                 // uniform over the pair
+        if (warp == 0) {
+            if (lane == 0) {
+                const uint32_t k_base = (uint32_t)(kt * 256 + rank * 128), c_base = (uint32_t)(ct * BN + rank * HB);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int st = kb % STAGES;
+                    mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
+                    int t = pt0 + kb;
+                    const int tw = t % p.tiles_w; t /= p.tiles_w;
+                    const int th = t % p.tiles_h;
+                    const int tn = t / p.tiles_h;
+                    const int q0 = tw * p.WT, p0 = th * p.HT, b0 = tn * p.NT;
+                    uint8_t* a_dst = smem + st * STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + A_BYTES;
+                    if (leader) mbar_expect_tx(&full[st], 2 * STAGE_BYTES);
+                    const uint32_t bar = cl_map(&full[st], 0);
+                    tma_load_4d_pair(a_dst, &map_small, bar, (int)k_base, q0, p0, b0);
+                    tma_load_4d_pair(a_dst + CHUNK, &map_small, bar, (int)k_base + 64, q0, p0, b0);
+#pragma unroll
+                    for (int j = 0; j < HB / 64; ++j)
+                        tma_load_4d_pair(b_dst + j * CHUNK, &map_big, bar, (int)c_base + j * 64, q0 * p.stride - p.pad + s,
+                                         p0 * p.stride - p.pad + r, b0);
+                }
+            }
+        } else if (warp == 1) {
+            if (leader && lane == 0) {
+                constexpr uint32_t idesc = idesc_bf16_f32_pair(BN) | (1u << 15) | (1u << 16);      // both operands MN-major
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int st = kb % STAGES;
+                    mbar_wait(&full[st], (kb / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + st * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < PIX / 16; ++k)
+                        umma_bf16_pair(tmem_base, mnmajor_sw128_desc(a_addr + k * 2048, CHUNK), mnmajor_sw128_desc(b_addr + k * 2048, CHUNK),
+                                       idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_pair(&empty[st]);
+                }
+                umma_commit_pair(tmem_full);
+            }
+        } else {
+            const int q = warp & 3;
+            const int k = kt * 256 + rank * 128 + q * 32 + lane;          // output row = channel of `small`
+            const int RS = p.R * p.S;
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                float* dst = dw + ((long long)k * p.C + ct * BN + c0) * RS + tap;
+                if (k < p.K) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (ct * BN + c0 + c < p.C) atomicAdd(dst + (long long)c * RS, __uint_as_float(v[c]));
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    cl_sync();               // the leader's MMAs read the peer's shared memory and write its tensor memory
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair<BN>(tmem_base);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_tc_wgrad_pair(const CUtensorMap& ms, const CUtensorMap& mb, const TcWgradParams& p, float* dw, int splits,
+                                cudaStream_t stream) {
+    constexpr int SMEM = STAGES * (128 * 64 * 2 + (BN / 2) * 64 * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return fail("tc_wgrad_pair_kernel smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * p.k_tiles * p.c_tiles), (unsigned)(p.R * p.S), (unsigned)splits);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_wgrad_pair_kernel<BN, STAGES>, ms, mb, p, dw);
+    if (e != cudaSuccess) return fail("tc_wgrad_pair_kernel launch: %s", cudaGetErrorString(e));
+    return launched("tc_wgrad_pair_kernel");
+}
+
 template <int BN, int STAGES>
 static int launch_tc_wgrad(const CUtensorMap& ms, const CUtensorMap& mb, const TcWgradParams& p, float* dw, int splits,
                            cudaStream_t stream) {
@@ -830,6 +968,15 @@ static int launch_tc_wgrad(const CUtensorMap& ms, const CUtensorMap& mb, const T
     dim3 grid((unsigned)(p.k_tiles * p.c_tiles), (unsigned)(p.R * p.S), (unsigned)splits);
     tc_wgrad_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(ms, mb, p, dw);
     return launched("tc_wgrad_kernel");
+}
+
+// The CTA-pair weight gradient is correct (tests/test_kernels_gpu.py runs it) but measured slower than two single CTAs
+// per SM on this workload (210 vs 189 us on the 512x256 decoder layer: three 32 KB stages per CTA do not cover the TMA
+// latency); it stays opt-in until it gets a deeper ring.
+static bool wgrad_pair_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VARSEP_ENABLE_WGRAD_PAIR"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
 }
 
 int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream) {
@@ -849,13 +996,21 @@ int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, fl
     if (g->Q % p.WT != 0 || g->P % p.HT != 0) return -1;
     p.tiles_w = g->Q / p.WT; p.tiles_h = g->P / p.HT; p.tiles_n = (int)cdiv(g->N, p.NT);
     p.total_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int BN = (g->C % 128 == 0 || g->C >= 512) ? 128 : 64;
-    p.k_tiles = (int)cdiv(g->K, 128); p.c_tiles = (int)cdiv(g->C, BN);
-    const long long base = (long long)p.k_tiles * p.c_tiles * g->R * g->S;
-    long long splits = cdiv(4LL * num_sms(), base);
-    if (splits > p.total_ptiles) splits = p.total_ptiles;
-    if (splits > 65535) splits = 65535;
-    if (splits < 1) splits = 1;
+    // wide layers: CTA pairs, 256 channels of `small` x 256 (or 128) channels of `big` per pair
+    const bool pair = g->K % 256 == 0 && g->C % 128 == 0 && !wgrad_pair_disabled();
+    const int BN = pair ? (g->C % 256 == 0 ? 256 : 128) : ((g->C % 128 == 0 || g->C >= 512) ? 128 : 64);
+    p.k_tiles = (int)cdiv(g->K, pair ? 256 : 128); p.c_tiles = (int)cdiv(g->C, BN);
+    const long long base = (long long)p.k_tiles * p.c_tiles * g->R * g->S * (pair ? 2 : 1);
+    // Split of the pixel range over CTAs: the grid runs in waves of (2 CTAs per SM) and every CTA ends with an epilogue
+    // of 128*BN fp32 reductions (worth about 8 pixel blocks), so pick the split count that minimises
+    //   waves(base * splits) * (blocks per split + 8)
+    // (e.g. 640 CTAs = 2.2 waves cost 3 waves; 576 cost 2).
+    const long long slots = 2LL * num_sms();
+    long long splits = 1, best = -1;
+    for (long long sp = 1; sp <= 64 && sp <= p.total_ptiles; ++sp) {
+        const long long cost = cdiv(base * sp, slots) * (cdiv(p.total_ptiles, sp) + 8);
+        if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
     p.ptiles_per_split = (int)cdiv(p.total_ptiles, splits);
     splits = cdiv(p.total_ptiles, p.ptiles_per_split);
     if (p.WT * g->stride > 256 || p.HT * g->stride > 256) return -1;
@@ -881,6 +1036,9 @@ int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, fl
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(big) failed: %d", (int)rc);
     }
+    if (pair)
+        return BN == 256 ? launch_tc_wgrad_pair<256, 3>(ms, mb, p, dw, (int)splits, stream)
+                         : launch_tc_wgrad_pair<128, 4>(ms, mb, p, dw, (int)splits, stream);
     return BN == 128 ? launch_tc_wgrad<128, 3>(ms, mb, p, dw, (int)splits, stream)
                      : launch_tc_wgrad<64, 4>(ms, mb, p, dw, (int)splits, stream);
 }

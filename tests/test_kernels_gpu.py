@@ -131,6 +131,10 @@ TC_CASES = [
     (8, 8, 8, 40, 200, 4, 2, 1, 1),
     (64, 1, 1, 1200, 1200, 1, 1, 0, 2),      # the 1200-wide linear layers of the WaveEq MLP configuration
     (6, 1, 1, 20480, 1200, 1, 1, 0, 2),      # its first encoder layer
+    # CTA-pair (cta_group::2) kernels: 256-column tiles, odd number of pixel tiles, partial last 256-channel tile
+    (4, 8, 8, 256, 512, 4, 2, 1, 2),
+    (6, 8, 8, 128, 256, 3, 1, 1, 3),
+    (10, 4, 4, 512, 256, 4, 2, 1, 1),
 ]
 
 
@@ -394,3 +398,30 @@ def test_latent_rollout_kernels(T, B, d, h, nb):
     close(d_gpu[0].cpu(), d_cpu[0], torch.float32, 'rollout bwd dcodes[0]', scale=float(d_cpu[0].abs().max()))
     close(dres_gpu.cpu(), dres_cpu, torch.float32, 'rollout bwd dres', scale=float(dres_cpu.abs().max()))
     close(dh_gpu.cpu(), dh_cpu, torch.float32, 'rollout bwd dhidden', outliers=1e-4, scale=float(dh_cpu.abs().max()))
+
+
+_PAIR_WGRAD_SNIPPET = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from spatiotemporal_variable_separation_b200 import _lib as L
+torch.manual_seed(3)
+for (N, H, W, C, K, R, st, pad) in [(4, 8, 8, 256, 512, 4, 2, 1), (6, 8, 8, 128, 256, 3, 1, 1)]:
+    P = (H + 2 * pad - R) // st + 1; Q = (W + 2 * pad - R) // st + 1
+    small = torch.randn(N, P, Q, K, device='cuda').bfloat16(); big = torch.randn(N, H, W, C, device='cuda').bfloat16()
+    d1 = torch.zeros(K, C, R, R, device='cuda'); d2 = torch.zeros_like(d1)
+    L.call('vs_conv_wgrad', L.Geom(1, N, H, W, C, P, Q, K, R, R, st, pad, 1, 0, 0), small, big, d1, L.stream())
+    L.call('vs_conv_wgrad', L.Geom(1, N, H, W, C, P, Q, K, R, R, st, pad, 1, 0, L.FLAG_FORCE_SIMT), small, big, d2, L.stream())
+    torch.cuda.synchronize()
+    err = float((d1 - d2).abs().max()) / float(d2.abs().max())
+    assert err < 2e-3, err
+print('pair wgrad ok')
+'''
+
+
+def test_wgrad_cta_pair_opt_in():
+    """The cta_group::2 weight-gradient kernel is opt-in (VARSEP_ENABLE_WGRAD_PAIR=1, read once per process)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VARSEP_ENABLE_WGRAD_PAIR='1')
+    r = subprocess.run([sys.executable, '-c', _PAIR_WGRAD_SNIPPET % root], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'pair wgrad ok' in r.stdout, r.stdout + r.stderr
