@@ -1002,13 +1002,13 @@ int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, fl
     p.k_tiles = (int)cdiv(g->K, pair ? 256 : 128); p.c_tiles = (int)cdiv(g->C, BN);
     const long long base = (long long)p.k_tiles * p.c_tiles * g->R * g->S * (pair ? 2 : 1);
     // Split of the pixel range over CTAs: the grid runs in waves of (2 CTAs per SM) and every CTA ends with an epilogue
-    // of 128*BN fp32 reductions (worth about 8 pixel blocks), so pick the split count that minimises
-    //   waves(base * splits) * (blocks per split + 8)
+    // of 128*BN fp32 reductions (worth about 24 pixel blocks, fitted to the measured launches), so pick the split count that minimises
+    //   waves(base * splits) * (blocks per split + 24)
     // (e.g. 640 CTAs = 2.2 waves cost 3 waves; 576 cost 2).
     const long long slots = 2LL * num_sms();
     long long splits = 1, best = -1;
     for (long long sp = 1; sp <= 64 && sp <= p.total_ptiles; ++sp) {
-        const long long cost = cdiv(base * sp, slots) * (cdiv(p.total_ptiles, sp) + 8);
+        const long long cost = cdiv(base * sp, slots) * (cdiv(p.total_ptiles, sp) + 24);
         if (best < 0 || cost < best) { best = cost; splits = sp; }
     }
     p.ptiles_per_split = (int)cdiv(p.total_ptiles, splits);
