@@ -355,8 +355,8 @@ def _shutdown(tr, world):
 
 
 def conv_roofline(tr, dev, draws, dtype):
-    """Roofline of the dominant kernel, tc_conv_kernel (tcgen05 tap GEMM: fprop and dgrad of every eligible conv
-    layer).  CUDA events on the launching stream around each vs_conv_forward call of two extra eager steps; only the
+    """Roofline of the dominant kernel, the tcgen05 tap GEMM (tc_conv_kernel and its CTA-pair variant
+    tc_conv_pair_kernel: fprop and dgrad of every eligible conv layer).  CUDA events on the launching stream around each vs_conv_forward call of two extra eager steps; only the
     calls that the library routes to the tensor-core kernel (vs_conv_forward_path == 1) are counted.  Algorithmic
     FLOPs per launch = 2*N*P*Q*K*C*R*S (for a stride-2 transposed convolution the parity decomposition multiplies no
     structurally-zero tap, so this is also the executed count)."""
@@ -392,7 +392,7 @@ def conv_roofline(tr, dev, draws, dtype):
     tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get('tc_conv_kernel', {}).get('dram_bytes_per_launch')
-    return {'bound': 'tensor', 'kernel': 'tc_conv_kernel (tcgen05 fprop + dgrad launches)',
+    return {'bound': 'tensor', 'kernel': 'tc_conv_kernel + tc_conv_pair_kernel (tcgen05 tap GEMM: every fprop / dgrad launch of the eligible conv layers)',
             'achieved': tot_flop / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0, 'unit': 'TFLOP/s',
             'launches': len(records) // 2, 'avg_launch_ms': tot_ms / max(len(records), 1),
             'flop_per_launch': tot_flop / max(len(records), 1), 'traffic': traffic,

@@ -8,27 +8,44 @@
 
 namespace vs {
 
-// one thread per channel; sequential EMA over groups reproduces the order of the reference calls
-__global__ void bn_finalize_kernel(const double* __restrict__ stats, int G, int C, double count, float eps,
-                                   float momentum, float* __restrict__ mean, float* __restrict__ invstd,
-                                   float* __restrict__ rmean, float* __restrict__ rvar, long long* nbt) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && nbt != nullptr) *nbt += G;
-    if (c >= C) return;
-    float rm = rmean ? rmean[c] : 0.f, rv = rvar ? rvar[c] : 0.f;
-    for (int g = 0; g < G; ++g) {
-        const double s1 = stats[((long long)g * C + c) * 2], s2 = stats[((long long)g * C + c) * 2 + 1];
-        const double mu = s1 / count;
-        double var = s2 / count - mu * mu;          // biased variance, fp64: no cancellation issue at these sizes
-        if (var < 0.0) var = 0.0;
-        mean[g * C + c] = (float)mu;
-        invstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
-        const float unbiased = (float)(count > 1.0 ? var * count / (count - 1.0) : var);
-        rm = (1.f - momentum) * rm + momentum * (float)mu;
-        rv = (1.f - momentum) * rv + momentum * unbiased;
+// block = 32 channels x up to 32 groups: thread (c, g) turns the fp64 sums of its (group, channel) into mean / invstd
+// (the fp64 divisions and the square root run in parallel over the groups); the running-statistics EMA is then applied
+// group by group, in the order of the reference's calls, by the g == 0 thread of each channel
+constexpr int FIN_C = 32, FIN_G = 32;
+__global__ void __launch_bounds__(FIN_C * FIN_G) bn_finalize_kernel(const double* __restrict__ stats, int G, int C, double count, float eps,
+                                                                    float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                                                    float* __restrict__ rmean, float* __restrict__ rvar, long long* nbt) {
+    __shared__ float s_mu[FIN_G][FIN_C], s_ub[FIN_G][FIN_C];
+    const int cl = threadIdx.x, gl = threadIdx.y;
+    const int c = blockIdx.x * FIN_C + cl;
+    if (blockIdx.x == 0 && cl == 0 && gl == 0 && nbt != nullptr) *nbt += G;
+    float rm = 0.f, rv = 0.f;
+    if (gl == 0 && c < C) { rm = rmean ? rmean[c] : 0.f; rv = rvar ? rvar[c] : 0.f; }
+    for (int g0 = 0; g0 < G; g0 += blockDim.y) {
+        const int g = g0 + gl;
+        if (g < G && c < C) {
+            const double s1 = stats[((long long)g * C + c) * 2], s2 = stats[((long long)g * C + c) * 2 + 1];
+            const double mu = s1 / count;
+            double var = s2 / count - mu * mu;          // biased variance, fp64: no cancellation issue at these sizes
+            if (var < 0.0) var = 0.0;
+            mean[g * C + c] = (float)mu;
+            invstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+            s_mu[gl][cl] = (float)mu;
+            s_ub[gl][cl] = (float)(count > 1.0 ? var * count / (count - 1.0) : var);
+        }
+        __syncthreads();
+        if (gl == 0 && c < C) {
+            for (int k = 0; k < (int)blockDim.y && g0 + k < G; ++k) {
+                rm = (1.f - momentum) * rm + momentum * s_mu[k][cl];
+                rv = (1.f - momentum) * rv + momentum * s_ub[k][cl];
+            }
+        }
+        __syncthreads();
     }
-    if (rmean) rmean[c] = rm;
-    if (rvar) rvar[c] = rv;
+    if (gl == 0 && c < C) {
+        if (rmean) rmean[c] = rm;
+        if (rvar) rvar[c] = rv;
+    }
 }
 
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar, int C, float eps,
@@ -484,7 +501,9 @@ extern "C" int vs_bn_finalize(const double* stats, int32_t G, int32_t C, int64_t
                               float* mean, float* invstd, float* running_mean, float* running_var,
                               int64_t* num_batches_tracked, void* stream) {
     VS_REQUIRE(G >= 1 && C >= 1 && count >= 1, "bn_finalize: bad sizes");
-    bn_finalize_kernel<<<(int)cdiv(C, 128), 128, 0, as_stream(stream)>>>(
+    int gy = 1;
+    while (gy < G && gy < FIN_G) gy <<= 1;
+    bn_finalize_kernel<<<(int)cdiv(C, FIN_C), dim3(FIN_C, gy), 0, as_stream(stream)>>>(
         stats, G, C, (double)count, eps, momentum, mean, invstd, running_mean, running_var,
         reinterpret_cast<long long*>(num_batches_tracked));
     return launched("bn_finalize_kernel");

@@ -115,6 +115,35 @@ def repack_all():
         w.__dict__['_vs_pack'][key] = ((w._version, w.data_ptr(), _pack_epoch), out)
 
 
+# ------------------------------------------------------------------------------------------------
+# zero-initialised fp64 scratch (BatchNorm statistics / backward sums / loss accumulators).  One training step needs
+# ~25 small zeroed buffers; ``begin_step`` clears one arena with a single memset and the operators take consecutive
+# slices of it.  A slice is never handed out twice between two ``begin_step`` calls, so code that runs outside the
+# training step (or after the arena is exhausted) simply falls back to ``torch.zeros``.
+# ------------------------------------------------------------------------------------------------
+_zero_arena = {'buf': None, 'off': 0}
+_ZERO_ARENA_DOUBLES = 1 << 19          # 4 MB
+
+
+def begin_step(device):
+    """Called once at the start of a training step (train.step_losses)."""
+    a = _zero_arena
+    if a['buf'] is None or a['buf'].device != torch.device(device):
+        a['buf'] = torch.empty(_ZERO_ARENA_DOUBLES, device=device, dtype=torch.float64)
+    a['buf'].zero_()
+    a['off'] = 0
+
+
+def zeros_f64(n, device):
+    a = _zero_arena
+    buf = a['buf']
+    if buf is not None and buf.device == torch.device(device) and a['off'] + n <= buf.numel():
+        out = buf[a['off']:a['off'] + n]
+        a['off'] += (n + 1) & ~1          # keep slices 16-byte aligned
+        return out
+    return torch.zeros(n, device=device, dtype=torch.float64)
+
+
 ConvCfg = namedtuple('ConvCfg', 'kind K C R S stride pad act groups training has_bn eps momentum flags')
 
 
@@ -166,7 +195,7 @@ class ConvBlockFn(torch.autograd.Function):
             mean = torch.empty(G * OC, device=x.device, dtype=torch.float32)
             invstd = torch.empty_like(mean)
             if cfg.training:
-                stats = torch.zeros(G * OC * 2, device=x.device, dtype=torch.float64)
+                stats = zeros_f64(G * OC * 2, x.device)
                 g = _geom(cfg, dt, N, H, W, P, Q, 0, G)
                 L.call('vs_conv_forward', g, mode, ptr(x), ptr(wp), ptr(bias), ptr(y), ptr(stats), L.stream())
                 L.call('vs_bn_finalize', ptr(stats), G, OC, rows // G, cfg.eps, cfg.momentum, ptr(mean), ptr(invstd),
@@ -201,7 +230,7 @@ class ConvBlockFn(torch.autograd.Function):
         if cfg.has_bn:
             x, weight, y, mean, invstd, gamma, beta = ctx.saved_tensors
             G = ctx.G
-            sums = torch.zeros(G * OC * 2, device=dout.device, dtype=torch.float64)
+            sums = zeros_f64(G * OC * 2, dout.device)
             if cfg.training:
                 L.call('vs_bn_act_backward_reduce', ptr(dout), ptr(y), L.dtype_code(y), rows, OC, G, ptr(mean),
                      ptr(invstd), ptr(gamma), ptr(beta), act, ptr(sums), L.stream())

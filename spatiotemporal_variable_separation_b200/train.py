@@ -63,6 +63,8 @@ def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, l
     B, n_frames = full_data.shape[0], full_data.shape[1]
     if t_random is None:
         t_random = draw_t_random(nt_cond, n_frames, offset)
+    if full_data.is_cuda:
+        ops.begin_step(full_data.device)          # one memset for all the small zeroed buffers of this step
     # ---- encoders: two calls each, batched as two BatchNorm groups.  Es and Et are independent until the decoder, and
     # their launches (and the 64-CTA latent rollout that follows Et) each fill only part of the GPU, so the content
     # encoder runs on a side stream next to the dynamic encoder + rollout; autograd replays the same split in backward.
