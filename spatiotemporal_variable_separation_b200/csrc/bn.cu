@@ -547,7 +547,7 @@ extern "C" int vs_bn_act_backward_reduce(const void* dout, const void* y, int32_
     const long long rpg = rows / G;
     VS_DISPATCH_DTYPE(dtype, T, {
         ColPlan pl;
-        if (col_plan<T>(rows, C, G, pl, 8)) {
+        if (col_plan<T>(rows, C, G, pl, 9)) {      // 3 resident blocks per SM (80 registers, 64 KB): 9 per SM = three full waves
             VS_DISPATCH_ACT(act, A, {
                 if (int rc = reduce_smem_attr(bn_reduce_col_kernel<T, 0, A>)) return rc;
                 bn_reduce_col_kernel<T, 0, A><<<(unsigned)(G * pl.chunks), 256, REDUCE_SMEM, as_stream(stream)>>>((const T*)dout, (const T*)y, C, pl, mean, invstd, gamma, beta, act, sums);
