@@ -55,13 +55,19 @@ struct TcOutMaps { CUtensorMap m[TC_MAX_OUT_MAPS]; };
 // two TMEM accumulator stages let tile i+1's MMAs overlap tile i's epilogue.
 // TS: the epilogue stages the bf16 tile in shared memory and writes it with one TMA store (coalesced, clipped at the
 // tensor edges by the TMA unit) instead of 16-byte stores from every lane to 32 different lines.
-template <int BN, int STAGES, bool TS>
+// SS (with TS): the BatchNorm sums are taken from the staged tile -- thread (column pair, 16-row group) reads its 16
+// bf16x2 words (one 128-byte row per warp instruction: conflict-free) and keeps four fp32 running sums in registers
+// across the tiles of a BatchNorm group -- instead of two 31-shuffle transposes of the accumulator per warp and tile
+// (ncu: the epilogue warps executed ~770 instructions per tile at 8.5 cycles each and were the critical path of the
+// 128->64 decoder layer).  The statistics are then those of the bf16 values that BatchNorm will normalise.
+template <int BN, int STAGES, bool TS, bool SS>
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_constant__ CUtensorMap map_a,
                                                          const __grid_constant__ CUtensorMap map_b,
                                                          const __grid_constant__ TcOutMaps omaps,
                                                          const __grid_constant__ TcParams p,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                          double* __restrict__ stats) {
+    static_assert(!SS || TS, "statistics from the staged tile need the staged epilogue");
     using S = TcSmem<BN, STAGES, TS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -165,13 +171,36 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
         int lt = 0;
         int stat_key = -1;
         double stat_acc = 0.0;
+        float ss[4] = {0.f, 0.f, 0.f, 0.f};          // SS: sum / sum of squares of this thread's two columns
+        // SS: flush the register sums of the finished BatchNorm group through the shared-memory column table
+        auto ss_flush = [&](int key) {
+            const int t = threadIdx.x - 64, cp = t & 31;
+            atomicAdd(&sstat[(2 * cp) * 2], ss[0]);     atomicAdd(&sstat[(2 * cp) * 2 + 1], ss[1]);
+            atomicAdd(&sstat[(2 * cp + 1) * 2], ss[2]); atomicAdd(&sstat[(2 * cp + 1) * 2 + 1], ss[3]);
+            ss[0] = ss[1] = ss[2] = ss[3] = 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            if (t < 2 * BN) {
+                const int col = (key % p.n_tiles) * BN + (t >> 1);
+                if (col < p.OC) atomicAdd(&stats[((long long)(key / p.n_tiles) * p.OC + col) * 2 + (t & 1)], (double)sstat[t]);
+                sstat[t] = 0.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        };
         for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
             VS_TC_DECODE(idx)
             const int acc = lt & 1;
             const int i = i0 + h, j = j0 + w, nn = b0 + n;
             const bool ok = i < p.OHc && j < p.OWc && nn < p.N;
+            const bool full_tile = i0 + p.HT <= p.OHc && j0 + p.WT <= p.OWc && b0 + p.NT <= p.N;
             const long long pix = ((long long)nn * p.OH + (long long)i * p.ost + p.ca[cls]) * p.OW + (long long)j * p.ost + p.cb[cls];
             __nv_bfloat16* dst = out + pix * p.OC + n0;
+            if (SS && stats != nullptr) {
+                const int key = (b0 / p.n_per_group) * p.n_tiles + n0 / BN;      // a tile never straddles groups (host check)
+                if (key != stat_key) {                                           // uniform over the epilogue warps
+                    if (stat_key >= 0) ss_flush(stat_key);
+                    stat_key = key;
+                }
+            }
             mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -185,6 +214,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
 #pragma unroll
                 for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
                 if (TS) {
+                    if (SS && !full_tile && !ok) {          // rows beyond the tensor edge: clipped by the TMA store, must not count
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) xs[c] = 0.f;
+                    }
                     stage_row32(obuf + (lt & 1) * (TC_BM * 128), m, c0, xs, p.act);
                 } else if (p.partial || n0 + BN > p.OC) {
                     // tail tile in OC, or rows not 16-byte aligned: predicated scalar stores
@@ -207,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                         *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
-                if (stats != nullptr) {
+                if (!SS && stats != nullptr) {
                     // BatchNorm batch statistics of the fp32 accumulator (+bias), fused: 32 rows x 32 columns per warp
                     // (columns past OC hold exact zeros: zero-filled weight rows, no bias)
                     float wk[32];
@@ -236,7 +269,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                     tma_store_commit();
                 }
             }
-            if (stats != nullptr) {
+            if (SS && stats != nullptr) {
+                // columns 2cp, 2cp+1 of rows 16rg .. 16rg+15 of the tile staged above (complete since the barrier); the
+                // buffer is refilled two tiles from now, behind the next tile's barrier
+                const int t = threadIdx.x - 64, cp = t & 31, rg = t >> 5;
+                const uint8_t* tile = obuf + (lt & 1) * (TC_BM * 128) + (cp & 3) * 4;
+#pragma unroll
+                for (int rr = 0; rr < TC_BM / TC_EPI_WARPS; ++rr) {
+                    const int row = rg * (TC_BM / TC_EPI_WARPS) + rr;
+                    const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + row * 128 + (((cp >> 2) ^ (row & 7)) << 4));
+                    const float a = __uint_as_float(v << 16), b = __uint_as_float(v & 0xffff0000u);
+                    ss[0] += a; ss[1] = fmaf(a, a, ss[1]);
+                    ss[2] += b; ss[3] = fmaf(b, b, ss[3]);
+                }
+            }
+            if (!SS && stats != nullptr) {
                 // the epilogue warps have added their 32-row partials of this tile; thread i keeps the running fp64 sum of
                 // entry i (column n0 + i/2, sum or sum of squares) and flushes it when the (group, channel tile) changes
                 if (!TS) asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
@@ -256,7 +303,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
             }
         }
-        if (stats != nullptr && stat_key >= 0) {
+        if (SS) {
+            if (stats != nullptr && stat_key >= 0) ss_flush(stat_key);
+        } else if (stats != nullptr && stat_key >= 0) {
             const int t = threadIdx.x - 64;
             const int col = (stat_key % p.n_tiles) * BN + (t >> 1);
             if (t < 2 * BN && col < p.OC) atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (t & 1)], stat_acc);
@@ -489,13 +538,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------ host
-template <int BN, int STAGES, bool TS>
+template <int BN, int STAGES, bool TS, bool SS = false>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMaps& om, const TcParams& p, const float* bias,
                      void* out, int classes, double* stats, cudaStream_t stream) {
     using S = TcSmem<BN, STAGES, TS>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES, TS, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return fail("tc_conv_kernel smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
@@ -505,7 +554,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMa
     q.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * q.n_tiles * classes;
     const int resident = 2 * num_sms();                     // __launch_bounds__(TC_THREADS, 2)
     const int grid = q.total_tiles < resident ? q.total_tiles : resident;      // every CTA gets at least one work item
-    tc_conv_kernel<BN, STAGES, TS><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, om, q, bias, (__nv_bfloat16*)out, stats);
+    tc_conv_kernel<BN, STAGES, TS, SS><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, om, q, bias, (__nv_bfloat16*)out, stats);
     return launched("tc_conv_kernel");
 }
 
@@ -545,6 +594,12 @@ static int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb, const Tc
     cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_pair_kernel<BN, STAGES>, ma, mb, q, bias, (__nv_bfloat16*)out, stats);
     if (e != cudaSuccess) return fail("tc_conv_pair_kernel launch: %s", cudaGetErrorString(e));
     return launched("tc_conv_pair_kernel");
+}
+
+static bool staged_stats_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VARSEP_DISABLE_STAGED_STATS"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
 }
 
 static bool staged_epilogue_disabled() {
@@ -680,6 +735,8 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     int rc = pair ? (PBN == 256 ? launch_tc_pair<256, 6>(ma, mb, p, bias, out, classes, stp, stream)
                                 : launch_tc_pair<128, 8>(ma, mb, p, bias, out, classes, stp, stream))
              : BN == 128 ? launch_tc<128, 3, false>(ma, mb, om, p, bias, out, classes, stp, stream)
+             : staged && stp != nullptr && p.act == VS_ACT_NONE && !staged_stats_disabled()
+                       ? launch_tc<64, 3, true, true>(ma, mb, om, p, bias, out, classes, stp, stream)
              : staged  ? launch_tc<64, 3, true>(ma, mb, om, p, bias, out, classes, stp, stream)
                        : launch_tc<64, 4, false>(ma, mb, om, p, bias, out, classes, stp, stream);
     if (rc) return rc;
@@ -806,6 +863,138 @@ __global__ void __launch_bounds__(192, 2) tc_wgrad_kernel(const __grid_constant_
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                     if (ct * BN + c0 + c < p.C) atomicAdd(dst + (long long)c * RS, __uint_as_float(v[c]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+// Several taps per CTA: the box of `small` is staged ONCE per 64-pixel block and multiplied with the TAPS shifted boxes
+// of CB channels of `big`, which sit back to back in shared memory and so form ONE MN-major B operand of N = TAPS * CB
+// = 256 columns (accumulator column = tap * CB + channel).  Per block a CTA stages 16 + 32 KB for 128 x 256 x 64 MACs:
+// 87 FLOP per staged byte instead of 44 (CB = 64) / 64 (CB = 128) -- the one-tap kernel sits on the ~64 B/clk/SM
+// L2 -> shared-memory fill (measured 62 B/clk/SM, tensor pipe 72 % busy with N = 64 instructions).  The taps of a CTA
+// are consecutive in s, so for one (k, c) their gradients are contiguous in the torch layout: the epilogue issues one
+// vector reduction (red.global.add.v4/v2.f32) per (k, c) instead of TAPS scalar ones.
+template <int CB, int TAPS, int STAGES>
+__global__ void __launch_bounds__(192, 2) tc_wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_small,
+                                                               const __grid_constant__ CUtensorMap map_big,
+                                                               const __grid_constant__ TcWgradParams p,
+                                                               float* __restrict__ dw, int vec_ok) {
+    constexpr int PIX = 64, BN = CB * TAPS;
+    constexpr int A_BYTES = 128 * PIX * 2, B_BYTES = BN * PIX * 2, STAGE_BYTES = A_BYTES + B_BYTES, CHUNK = 64 * PIX * 2;
+    static_assert(BN == 256 && (TAPS == 2 || TAPS == 4), "one 256-column accumulator");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kt = blockIdx.x % p.k_tiles, ct = blockIdx.x / p.k_tiles;
+    const int tap0 = blockIdx.y * TAPS;                  // TAPS consecutive taps (same r: S % TAPS == 0, host check)
+    const int r = tap0 / p.S, s0 = tap0 % p.S;
+    const int pt0 = blockIdx.z * p.ptiles_per_split;
+    int pt1 = pt0 + p.ptiles_per_split;
+    if (pt1 > p.total_ptiles) pt1 = p.total_ptiles;
+    const int nkb = pt1 - pt0;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_small);
+        prefetch_tmap(&map_big);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (nkb <= 0) {          // uniform: nothing to reduce for this split
+        __syncthreads();
+        if (warp == 1) tmem_dealloc<BN>(tmem_base);
+        return;
+    }
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                int t = pt0 + kb;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h;
+                const int tn = t / p.tiles_h;
+                const int q0 = tw * p.WT, p0 = th * p.HT, b0 = tn * p.NT;
+                uint8_t* a_dst = smem + st * STAGE_BYTES;
+                uint8_t* b_dst = a_dst + A_BYTES;
+                mbar_expect_tx(&full[st], STAGE_BYTES);
+                tma_load_4d(a_dst, &map_small, &full[st], kt * 128, q0, p0, b0);
+                tma_load_4d(a_dst + CHUNK, &map_small, &full[st], kt * 128 + 64, q0, p0, b0);
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) {      // chunk j = tap j / (CB/64), 64-channel slice j % (CB/64)
+                    const int tj = j / (CB / 64), cj = j % (CB / 64);
+                    tma_load_4d(b_dst + j * CHUNK, &map_big, &full[st], ct * CB + cj * 64, q0 * p.stride - p.pad + s0 + tj,
+                                p0 * p.stride - p.pad + r, b0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16_f32(BN) | (1u << 15) | (1u << 16);      // both operands MN-major
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + st * STAGE_BYTES);
+                const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < PIX / 16; ++k)
+                    umma_bf16(tmem_base, mnmajor_sw128_desc(a_addr + k * 2048, CHUNK), mnmajor_sw128_desc(b_addr + k * 2048, CHUNK),
+                              idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_commit(&empty[st]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int k = kt * 128 + q * 32 + lane;          // output row = channel of `small`
+        const int RS = p.R * p.S;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < CB; c0 += 8) {
+            uint32_t v[TAPS][8];
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * CB + c0), v[j]);
+            tmem_ld_wait();
+            if (k < p.K) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = ct * CB + c0 + e;
+                    if (c >= p.C) break;
+                    float* dst = dw + ((long long)k * p.C + c) * RS + tap0;
+                    if (vec_ok) {
+                        if (TAPS == 4)
+                            red_add_v4(dst, __uint_as_float(v[0][e]), __uint_as_float(v[1][e]), __uint_as_float(v[2 % TAPS][e]),
+                                       __uint_as_float(v[3 % TAPS][e]));
+                        else
+                            red_add_v2(dst, __uint_as_float(v[0][e]), __uint_as_float(v[1][e]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TAPS; ++j) atomicAdd(dst + j, __uint_as_float(v[j][e]));
+                    }
+                }
             }
         }
         tc_fence_before();
@@ -970,6 +1159,29 @@ static int launch_tc_wgrad(const CUtensorMap& ms, const CUtensorMap& mb, const T
     return launched("tc_wgrad_kernel");
 }
 
+template <int CB, int TAPS, int STAGES>
+static int launch_tc_wgrad_taps(const CUtensorMap& ms, const CUtensorMap& mb, const TcWgradParams& p, float* dw, int splits,
+                                cudaStream_t stream) {
+    constexpr int SMEM = STAGES * (128 * 64 * 2 + CB * TAPS * 64 * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_taps_kernel<CB, TAPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return fail("tc_wgrad_taps_kernel smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    // vector reductions need the TAPS gradients of one (k, c) aligned to their total size
+    const int vec_ok = ((p.R * p.S) % TAPS == 0 && (reinterpret_cast<uintptr_t>(dw) % (TAPS * 4)) == 0) ? 1 : 0;
+    dim3 grid((unsigned)(p.k_tiles * p.c_tiles), (unsigned)(p.R * p.S / TAPS), (unsigned)splits);
+    tc_wgrad_taps_kernel<CB, TAPS, STAGES><<<grid, 192, SMEM, stream>>>(ms, mb, p, dw, vec_ok);
+    return launched("tc_wgrad_taps_kernel");
+}
+
+static bool wgrad_taps_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VARSEP_DISABLE_WGRAD_TAPS"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 // The CTA-pair weight gradient is correct (tests/test_kernels_gpu.py runs it) but measured slower than two single CTAs
 // per SM on this workload (210 vs 189 us on the 512x256 decoder layer: three 32 KB stages per CTA do not cover the TMA
 // latency); it stays opt-in until it gets a deeper ring.
@@ -999,16 +1211,21 @@ int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, fl
     // wide layers: CTA pairs, 256 channels of `small` x 256 (or 128) channels of `big` per pair
     const bool pair = g->K % 256 == 0 && g->C % 128 == 0 && !wgrad_pair_disabled();
     const int BN = pair ? (g->C % 256 == 0 ? 256 : 128) : ((g->C % 128 == 0 || g->C >= 512) ? 128 : 64);
+    // several taps per CTA (one 256-column accumulator = TAPS x BN channels) when the filter rows split evenly
+    const int TAPS = pair || wgrad_taps_disabled() ? 1 : 256 / BN;
+    const bool taps = TAPS > 1 && g->S % TAPS == 0;
     p.k_tiles = (int)cdiv(g->K, pair ? 256 : 128); p.c_tiles = (int)cdiv(g->C, BN);
-    const long long base = (long long)p.k_tiles * p.c_tiles * g->R * g->S * (pair ? 2 : 1);
+    const long long base = (long long)p.k_tiles * p.c_tiles * (g->R * g->S / (taps ? TAPS : 1)) * (pair ? 2 : 1);
     // Split of the pixel range over CTAs: the grid runs in waves of (2 CTAs per SM) and every CTA ends with an epilogue
     // of 128*BN fp32 reductions (worth about 24 pixel blocks, fitted to the measured launches), so pick the split count that minimises
     //   waves(base * splits) * (blocks per split + 24)
     // (e.g. 640 CTAs = 2.2 waves cost 3 waves; 576 cost 2).
     const long long slots = 2LL * num_sms();
     long long splits = 1, best = -1;
-    for (long long sp = 1; sp <= 64 && sp <= p.total_ptiles; ++sp) {
-        const long long cost = cdiv(base * sp, slots) * (cdiv(p.total_ptiles, sp) + 24);
+    // (with TAPS taps per CTA a pixel block carries TAPS times the MMA work and the epilogue TAPS times the data)
+    const long long epi = taps ? 12 : 24;
+    for (long long sp = 1; sp <= (taps ? 128 : 64) && sp <= p.total_ptiles; ++sp) {
+        const long long cost = cdiv(base * sp, slots) * (cdiv(p.total_ptiles, sp) + epi);
         if (best < 0 || cost < best) { best = cost; splits = sp; }
     }
     p.ptiles_per_split = (int)cdiv(p.total_ptiles, splits);
@@ -1036,6 +1253,9 @@ int conv_wgrad_tc(const vs_conv_geom* g, const void* small_, const void* big, fl
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(big) failed: %d", (int)rc);
     }
+    if (taps)
+        return BN == 128 ? launch_tc_wgrad_taps<128, 2, 2>(ms, mb, p, dw, (int)splits, stream)
+                         : launch_tc_wgrad_taps<64, 4, 2>(ms, mb, p, dw, (int)splits, stream);
     if (pair)
         return BN == 256 ? launch_tc_wgrad_pair<256, 3>(ms, mb, p, dw, (int)splits, stream)
                          : launch_tc_wgrad_pair<128, 4>(ms, mb, p, dw, (int)splits, stream);

@@ -17,6 +17,12 @@ LeakyReLU layer whatever N is - which is also why the reference's own fp32 gradi
 from its fp64 ones (SURVEY D6).  Module-level checks against the fp64 oracle therefore use 1e-2;
 bit-level exactness is pinned per block (test_conv_block_exact) and per kernel (test_kernels_gpu.py)."""
 KINK = 5e-2
+# goldens whose measured gradient error stays below the north-star 1e-4 on every tensor (no unit of these tiny batches
+# sits within rounding distance of a kink): checked WITHOUT the allowance.  The VGG / ResNet18 / SST goldens keep it
+# (max-pool arg-max and LeakyReLU flips; the reference's own fp32-vs-fp64 error is 1e-3 class there), and so does
+# mnist-small-mul (clean under the emulator, one flipped unit on the GPU path: 8.5e-3 on Et.conv.0;
+# profiles/r01_grad_parity_gpu.json holds the measured distributions).
+STRICT = ('mnist-small', 'mnist-small-no_s', 'mnist-small-skipco', 'wave-small')
 import numpy as np
 import pytest
 import torch
@@ -47,7 +53,7 @@ def run_step(net, cfg, t_random, device='cpu'):
                                 cfg['architecture'] == 'encoderSST', t_random)
 
 
-def check_against_golden(g, out, grads, rtol_loss=2e-5, rtol_grad=2e-4):
+def check_against_golden(g, out, grads, rtol_loss=2e-5, rtol_grad=2e-4, kink=KINK):
     ours = np.array([float(out[k].detach()) for k in ('ae', 's', 'pred', 't', 'total')])
     np.testing.assert_allclose(ours, g['loss32'], rtol=rtol_loss, atol=1e-7)
     assert list(out['forecasts'].shape) == list(g['forecast_shape'])
@@ -66,7 +72,7 @@ def check_against_golden(g, out, grads, rtol_loss=2e-5, rtol_grad=2e-4):
         assert gr is not None, n
         s = summarize(str(n), gr)
         err_new, err_ref = np.abs(s - ref64).max(), np.abs(ref32 - ref64).max()
-        tol = max(rtol_grad * abs(ref64[0]), 2 * err_ref) + KINK * abs(ref64[0]) + 1e-6 * gmax
+        tol = max(rtol_grad * abs(ref64[0]), 2 * err_ref) + kink * abs(ref64[0]) + 1e-6 * gmax
         worst = max(worst, err_new / max(tol, 1e-300))
         assert err_new <= tol, (str(n), s, ref32, ref64)
     return worst
@@ -83,7 +89,10 @@ def test_step_matches_reference_golden(name):
         out = run_step(net, cfg, t_random)
         out['total'].backward()
         grads = {f'{part}.{k}': p.grad for part in harness.PARTS for k, p in getattr(net, part).named_parameters()}
-        check_against_golden(g, out, grads)
+        if name in STRICT:
+            check_against_golden(g, out, grads, rtol_grad=1e-4, kink=0.0)
+        else:
+            check_against_golden(g, out, grads)
 
 
 @pytest.mark.parametrize('name', ['mnist-small', 'wave-small', 'mnist-small-skipco'])

@@ -135,6 +135,8 @@ TC_CASES = [
     (4, 8, 8, 256, 512, 4, 2, 1, 2),
     (6, 8, 8, 128, 256, 3, 1, 1, 3),
     (10, 4, 4, 512, 256, 4, 2, 1, 1),
+    # partial pixel tiles (12 of 16 columns, 4 of 8 rows) with BatchNorm statistics fused in the staged epilogue
+    (6, 12, 12, 64, 64, 3, 1, 1, 1),
 ]
 
 
