@@ -283,27 +283,68 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 
 // all packed weight copies of a model in ONE launch: table rows = {src, dst, K, C, RS, swap, dtype, first_block}
 struct PackEntry { const float* src; void* dst; int K, C, RS, swap, dtype, first_block; };
-__global__ void pack_multi_kernel(const PackEntry* __restrict__ table, int n) {
-    // binary search of the entry that owns this block
-    int lo = 0, hi = n - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (table[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    const PackEntry e = table[lo];
-    const long long total = (long long)e.K * e.C * e.RS;
-    const long long base = (long long)(blockIdx.x - e.first_block) * 1024;
-    for (int t = threadIdx.x; t < 1024; t += blockDim.x) {
-        const long long i = base + t;
-        if (i >= total) return;
-        const int B = e.swap ? e.K : e.C;
-        const int b = (int)(i % B);
-        const int tap = (int)((i / B) % e.RS);
-        const int a = (int)(i / ((long long)B * e.RS));
-        const int k = e.swap ? b : a, c = e.swap ? a : b;
-        const float v = e.src[((long long)k * e.C + c) * e.RS + tap];
-        if (e.dtype == VS_F32) reinterpret_cast<float*>(e.dst)[i] = v;
-        else reinterpret_cast<__nv_bfloat16*>(e.dst)[i] = __float2bfloat16_rn(v);
+constexpr int PACK_BT = 64, PACK_MAX_RS = 25;
+// Persistent CTAs walk the table's virtual blocks (block vb belongs to the entry with the largest first_block <= vb);
+// the table sits in shared memory, so the binary search costs a few shared-memory reads instead of ~6 dependent
+// global loads per 1024 elements (which, not bandwidth, bounded the one-block-per-1024-elements form at 0.6 TB/s).
+__global__ void pack_multi_kernel(const PackEntry* __restrict__ gtable, int n, int total_blocks) {
+    extern __shared__ __align__(16) unsigned char pack_smem[];
+    PackEntry* table = reinterpret_cast<PackEntry*>(pack_smem);
+    for (int i = threadIdx.x; i < n * (int)(sizeof(PackEntry) / 8); i += blockDim.x)
+        reinterpret_cast<unsigned long long*>(table)[i] = reinterpret_cast<const unsigned long long*>(gtable)[i];
+    __shared__ float tile[PACK_BT * (PACK_MAX_RS + 1)];
+    __syncthreads();
+    for (int vb = blockIdx.x; vb < total_blocks; vb += gridDim.x) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[mid].first_block <= vb) lo = mid; else hi = mid - 1;
+        }
+        const PackEntry e = table[lo];
+        const long long total = (long long)e.K * e.C * e.RS;
+        if (e.RS >= 4 && e.RS <= PACK_MAX_RS) {
+            // Filters: for one output row a (= k, or c when swapped) the copy is a [b][tap] -> [tap][b] transpose of rows of
+            // RS contiguous floats (row pitch RS, or C*RS when swapped).  The entry's blocks walk tiles of (a, 64 values of
+            // b): coalesced reads of whole tap rows into a padded shared-memory tile, coalesced writes of b-contiguous runs.
+            const int nblk = (lo + 1 < n ? table[lo + 1].first_block : total_blocks) - e.first_block;
+            const int A = e.swap ? e.C : e.K, B = e.swap ? e.K : e.C, RS = e.RS;
+            const int pitch = RS | 1;
+            const int tiles_b = (B + PACK_BT - 1) / PACK_BT, ntiles = A * tiles_b;
+            const long long row_pitch = e.swap ? (long long)e.C * RS : RS;
+            for (int tl = vb - e.first_block; tl < ntiles; tl += nblk) {
+                const int a = tl / tiles_b, b0 = (tl - a * tiles_b) * PACK_BT;
+                const int nb = B - b0 < PACK_BT ? B - b0 : PACK_BT;
+                const float* src = e.src + (e.swap ? ((long long)b0 * e.C + a) * RS : ((long long)a * e.C + b0) * RS);
+                for (int idx = threadIdx.x; idx < nb * RS; idx += blockDim.x) {
+                    const int row = idx / RS, tap = idx - row * RS;
+                    tile[row * pitch + tap] = src[row * row_pitch + tap];
+                }
+                __syncthreads();
+                const long long obase = (long long)a * RS * B + b0;
+                for (int idx = threadIdx.x; idx < nb * RS; idx += blockDim.x) {
+                    const int tap = idx / nb, bb = idx - tap * nb;
+                    const float v = tile[bb * pitch + tap];
+                    const long long o = obase + (long long)tap * B + bb;
+                    if (e.dtype == VS_F32) reinterpret_cast<float*>(e.dst)[o] = v;
+                    else reinterpret_cast<__nv_bfloat16*>(e.dst)[o] = __float2bfloat16_rn(v);
+                }
+                __syncthreads();
+            }
+            continue;
+        }
+        const long long base = (long long)(vb - e.first_block) * 1024;
+        for (int t = threadIdx.x; t < 1024; t += blockDim.x) {
+            const long long i = base + t;
+            if (i >= total) break;
+            const int B = e.swap ? e.K : e.C;
+            const int bb = (int)(i % B);
+            const int tap = (int)((i / B) % e.RS);
+            const int a = (int)(i / ((long long)B * e.RS));
+            const int k = e.swap ? bb : a, c = e.swap ? a : bb;
+            const float v = e.src[((long long)k * e.C + c) * e.RS + tap];
+            if (e.dtype == VS_F32) reinterpret_cast<float*>(e.dst)[i] = v;
+            else reinterpret_cast<__nv_bfloat16*>(e.dst)[i] = __float2bfloat16_rn(v);
+        }
     }
 }
 
@@ -409,7 +450,10 @@ extern "C" int vs_pack_weight(const float* w, void* out, int32_t dtype, int32_t 
 
 extern "C" int vs_pack_weights_multi(const void* table, int32_t n, int32_t total_blocks, void* stream) {
     if (n <= 0 || total_blocks <= 0) return 0;
-    pack_multi_kernel<<<(unsigned)total_blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const PackEntry*>(table), n);
+    VS_REQUIRE(n <= 1024, "pack_weights_multi: at most 1024 table rows (got %d)", n);
+    VS_REQUIRE((reinterpret_cast<uintptr_t>(table) & 7) == 0, "pack_weights_multi: table must be 8-byte aligned");
+    const int grid = total_blocks < 8 * num_sms() ? total_blocks : 8 * num_sms();
+    pack_multi_kernel<<<(unsigned)grid, 256, (size_t)n * sizeof(PackEntry), as_stream(stream)>>>(reinterpret_cast<const PackEntry*>(table), n, total_blocks);
     return launched("pack_multi_kernel");
 }
 

@@ -427,3 +427,29 @@ def test_wgrad_cta_pair_opt_in():
     env = dict(os.environ, VARSEP_ENABLE_WGRAD_PAIR='1')
     r = subprocess.run([sys.executable, '-c', _PAIR_WGRAD_SNIPPET % root], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'pair wgrad ok' in r.stdout, r.stdout + r.stderr
+
+
+def test_pack_weights_multi_matches_single_entry_kernel():
+    """One-launch repack of many (parameter, layout) pairs == the per-parameter kernel, bit for bit: filter shapes with
+    4x4 / 3x3 / 5x5 / 1x1 taps, both layouts, both dtypes, channel counts that are not multiples of the 64-wide tile."""
+    import struct
+    torch.manual_seed(11)
+    shapes = [(64, 5, 16), (128, 64, 16), (70, 130, 16), (1, 64, 16), (64, 1, 16), (24, 40, 9), (16, 15, 25), (50, 37, 1),
+              (1200, 96, 1), (512, 148, 16)]
+    rows, first, keep = [], 0, []
+    for (K, C, RS) in shapes:
+        w = torch.randn(K, C, RS, device='cuda')
+        for swap in (0, 1):
+            for dt in (torch.float32, torch.bfloat16):
+                out = torch.full((K * C * RS,), float('nan'), device='cuda', dtype=dt)
+                want = torch.empty_like(out)
+                L.call('vs_pack_weight', w, want, L.dtype_code(want), K, C, RS, swap, L.stream())
+                rows.append(struct.pack('<QQiiiiii', w.data_ptr(), out.data_ptr(), K, C, RS, swap,
+                                        L.VS_F32 if dt == torch.float32 else L.VS_BF16, first))
+                first += (K * C * RS + 1023) // 1024
+                keep.append((w, out, want, (K, C, RS, swap, dt)))
+    table = torch.frombuffer(bytearray(b''.join(rows)), dtype=torch.uint8).cuda()
+    L.call('vs_pack_weights_multi', table, len(rows), first, L.stream())
+    torch.cuda.synchronize()
+    for w, out, want, what in keep:
+        assert torch.equal(out, want), what
