@@ -307,6 +307,33 @@ __global__ void pack_multi_kernel(const PackEntry* __restrict__ gtable, int n, i
             // RS contiguous floats (row pitch RS, or C*RS when swapped).  The entry's blocks walk tiles of (a, 64 values of
             // b): coalesced reads of whole tap rows into a padded shared-memory tile, coalesced writes of b-contiguous runs.
             const int nblk = (lo + 1 < n ? table[lo + 1].first_block : total_blocks) - e.first_block;
+            if (e.swap && e.RS == 16 && e.K % 32 == 0 && e.C % 2 == 0 && (reinterpret_cast<uintptr_t>(e.src) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(e.dst) & 7) == 0) {
+                // swapped 4x4 filters: out[c][tap][k] = w[k][c][tap].  Tiles of 32 k x 2 c x 16 taps: every k row contributes one
+                // full 128-byte line (the 64-value form read 64-byte pieces 8+ KB apart: DRAM-page bound at 0.5 TB/s), every
+                // (c, tap) row of the output receives one 64-byte run of k.
+                const int tiles_k = e.K / 32, ntl = (e.C / 2) * tiles_k;
+                for (int tl = vb - e.first_block; tl < ntl; tl += nblk) {
+                    const int c0 = (tl / tiles_k) * 2, k0 = (tl % tiles_k) * 32;
+                    {
+                        const int kl = threadIdx.x >> 3, f = threadIdx.x & 7;
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(e.src + ((long long)(k0 + kl) * e.C + c0) * 16) + f);
+                        float* d = tile + kl * 33 + f * 4;
+                        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int idx2 = threadIdx.x + h * 256, kp = idx2 & 15, ct = idx2 >> 4;       // ct = c_local * 16 + tap
+                        const float v0 = tile[(2 * kp) * 33 + ct], v1 = tile[(2 * kp + 1) * 33 + ct];
+                        const long long o = ((long long)c0 * 16 + ct) * e.K + k0 + 2 * kp;
+                        if (e.dtype == VS_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(e.dst) + o) = make_float2(v0, v1);
+                        else *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(e.dst) + o) = __floats2bfloat162_rn(v0, v1);
+                    }
+                    __syncthreads();
+                }
+                continue;
+            }
             const int A = e.swap ? e.C : e.K, B = e.swap ? e.K : e.C, RS = e.RS;
             const int pitch = RS | 1;
             const int tiles_b = (B + PACK_BT - 1) / PACK_BT, ntiles = A * tiles_b;
@@ -315,12 +342,35 @@ __global__ void pack_multi_kernel(const PackEntry* __restrict__ gtable, int n, i
                 const int a = tl / tiles_b, b0 = (tl - a * tiles_b) * PACK_BT;
                 const int nb = B - b0 < PACK_BT ? B - b0 : PACK_BT;
                 const float* src = e.src + (e.swap ? ((long long)b0 * e.C + a) * RS : ((long long)a * e.C + b0) * RS);
+                const bool fast = RS == 16 && nb == PACK_BT && ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(row_pitch * 4)) & 15) == 0 &&
+                                  (((uintptr_t)e.dst | (uintptr_t)(B * 2)) & 7) == 0;
+                const long long obase = (long long)a * RS * B + b0;
+                if (fast) {
+                    // 4x4 filters, full tile: one float4 (four taps of one row) per thread in, two packed pairs of b per
+                    // thread out; shifts instead of divisions (the element-wise loops below spend ~80 instructions per element)
+                    {
+                        const int row = threadIdx.x >> 2, quad = threadIdx.x & 3;
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(src + row * row_pitch) + quad);
+                        float* d = tile + row * pitch + quad * 4;
+                        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int idx2 = threadIdx.x + h * 256, tap = idx2 >> 5, bp = idx2 & 31;
+                        const float v0 = tile[(2 * bp) * pitch + tap], v1 = tile[(2 * bp + 1) * pitch + tap];
+                        const long long o = obase + (long long)tap * B + 2 * bp;
+                        if (e.dtype == VS_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(e.dst) + o) = make_float2(v0, v1);
+                        else *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(e.dst) + o) = __floats2bfloat162_rn(v0, v1);
+                    }
+                    __syncthreads();
+                    continue;
+                }
                 for (int idx = threadIdx.x; idx < nb * RS; idx += blockDim.x) {
                     const int row = idx / RS, tap = idx - row * RS;
                     tile[row * pitch + tap] = src[row * row_pitch + tap];
                 }
                 __syncthreads();
-                const long long obase = (long long)a * RS * B + b0;
                 for (int idx = threadIdx.x; idx < nb * RS; idx += blockDim.x) {
                     const int tap = idx / nb, bb = idx - tap * nb;
                     const float v = tile[bb * pitch + tap];
@@ -387,6 +437,39 @@ __global__ void __launch_bounds__(256) colsum_narrow_kernel(const T* __restrict_
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
         atomicAdd(&db[threadIdx.x], t);
+    }
+}
+
+// C == 1: a flat sum.  16-byte loads, four per thread in flight (the per-row form above issues one 2-byte load at a time)
+template <typename T>
+__global__ void __launch_bounds__(256) sum_flat_kernel(const T* __restrict__ a, long long n, float* __restrict__ db) {
+    constexpr int V = 16 / (int)sizeof(T);
+    __shared__ float red[8];
+    const long long nv = n / V, stride = (long long)gridDim.x * blockDim.x;
+    float s = 0.f;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nv; i0 += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * stride;
+            v[u] = i < nv ? __ldg(reinterpret_cast<const uint4*>(a) + i) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const T* e = reinterpret_cast<const T*>(&v[u]);
+#pragma unroll
+            for (int j = 0; j < V; ++j) s += ld<T>(e + j);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - nv * V)) s += ld<T>(a + nv * V + threadIdx.x);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(db, t);
     }
 }
 
@@ -459,6 +542,13 @@ extern "C" int vs_pack_weights_multi(const void* table, int32_t n, int32_t total
 
 extern "C" int vs_colsum(const void* a, int32_t dtype, int64_t rows, int32_t C, float* db, void* stream) {
     if (rows == 0 || C == 0) return 0;
+    if (C == 1 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+        long long blocks = cdiv(rows, 256 * 16 * 4);
+        if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+        if (blocks < 1) blocks = 1;
+        VS_DISPATCH_DTYPE(dtype, T, (sum_flat_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const T*)a, rows, db)));
+        return launched("sum_flat_kernel");
+    }
     if (C <= 4) {
         long long blocks = cdiv(rows, 1024);
         if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();

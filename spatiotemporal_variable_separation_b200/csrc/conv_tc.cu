@@ -320,6 +320,240 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
 #undef VS_TC_DECODE
 }
 
+// ------------------------------------------------------------------------------------------ fused parity classes
+// ConvTranspose k4 s2 p1 with 64 output channels per tile: the four output-parity classes of a 128-pixel tile of the class
+// grid are computed TOGETHER.  They read the same 3x3 neighbourhood of input shifts (each class uses 2x2 of them), so one
+// work item stages 9 input boxes instead of 16, and a shift shared by 2 or 4 classes is multiplied by the classes'
+// weight slabs in ONE tcgen05.mma of N = 128 or 256: the slabs sit back to back in shared memory in the order of the
+// classes' accumulator column blocks [(0,0) (0,1) (1,1) (1,0)], in which three of the four class pairs that share a shift
+// are adjacent.  10 MMAs per 16 input channels instead of 16 N = 64 ones (ncu: N = 64 instructions keep the tensor pipe
+// 65 % busy at 36 % of its FLOP rate).  The centre shift (all four classes) is issued first, so it alone initialises
+// the accumulators.  Accumulators: 2 stages x 256 columns = all of TMEM, one CTA per SM.  Epilogue: the four class
+// tiles are staged as bf16 in shared memory, written by four TMA stores, and the BatchNorm sums are read back from the
+// staged tiles (see SS above).
+constexpr int TCF_SHIFTS = 9;
+// canonical schedule: shift (dh, dw), then per MMA of the shift: first slab, slabs (x 64 columns), first column block.
+// Column blocks hold the classes (0,0) (0,1) (1,1) (1,0); equal instruction shapes are issued back to back.
+__device__ constexpr signed char TCF_DH[TCF_SHIFTS] = {0, -1, 0, 1, 0, -1, -1, 1, 1};
+__device__ constexpr signed char TCF_DW[TCF_SHIFTS] = {0, 0, 1, 0, -1, -1, 1, 1, -1};
+__device__ constexpr unsigned char TCF_NG[TCF_SHIFTS] = {1, 1, 1, 1, 2, 1, 1, 1, 1};
+__device__ constexpr unsigned char TCF_SLAB[TCF_SHIFTS][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 1}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+__device__ constexpr unsigned char TCF_N[TCF_SHIFTS][2] = {{4, 0}, {2, 0}, {2, 0}, {2, 0}, {1, 1}, {1, 0}, {1, 0}, {1, 0}, {1, 0}};
+__device__ constexpr unsigned char TCF_POS[TCF_SHIFTS][2] = {{0, 0}, {0, 0}, {1, 0}, {2, 0}, {0, 3}, {0, 0}, {1, 0}, {2, 0}, {3, 0}};
+struct TcFusedTab {
+    int nshift;
+    signed char dh[TCF_SHIFTS], dw[TCF_SHIFTS];
+    unsigned char nslab[TCF_SHIFTS];              // classes that use the shift
+    unsigned char slab_wtap[TCF_SHIFTS][4];       // packed-weight tap of slab j (slabs ordered by column block)
+    unsigned char ngrp[TCF_SHIFTS];               // MMAs per shift: runs of adjacent column blocks
+    unsigned char grp_slab[TCF_SHIFTS][4], grp_n[TCF_SHIFTS][4], grp_pos[TCF_SHIFTS][4];
+    unsigned char pos_cls[4];                     // class whose outputs column block `pos` holds
+};
+
+template <int STAGES>
+struct TcFusedSmem {
+    static constexpr int A_BYTES = TC_BM * TC_BK * 2, SLAB = 64 * TC_BK * 2, STAGE_BYTES = A_BYTES + 4 * SLAB;
+    static constexpr int OUT_BYTES = 4 * TC_BM * 128;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/ + 64 * 2 * 4 /*column sums*/;
+    static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_convT4_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_b,
+                                                                  const __grid_constant__ TcOutMaps omaps,
+                                                                  const __grid_constant__ TcParams p,
+                                                                  const __grid_constant__ TcFusedTab tab,
+                                                                  const float* __restrict__ bias, double* __restrict__ stats) {
+    using S = TcFusedSmem<STAGES>;
+    constexpr int BN = 64, ACC = 4 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* obuf = smem + STAGES * S::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;        // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* sstat = reinterpret_cast<float*>(smem + S::BAR_OFF + 256);      // [BN][2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t_begin = (int)((long long)blockIdx.x * p.total_tiles / gridDim.x);
+    const int t_end = (int)((long long)(blockIdx.x + 1) * p.total_tiles / gridDim.x);
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<2 * ACC>(tmem_slot);
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item -> (output-channel tile, pixel tile of the class grid); all four classes belong to the item
+#define VS_TCF_DECODE(idx)                                                  \
+    const int n0 = ((idx) % p.n_tiles) * BN;                                \
+    int t_ = (idx) / p.n_tiles;                                             \
+    const int tw = t_ % p.tiles_w; t_ /= p.tiles_w;                         \
+    const int th = t_ % p.tiles_h;                                          \
+    const int tn = t_ / p.tiles_h;                                          \
+    const int j0 = tw * p.WT, i0 = th * p.HT, b0 = tn * p.NT;
+
+    if (warp == 0) {
+        // ===== TMA producer: per (shift, 64-channel chunk) one input box + the weight slabs of the classes that use it =====
+        if (lane == 0) {
+            int it = 0;
+            for (int idx = t_begin; idx < t_end; ++idx) {
+                VS_TCF_DECODE(idx)
+                for (int sh = 0; sh < tab.nshift; ++sh) {
+                    const int ns = tab.nslab[sh];
+                    for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+                        mbar_expect_tx(&full[s], (uint32_t)(S::A_BYTES + ns * S::SLAB));
+                        tma_load_4d(a_dst, &map_a, &full[s], kc * TC_BK, j0 + tab.dw[sh], i0 + tab.dh[sh], b0);
+                        for (int j = 0; j < ns; ++j)
+                            tma_load_2d(a_dst + S::A_BYTES + j * S::SLAB, &map_b, &full[s], tab.slab_wtap[sh][j] * p.IC + kc * TC_BK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread).  The MMA schedule of a work item is fixed (TCF_* tables below, canonical shift
+        // order enforced by the host), so the loops are fully unrolled with compile-time column blocks, slab offsets and
+        // instruction descriptors: a table-driven issuer spent ~250 cycles of dependent scalar work per MMA and left the
+        // tensor pipe 25 % busy =====
+        if (lane == 0) {
+            int it = 0, lt = 0;
+            for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC);
+#pragma unroll
+                for (int sh = 0; sh < TCF_SHIFTS; ++sh) {
+#pragma unroll 1
+                    for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(&full[s], (it / STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+                        const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+#pragma unroll
+                            for (int g = 0; g < TCF_NG[sh]; ++g) {
+                                // the first MMA of a work item is the centre shift: N = 256, it overwrites all four blocks
+                                umma_bf16(tmem_d + (uint32_t)(TCF_POS[sh][g] * BN), kmajor_sw128_desc(a_addr + k * 32),
+                                          kmajor_sw128_desc(b_addr + TCF_SLAB[sh][g] * S::SLAB + k * 32), idesc_bf16_f32(64 * TCF_N[sh][g]),
+                                          (sh != 0 || (kc | k) != 0) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(&empty[s]);
+                    }
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..9; lane quarter q, column blocks {2*half, 2*half + 1} =====
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int m = q * 32 + lane;
+        const int w = m % p.WT, h = (m / p.WT) % p.HT, n = m / (p.WT * p.HT);
+        const int t = threadIdx.x - 64, cp = t & 31, rg = t >> 5;
+        int lt = 0;
+        int stat_key = -1;
+        float ss[4] = {0.f, 0.f, 0.f, 0.f};
+        auto ss_flush = [&](int key) {
+            atomicAdd(&sstat[(2 * cp) * 2], ss[0]);     atomicAdd(&sstat[(2 * cp) * 2 + 1], ss[1]);
+            atomicAdd(&sstat[(2 * cp + 1) * 2], ss[2]); atomicAdd(&sstat[(2 * cp + 1) * 2 + 1], ss[3]);
+            ss[0] = ss[1] = ss[2] = ss[3] = 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            if (t < 2 * BN) {
+                const int col = (key % p.n_tiles) * BN + (t >> 1);
+                if (col < p.OC) atomicAdd(&stats[((long long)(key / p.n_tiles) * p.OC + col) * 2 + (t & 1)], (double)sstat[t]);
+                sstat[t] = 0.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        };
+        for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
+            VS_TCF_DECODE(idx)
+            const int acc = lt & 1;
+            const int i = i0 + h, j = j0 + w, nn = b0 + n;
+            const bool ok = i < p.OHc && j < p.OWc && nn < p.N;
+            const bool full_tile = i0 + p.HT <= p.OHc && j0 + p.WT <= p.OWc && b0 + p.NT <= p.N;
+            if (stats != nullptr) {
+                const int key = (b0 / p.n_per_group) * p.n_tiles + n0 / BN;
+                if (key != stat_key) {
+                    if (stat_key >= 0) ss_flush(stat_key);
+                    stat_key = key;
+                }
+            }
+            mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+            tc_fence_after();
+            // the previous item's TMA stores (and everybody's statistics reads) are done with the staging tiles
+            if (threadIdx.x == 64) tma_store_wait_read();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                const int pb = 2 * half + (cc >> 1), c0 = (cc & 1) * 32;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC + pb * BN + c0), r);
+                const float bias_l = (p.has_bias && n0 + c0 + lane < p.OC) ? __ldg(bias + n0 + c0 + lane) : 0.f;
+                float xs[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                if (!full_tile && !ok) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) xs[c] = 0.f;
+                }
+                stage_row32(obuf + pb * (TC_BM * 128), m, c0, xs, p.act);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            fence_proxy_async();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            if (threadIdx.x == 64) {
+#pragma unroll
+                for (int pb = 0; pb < 4; ++pb) tma_store_4d(&omaps.m[tab.pos_cls[pb]], obuf + pb * (TC_BM * 128), n0, j0, i0, b0);
+                tma_store_commit();
+            }
+            if (stats != nullptr) {
+#pragma unroll 1
+                for (int pb = 0; pb < 4; ++pb) {
+                    const uint8_t* tile = obuf + pb * (TC_BM * 128) + (cp & 3) * 4;
+#pragma unroll
+                    for (int rr = 0; rr < TC_BM / TC_EPI_WARPS; ++rr) {
+                        const int row = rg * (TC_BM / TC_EPI_WARPS) + rr;
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + row * 128 + (((cp >> 2) ^ (row & 7)) << 4));
+                        const float a = __uint_as_float(v << 16), b = __uint_as_float(v & 0xffff0000u);
+                        ss[0] += a; ss[1] = fmaf(a, a, ss[1]);
+                        ss[2] += b; ss[3] = fmaf(b, b, ss[3]);
+                    }
+                }
+            }
+        }
+        if (stats != nullptr && stat_key >= 0) ss_flush(stat_key);
+        if (threadIdx.x == 64) tma_store_wait_all();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * ACC>(tmem_base);
+    }
+#undef VS_TCF_DECODE
+}
+
 // ------------------------------------------------------------------------------------------ CTA pairs
 // cta_group::2 variant for the wide layers (OC a multiple of 128): the two CTAs of a cluster (one TPC) work on two
 // adjacent 128-pixel tiles and the SAME BN output channels.  Each CTA stages its own A box and only HALF of the weight
@@ -602,6 +836,95 @@ static bool staged_stats_disabled() {
     return v == 1;
 }
 
+// The fused-class kernel is correct (tests/test_kernels_gpu.py runs it) but measured SLOWER than the per-class kernel
+// on the 128->64 decoder layer: 488 us with a table-driven MMA issuer (~250 cycles of dependent scalar work per MMA,
+// tensor pipe 25 % busy), 275 us with the compile-time schedule, against 223 us for four per-class launches' worth of
+// work in tc_conv_kernel.  With all of TMEM and a 64 KB staging area it runs ONE CTA per SM with three stages in
+// flight and a single epilogue, where the per-class kernel overlaps two CTAs (six stages) per SM.  Opt-in
+// (VARSEP_ENABLE_FUSED_CLASSES=1) until it gets a deeper ring / resident weight slabs.
+static bool fused_classes_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VARSEP_ENABLE_FUSED_CLASSES"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
+// shift table of the fused-class kernel from the per-class tap tables of a k4 s2 p1 transposed convolution;
+// false when the geometry does not have the 3x3-shifts / 2x2-per-class structure
+static bool build_fused_tab(const TcParams& p, int classes, TcFusedTab& tab) {
+    if (classes != 4 || p.ntaps != 4 || p.ost != 2) return false;
+    memset(&tab, 0, sizeof(tab));
+    static const int cls_pos[4] = {0, 1, 3, 2};          // class a*2+b -> column block: (0,0) (0,1) (1,1) (1,0)
+    for (int cls = 0; cls < 4; ++cls) {
+        if (p.ca[cls] * 2 + p.cb[cls] != cls) return false;
+        tab.pos_cls[cls_pos[cls]] = (unsigned char)cls;
+    }
+    int uses[TCF_SHIFTS][4];                              // [shift][pos] = packed tap, or -1
+    int sdh[TCF_SHIFTS], sdw[TCF_SHIFTS], ns = 0;
+    for (int cls = 0; cls < 4; ++cls)
+        for (int t = 0; t < 4; ++t) {
+            const int dh = p.dh[cls * 4 + t], dw = p.dw[cls * 4 + t];
+            int sh = -1;
+            for (int i = 0; i < ns; ++i) if (sdh[i] == dh && sdw[i] == dw) sh = i;
+            if (sh < 0) {
+                if (ns == TCF_SHIFTS) return false;
+                sh = ns++; sdh[sh] = dh; sdw[sh] = dw;
+                for (int q = 0; q < 4; ++q) uses[sh][q] = -1;
+            }
+            if (uses[sh][cls_pos[cls]] >= 0) return false;
+            uses[sh][cls_pos[cls]] = p.wtap[cls * 4 + t];
+        }
+    // canonical order of the device-side schedule (TCF_* tables); every shift must have exactly the expected MMAs
+    static const signed char cdh[TCF_SHIFTS] = {0, -1, 0, 1, 0, -1, -1, 1, 1}, cdw[TCF_SHIFTS] = {0, 0, 1, 0, -1, -1, 1, 1, -1};
+    static const unsigned char cng[TCF_SHIFTS] = {1, 1, 1, 1, 2, 1, 1, 1, 1};
+    static const unsigned char cn[TCF_SHIFTS][2] = {{4, 0}, {2, 0}, {2, 0}, {2, 0}, {1, 1}, {1, 0}, {1, 0}, {1, 0}, {1, 0}};
+    static const unsigned char cpos[TCF_SHIFTS][2] = {{0, 0}, {0, 0}, {1, 0}, {2, 0}, {0, 3}, {0, 0}, {1, 0}, {2, 0}, {3, 0}};
+    static const unsigned char cslab[TCF_SHIFTS][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 1}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    if (ns != TCF_SHIFTS) return false;
+    tab.nshift = ns;
+    for (int o = 0; o < ns; ++o) {
+        int i = -1;
+        for (int j = 0; j < ns; ++j) if (sdh[j] == cdh[o] && sdw[j] == cdw[o]) i = j;
+        if (i < 0) return false;
+        tab.dh[o] = (signed char)sdh[i]; tab.dw[o] = (signed char)sdw[i];
+        int nslab = 0, ng = 0;
+        for (int q = 0; q < 4; ++q) {
+            if (uses[i][q] < 0) continue;
+            tab.slab_wtap[o][nslab] = (unsigned char)uses[i][q];
+            if (q > 0 && uses[i][q - 1] >= 0) {           // adjacent to the previous slab's column block: same MMA
+                tab.grp_n[o][ng - 1]++;
+            } else {
+                tab.grp_slab[o][ng] = (unsigned char)nslab; tab.grp_pos[o][ng] = (unsigned char)q; tab.grp_n[o][ng] = 1;
+                ++ng;
+            }
+            ++nslab;
+        }
+        if (ng != cng[o]) return false;
+        for (int g = 0; g < ng; ++g)
+            if (tab.grp_n[o][g] != cn[o][g] || tab.grp_pos[o][g] != cpos[o][g] || tab.grp_slab[o][g] != cslab[o][g]) return false;
+        tab.nslab[o] = (unsigned char)nslab; tab.ngrp[o] = (unsigned char)ng;
+    }
+    return true;
+}
+
+template <int STAGES>
+static int launch_tc_fused(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMaps& om, const TcParams& p, const TcFusedTab& tab,
+                           const float* bias, double* stats, cudaStream_t stream) {
+    using S = TcFusedSmem<STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_convT4_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return fail("tc_convT4_kernel smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    TcParams q = p;
+    q.classes = 4;
+    q.n_tiles = (int)cdiv(p.OC, 64);
+    q.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * q.n_tiles;
+    const int grid = q.total_tiles < num_sms() ? q.total_tiles : num_sms();      // one CTA per SM (all 512 TMEM columns)
+    tc_convT4_kernel<STAGES><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, om, q, tab, bias, stats);
+    return launched("tc_convT4_kernel");
+}
+
 static bool staged_epilogue_disabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("VARSEP_DISABLE_STAGED_EPILOGUE"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -732,6 +1055,13 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
         }
     }
     double* stp = fuse_stats ? stats : nullptr;
+    TcFusedTab ftab;
+    if (tr && staged && !pair && (stp == nullptr || p.act == VS_ACT_NONE) && !fused_classes_disabled() && build_fused_tab(p, classes, ftab)) {
+        int rc = launch_tc_fused<3>(ma, mb, om, p, ftab, bias, stp, stream);
+        if (rc) return rc;
+        if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
+        return rc;
+    }
     int rc = pair ? (PBN == 256 ? launch_tc_pair<256, 6>(ma, mb, p, bias, out, classes, stp, stream)
                                 : launch_tc_pair<128, 8>(ma, mb, p, bias, out, classes, stp, stream))
              : BN == 128 ? launch_tc<128, 3, false>(ma, mb, om, p, bias, out, classes, stp, stream)

@@ -298,10 +298,23 @@ def test_elementwise_kernels(dt):
     assert torch.equal(gpu[2], cpu[2])
     gpu, cpu = run_both('vs_nchw_to_nhwc', [cpu[2], torch.zeros(3, 6, 5, 4).to(dtype), code, 3, 4, 6, 5, None])
     assert torch.equal(gpu[1], cpu[1])
-    # column sums
-    m = torch.randn(1000, 37).to(dtype)
-    gpu, cpu = run_both('vs_colsum', [m, code, 1000, 37, torch.randn(37), None])
-    close(gpu[4], cpu[4], torch.float32, 'colsum', scale=float(cpu[4].abs().max()))
+    # ... the block-staged frame folding (full 256-pixel blocks + a tail block), windows of 5 and of 15 folded channels
+    for (B_, T_, Cf, H_, W_, t0, nt) in [(5, 9, 1, 24, 24, 3, 5), (3, 8, 3, 20, 17, 2, 5), (2, 6, 5, 16, 16, 1, 4)]:
+        fr = torch.randn(B_, T_, Cf, H_, W_)
+        gpu, cpu = run_both('vs_frames_to_nhwc', [fr, B_, T_, Cf, H_, W_, t0, nt, torch.zeros(B_, H_, W_, nt * Cf).to(dtype), code, None])
+        assert torch.equal(gpu[8], cpu[8]), (B_, T_, Cf, H_, W_, t0, nt)
+    # ... single-channel / 1x1 tensors, where the layout change is a cast (vector body + scalar tail)
+    for (N_, C_, H_, W_) in [(7, 1, 33, 31), (9, 37, 1, 1), (4, 1, 64, 64)]:
+        xi = torch.randn(N_, H_, W_, C_).to(dtype)
+        gpu, cpu = run_both('vs_nhwc_to_nchw', [xi, code, torch.zeros(N_, C_, H_, W_), N_, C_, H_, W_, None])
+        assert torch.equal(gpu[2], cpu[2])
+        gpu, cpu = run_both('vs_nchw_to_nhwc', [cpu[2], torch.zeros(N_, H_, W_, C_).to(dtype), code, N_, C_, H_, W_, None])
+        assert torch.equal(gpu[1], cpu[1])
+    # column sums (general, narrow, and the flat single-column form with a tail)
+    for rows, C_ in [(1000, 37), (5000, 3), (70001, 1), (100, 1)]:
+        m = torch.randn(rows, C_).to(dtype)
+        gpu, cpu = run_both('vs_colsum', [m, code, rows, C_, torch.randn(C_), None])
+        close(gpu[4], cpu[4], torch.float32, 'colsum', scale=float(cpu[4].abs().max()) + float(m.float().abs().sum(0).max()) * 1e-3)
 
 
 def test_loss_and_adam_kernels():
@@ -319,6 +332,12 @@ def test_loss_and_adam_kernels():
     assert abs(float(gpu[9][0]) - want) < 1e-6 * want and abs(float(cpu[9][0]) - want) < 1e-6 * want
     gpu, cpu = run_both('vs_sqdiff_sum', [abase, Ln, B * Ln, None, 0, 0, B, T, Ln, acc[1:2], None])
     assert abs(float(gpu[9][0]) - float((a ** 2).double().sum())) < 1e-6 * want
+    # rows that are not a multiple of four floats take the element-wise form
+    a7, b7 = torch.randn(3, 2, 7), torch.randn(3, 2, 7)
+    acc7 = torch.zeros(1, dtype=torch.float64)
+    gpu, cpu = run_both('vs_sqdiff_sum', [a7.reshape(-1), 14, 7, b7.reshape(-1), 14, 7, 3, 2, 7, acc7, None])
+    want7 = float(((a7 - b7) ** 2).double().sum())
+    assert abs(float(gpu[9][0]) - want7) < 1e-6 * want7 and abs(float(cpu[9][0]) - want7) < 1e-6 * want7
     gt = torch.tensor([0.5, 2.0])
     for accumulate in (0, 1):
         da = torch.randn(T * B * Ln)
@@ -453,3 +472,38 @@ def test_pack_weights_multi_matches_single_entry_kernel():
     torch.cuda.synchronize()
     for w, out, want, what in keep:
         assert torch.equal(out, want), what
+
+
+_FUSED_CLASSES_SNIPPET = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from spatiotemporal_variable_separation_b200 import _lib as L
+torch.manual_seed(5)
+# transposed k4 s2 p1 with 64 output channels: full tiles, several images per tile, a partial last tile, two channel tiles
+for (N, P, K, C, G) in [(6, 16, 128, 64, 3), (16, 8, 64, 64, 2), (5, 4, 64, 64, 1), (4, 8, 72, 96, 2)]:
+    H = 2 * P
+    x = torch.randn(N, P, P, K, device='cuda').bfloat16()
+    wp = (torch.randn(C, 16, K, device='cuda') / (16 * K) ** 0.5).bfloat16()
+    bias = torch.randn(C, device='cuda')
+    outs, sts = [], []
+    for flags in (0, L.FLAG_FORCE_SIMT):
+        out = torch.full((N, H, H, C), float('nan'), device='cuda').bfloat16()
+        st = torch.zeros(G * C * 2, device='cuda', dtype=torch.float64)
+        before = L.launch_count()
+        L.call('vs_conv_forward', L.Geom(1, N, H, H, C, P, P, K, 4, 4, 2, 1, G, 0, flags), L.TRANSPOSED, x, wp, bias, out, st, L.stream())
+        torch.cuda.synchronize()
+        outs.append(out.float()); sts.append(st)
+    err = float((outs[0] - outs[1]).abs().max()) / float(outs[1].abs().max())
+    serr = float((sts[0] - sts[1]).abs().max()) / float(sts[1].abs().max())
+    assert err < 2 ** -7 and serr < 2e-3, (N, P, K, C, err, serr)
+print('fused classes ok')
+'''
+
+
+def test_fused_class_transposed_conv_opt_in():
+    """The fused-parity-class kernel (tc_convT4_kernel) is opt-in (VARSEP_ENABLE_FUSED_CLASSES=1, read once per process)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VARSEP_ENABLE_FUSED_CLASSES='1')
+    r = subprocess.run([sys.executable, '-c', _FUSED_CLASSES_SNIPPET % root], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'fused classes ok' in r.stdout, r.stdout + r.stderr
