@@ -356,7 +356,7 @@ def _shutdown(tr, world):
 
 def conv_roofline(tr, dev, draws, dtype):
     """Roofline of the dominant kernel, the tcgen05 tap GEMM (tc_conv_kernel and its CTA-pair variant
-    tc_conv_pair_kernel: fprop and dgrad of every eligible conv layer).  CUDA events on the launching stream around each vs_conv_forward call of two extra eager steps; only the
+    tc_conv_pair_kernel: fprop and dgrad of every eligible conv layer).  CUDA events on the launching stream around each vs_conv_forward call of two extra eager steps (each pair enqueued behind a short spin kernel, so that the interval is the kernel's duration and not its launch latency); only the
     calls that the library routes to the tensor-core kernel (vs_conv_forward_path == 1) are counted.  Algorithmic
     FLOPs per launch = 2*N*P*Q*K*C*R*S (for a stride-2 transposed convolution the parity decomposition multiplies no
     structurally-zero tap, so this is also the executed count)."""
@@ -371,6 +371,10 @@ def conv_roofline(tr, dev, draws, dtype):
         g = a[0]
         flops = 2.0 * g.N * g.P * g.Q * g.K * g.C * g.R * g.S
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # an eager step is CPU bound between launches: without work ahead of it in the stream the first event fires at
+        # once and the interval would include the launch latency of the kernel.  A ~20 us spin kernel keeps the stream
+        # busy while the event pair and the convolution are enqueued behind it.
+        torch.cuda._sleep(40000)
         e0.record()
         orig(name, *a)
         e1.record()

@@ -256,10 +256,15 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-                const float bias_l = (p.has_bias && c0 + lane < p.K) ? __ldg(bias + c0 + lane) : 0.f;
                 float xs[32];
+                if (p.has_bias) {          // uniform: dgrad launches carry no bias and skip the 32 shuffles
+                    const float bias_l = (p.has_bias && c0 + lane < p.K) ? __ldg(bias + c0 + lane) : 0.f;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                    for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]);
+                }
                 if (TS) {
                     stage_row32(obuf + (lt & 1) * (TC_BM * 128), m, c0, xs, p.act);
                 } else if (p.partial || BN > p.K) {

@@ -209,10 +209,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
                 // one coalesced bias load per chunk, broadcast by shuffle (instead of 32 loads per thread); the
                 // shuffles are executed by all lanes before any per-lane predicate
-                const float bias_l = (p.has_bias && n0 + c0 + lane < p.OC) ? __ldg(bias + n0 + c0 + lane) : 0.f;
                 float xs[32];
+                if (p.has_bias) {          // uniform: dgrad launches carry no bias and skip the 32 shuffles
+                    const float bias_l = (p.has_bias && n0 + c0 + lane < p.OC) ? __ldg(bias + n0 + c0 + lane) : 0.f;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                    for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]);
+                }
                 if (TS) {
                     if (SS && !full_tile && !ok) {          // rows beyond the tensor edge: clipped by the TMA store, must not count
 #pragma unroll
@@ -508,10 +513,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_convT4_kernel(const __grid_c
                 const int pb = 2 * half + (cc >> 1), c0 = (cc & 1) * 32;
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC + pb * BN + c0), r);
-                const float bias_l = (p.has_bias && n0 + c0 + lane < p.OC) ? __ldg(bias + n0 + c0 + lane) : 0.f;
                 float xs[32];
+                if (p.has_bias) {          // uniform: dgrad launches carry no bias and skip the 32 shuffles
+                    const float bias_l = (p.has_bias && n0 + c0 + lane < p.OC) ? __ldg(bias + n0 + c0 + lane) : 0.f;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                    for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]);
+                }
                 if (!full_tile && !ok) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) xs[c] = 0.f;
@@ -694,10 +704,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
             for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-                const float bias_l = p.has_bias ? __ldg(bias + n0 + c0 + lane) : 0.f;
                 float xs[32];
+                if (p.has_bias) {          // uniform: dgrad launches carry no bias and skip the 32 shuffles
+                    const float bias_l = p.has_bias ? __ldg(bias + n0 + c0 + lane) : 0.f;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                    for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]);
+                }
                 if (ok) {
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {

@@ -109,7 +109,7 @@ class SeparableNetwork(nn.Module):
         frames = self.decoder.decode_external(s_int, t_all, skip_int, groups=n_groups)
         frames = frames.view(n_groups, B, *frames.shape[1:])
         if extra_t is not None:
-            recon, frames = frames[0], frames[1:]
+            recon, frames = ops.split_first_group(frames)
         forecasts = frames.transpose(0, 1)                                   # [B, T, C, H, W] view
         s_code = _external_codes(s_int)
         if extra_t is not None:

@@ -542,6 +542,35 @@ def _btl(t):
     return 1, 1, t.numel(), 0, 0
 
 
+class SplitFirstGroupFn(torch.autograd.Function):
+    """frames [G, B, ...] -> (frames[0], frames[1:]).  Autograd's own select / slice backward would zero-fill two
+    full-size buffers, copy each gradient into its own and add them (two 33 MB fills + a 100 MB add per step for the
+    mnist decoder output); here both gradients are copied into ONE buffer."""
+
+    @staticmethod
+    def forward(ctx, frames):
+        ctx.meta = (frames.shape, frames.dtype, frames.device)
+        return frames[0], frames[1:]
+
+    @staticmethod
+    def backward(ctx, g_first, g_rest):
+        shape, dtype, device = ctx.meta
+        out = torch.empty(shape, device=device, dtype=dtype)
+        if g_first is None:
+            out[0].zero_()
+        else:
+            out[0].copy_(g_first)
+        if g_rest is None:
+            out[1:].zero_()
+        else:
+            out[1:].copy_(g_rest)
+        return out
+
+
+def split_first_group(frames):
+    return SplitFirstGroupFn.apply(frames)
+
+
 class LossTermsFn(torch.autograd.Function):
     """All squared-error terms of the step in one pass each, combined on the device.
 
