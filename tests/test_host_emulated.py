@@ -275,3 +275,14 @@ def test_no_cpu_fallback():
     cond, _ = harness.inputs(harness.load_golden('mnist-small')['cfg'])
     with pytest.raises(RuntimeError, match='CUDA device only'):
         net.Es(cond)
+
+
+@pytest.mark.parametrize('name', harness.eval_golden_names())
+def test_eval_rollout_and_content_swap(name):
+    """Eval-mode long-horizon forecast, restart from init_t_code and content swap through init_s_code (the callers of
+    get_forecast in the reference's test/* scripts) through the shipped modules over the emulated C ABI."""
+    g = harness.load_eval_golden(name)
+    ops.set_compute_dtype(torch.float32)
+    with emu.install():
+        net = build_filled(g['cfg']).eval()
+        harness.check_eval_rollout(g, net, g['cfg']['skipco'])

@@ -76,3 +76,14 @@ def test_fp64_oracle_agrees_with_fp64_reference():
     _, out, _ = harness.oracle_step(g['cfg'], torch.float64, int(g['np_seed']))
     ours = np.array([float(out[k].detach()) for k in ('ae', 's', 'pred', 't', 'total')])
     np.testing.assert_allclose(ours, g['loss64'], rtol=1e-12)
+
+
+@pytest.mark.parametrize('name', harness.eval_golden_names())
+def test_eval_rollout_and_content_swap(name):
+    """eval-mode forecast over three training horizons, restart from a given T code and
+    content swap through init_s_code, oracle against the reference's recorded values (1e-5)."""
+    g = harness.load_eval_golden(name)
+    torch.set_num_threads(8)
+    net = harness.oracle_net(g['cfg']).requires_grad_(False)
+    net.train = False
+    harness.check_eval_rollout(g, net, g['cfg']['skipco'], rtol=1e-5)

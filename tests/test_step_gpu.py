@@ -155,6 +155,16 @@ def test_eval_rollout_is_bit_reproducible_and_batch_invariant():
     assert torch.equal(f1[:2].contiguous(), f3.contiguous())
 
 
+@pytest.mark.parametrize('name', harness.eval_golden_names())
+def test_eval_rollout_and_content_swap_match_reference(name):
+    """eval-mode forecast over three training horizons (running BatchNorm statistics), its
+    restart from init_t_code and the content swap through init_s_code against the values recorded from the reference
+    (tests/golden/gen_eval_golden.py), fp32, 2e-5."""
+    g = harness.load_eval_golden(name)
+    net = build_filled(g['cfg'], 'cuda').eval()
+    harness.check_eval_rollout(g, net, g['cfg']['skipco'], device='cuda')
+
+
 def test_full_size_mnist_properties():
     """BASELINE configs[1] at full size (B=128, nf=64): finite losses, AE/pred losses of a sigmoid
     decoder on [0,1] data lie in (0, 1), every parameter receives a finite gradient, the conv biases
