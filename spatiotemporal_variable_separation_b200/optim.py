@@ -23,7 +23,9 @@ class FusedAdam:
         assert self.params, 'no parameters'
         dev = self.params[0].device
         L.require_cuda(self.params[0])
-        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        # one parameter group, kept as a persistent dict so that learning-rate schedules can write to it
+        self._groups = [dict(params=self.params, lr=float(lr), initial_lr=float(lr), betas=(float(betas[0]), float(betas[1])),
+                             eps=float(eps), weight_decay=0, amsgrad=False)]
         self.offsets, total = [], 0
         for p in self.params:
             self.offsets.append(total)
@@ -49,7 +51,23 @@ class FusedAdam:
     # torch.optim-like surface used by train()
     @property
     def param_groups(self):
-        return [{'params': self.params, 'lr': self.lr, 'betas': self.betas, 'eps': self.eps}]
+        return self._groups
+
+    @property
+    def lr(self):
+        return self._groups[0]['lr']
+
+    @lr.setter
+    def lr(self, value):
+        self._groups[0]['lr'] = float(value)
+
+    @property
+    def betas(self):
+        return self._groups[0]['betas']
+
+    @property
+    def eps(self):
+        return self._groups[0]['eps']
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
@@ -63,3 +81,73 @@ class FusedAdam:
 
     def grad_of(self, p):
         return p._vs_grad
+
+    # ---- checkpointing in torch.optim.Adam's own format (the reference saves no optimizer state) ----
+    def state_dict(self):
+        """Same layout as ``torch.optim.Adam(...).state_dict()`` over the same parameter list, so training can resume
+        under either optimizer: per parameter index ``step`` (fp32 scalar), ``exp_avg``, ``exp_avg_sq``."""
+        step = float(self.step_dev.item())
+        state = {}
+        if step > 0:
+            for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+                n = p.numel()
+                state[i] = {'step': torch.tensor(step),
+                            'exp_avg': self.exp_avg[off:off + n].view(p.shape).clone(),
+                            'exp_avg_sq': self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+        group = {k: v for k, v in self._groups[0].items() if k != 'params'}
+        group['params'] = list(range(len(self.params)))
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd['param_groups']
+        assert len(groups) == 1 and len(groups[0]['params']) == len(self.params), 'parameter list does not match'
+        g = groups[0]
+        assert not g.get('amsgrad', False) and not g.get('weight_decay', 0), 'amsgrad / weight decay are not implemented'
+        self._groups[0].update(lr=float(g['lr']), betas=(float(g['betas'][0]), float(g['betas'][1])), eps=float(g['eps']))
+        if 'initial_lr' in g:
+            self._groups[0]['initial_lr'] = float(g['initial_lr'])
+        steps = set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            st = sd['state'].get(i)
+            if st is None:                       # a parameter torch.optim.Adam never saw a gradient for
+                continue
+            n = p.numel()
+            self.exp_avg[off:off + n].copy_(st['exp_avg'].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+            steps.add(int(float(st['step'])))
+        assert len(steps) <= 1, f'parameters at different step counts: {sorted(steps)}'
+        self.step_dev.fill_(steps.pop() if steps else 0)
+
+
+class MultiStepLR:
+    """``torch.optim.lr_scheduler.MultiStepLR`` (main.py:146-147) for ``FusedAdam``: lr = initial_lr * gamma^(number of
+    milestones reached), one ``step()`` per epoch (train.py:166-167).  Works on any object with ``param_groups``.
+    (A captured CUDA graph bakes the learning rate in: re-capture after a change.)"""
+
+    def __init__(self, optimizer, milestones, gamma=0.1, last_epoch=0):
+        self.optimizer, self.milestones, self.gamma = optimizer, sorted(int(m) for m in milestones), float(gamma)
+        self.last_epoch = int(last_epoch)
+        for g in optimizer.param_groups:
+            g.setdefault('initial_lr', g['lr'])
+        self._apply()
+
+    def _apply(self):
+        k = sum(1 for m in self.milestones if m <= self.last_epoch)
+        for g in self.optimizer.param_groups:
+            g['lr'] = g['initial_lr'] * self.gamma ** k
+
+    def step(self):
+        self.last_epoch += 1
+        self._apply()
+
+    def get_last_lr(self):
+        return [g['lr'] for g in self.optimizer.param_groups]
+
+    def state_dict(self):
+        return {'milestones': list(self.milestones), 'gamma': self.gamma, 'last_epoch': self.last_epoch}
+
+    def load_state_dict(self, sd):
+        self.milestones, self.gamma, self.last_epoch = sorted(sd['milestones']), float(sd['gamma']), int(sd['last_epoch'])
+        self._apply()

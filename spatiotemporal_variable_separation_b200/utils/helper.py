@@ -1,8 +1,13 @@
-"""Checkpoint helpers (counterpart of /root/reference/var_sep/utils/helper.py:22-33).
+"""Checkpoint helpers (counterpart of /root/reference/var_sep/utils/helper.py:22-33,54-78).
 
-The reference pickles whole nn.Modules; here the four networks are stored as ``state_dict``s
-(identical keys and shapes, so they load into the reference modules and vice versa) under the
-reference's file names."""
+The reference pickles whole nn.Modules under ``ov_Et.pt / ov_Es.pt / decoder.pt / t_resnet.pt`` (``save``) and
+unpickles them in ``test/utils.py:8-16``.  Here the four networks are stored as ``state_dict``s under the same file
+names (identical keys and shapes, so they load into the reference's modules with ``load_state_dict`` and vice versa),
+and ``load`` accepts BOTH formats: a file written by the reference (a pickled module; needs the reference package
+importable for unpickling) is reduced to its ``state_dict``.  ``save_training_state`` / ``load_training_state`` add what
+the reference never saves: the optimizer moments and step count (in ``torch.optim.Adam``'s own format) and the
+learning-rate schedule, so that training can resume bit-exactly."""
+import json
 import os
 
 import torch
@@ -17,9 +22,54 @@ def save(elem_xp_path, sep_net, epoch_number=None):
         torch.save(sd, os.path.join(elem_xp_path, f'{name}{suffix}.pt'))
 
 
+def _state_dict_of(obj, path):
+    if isinstance(obj, torch.nn.Module):                 # written by the reference: torch.save(module)
+        return obj.state_dict()
+    if isinstance(obj, dict):
+        return obj
+    raise TypeError(f'{path}: expected a state_dict or a pickled nn.Module, got {type(obj).__name__}')
+
+
 def load(elem_xp_path, sep_net, epoch_number=None):
     suffix = f'_{epoch_number}' if epoch_number is not None else ''
     for attr, name in _FILES:
-        sd = torch.load(os.path.join(elem_xp_path, f'{name}{suffix}.pt'), map_location='cpu')
-        getattr(sep_net, attr).load_state_dict(sd)
+        path = os.path.join(elem_xp_path, f'{name}{suffix}.pt')
+        try:
+            obj = torch.load(path, map_location='cpu', weights_only=True)
+        except Exception:
+            # a module pickled by the reference (torch < 2.6 default); its classes must be importable (var_sep.networks.*)
+            obj = torch.load(path, map_location='cpu', weights_only=False)
+        getattr(sep_net, attr).load_state_dict(_state_dict_of(obj, path))
     return sep_net
+
+
+def save_training_state(elem_xp_path, optimizer, scheduler=None, epoch=None):
+    state = {'optimizer': optimizer.state_dict(), 'scheduler': scheduler.state_dict() if scheduler is not None else None,
+             'epoch': epoch}
+    torch.save(state, os.path.join(elem_xp_path, 'training_state.pt'))
+
+
+def load_training_state(elem_xp_path, optimizer, scheduler=None):
+    state = torch.load(os.path.join(elem_xp_path, 'training_state.pt'), map_location='cpu', weights_only=False)
+    optimizer.load_state_dict(state['optimizer'])
+    if scheduler is not None and state.get('scheduler') is not None:
+        scheduler.load_state_dict(state['scheduler'])
+    return state.get('epoch')
+
+
+class DotDict(dict):
+    """Dot access to dictionary entries (helper.py:54-60)."""
+    __getattr__ = dict.get
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
+
+
+def load_json(path):
+    with open(path, 'r') as f:
+        return DotDict(json.load(f))
+
+
+def load_yaml(path):
+    import yaml
+    with open(path, 'r') as f:
+        return DotDict(yaml.safe_load(f))
