@@ -97,3 +97,18 @@ def test_init_net_statistics():
     assert torch.allclose(w @ w.t(), 0.71 ** 2 * torch.eye(20), atol=1e-4)
     e = factory.get_encoder('dcgan', [1, 64, 64], 16, 8, 3, 5, 'normal', 0.02)
     assert abs(float(e.conv[1][1].weight.mean()) - 1.0) < 0.02 and float(e.conv[1][0].bias.abs().max()) == 0.0
+
+
+def test_split_first_group_backward_fills_one_buffer():
+    """ops.split_first_group: both gradients land in ONE buffer; a missing gradient becomes zeros (pure torch plumbing)."""
+    from spatiotemporal_variable_separation_b200 import ops
+    x = torch.randn(4, 3, 2, 5, requires_grad=True)
+    first, rest = ops.split_first_group(x)
+    assert torch.equal(first, x[0]) and torch.equal(rest, x[1:])
+    w1, w2 = torch.randn_like(first), torch.randn_like(rest)
+    ((first * w1).sum() + (rest.transpose(0, 1) * w2.transpose(0, 1)).sum()).backward()
+    assert torch.equal(x.grad[0], w1) and torch.equal(x.grad[1:], w2)
+    y = torch.randn(3, 2, requires_grad=True)
+    first, rest = ops.split_first_group(y)
+    rest.sum().backward()
+    assert torch.equal(y.grad, torch.cat([torch.zeros(1, 2), torch.ones(2, 2)]))
