@@ -208,6 +208,17 @@ int vs_latent_rollout_forward(float* codes, const float* const* w_host, int32_t 
 int vs_latent_rollout_backward(float* dcodes, const float* const* w_host, int32_t T, int32_t B, int32_t d, int32_t h,
                                int32_t n_blocks, const float* hidden, float* dres, float* dhidden, void* stream);
 
+/* ---- evaluation metrics ---------------------------------------------------------------------
+ * replaces: var_sep/utils/ssim.py:95-116 (_ssim: five grouped Gaussian conv2d + the SSIM formula, reduction over the
+ * map by the caller, test/utils.py:19-24) and the per-frame F.mse_loss(..., 'none').mean([3,4]) of
+ * test/mnist/test.py:137.  pred / target: `planes` contiguous fp32 H x W planes (NCHW images, one plane per (image,
+ * channel)); kernel: fs x fs window weights (ssim.py:84-92), fs <= 15, H*W <= 4096.  Per plane:
+ *   mse_mean[p]  = mean((pred - target)^2),
+ *   ssim_mean[p] = mean over the (H-fs+1) x (W-fs+1) valid window positions of the SSIM index,
+ *   ssim_map (may be NULL): that map, [planes][H-fs+1][W-fs+1]. */
+int vs_ssim_mse_planes(const float* pred, const float* target, int64_t planes, int32_t H, int32_t W, const float* kernel,
+                       int32_t fs, float c1, float c2, float* ssim_map, float* ssim_mean, float* mse_mean, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -367,3 +367,25 @@ _orig_pointer_array = L.pointer_array
 def _emu_pointer_array(tensors):
     _register(tensors)
     return [t.data_ptr() for t in tensors]
+
+
+# ---- evaluation metrics (appended after _TABLE is built: registered explicitly) -----------------------
+def vs_ssim_mse_planes(pred, target, planes, H, W, kernel, fs, c1, c2, ssim_map, ssim_mean, mse_mean, stream):
+    """utils/ssim.py:95-116 on `planes` single-channel images + the per-plane mean squared error."""
+    import torch.nn.functional as F
+    x = pred.reshape(-1)[:planes * H * W].reshape(planes, 1, H, W).float()
+    y = target.reshape(-1)[:planes * H * W].reshape(planes, 1, H, W).float()
+    k = kernel.reshape(-1)[:fs * fs].reshape(1, 1, fs, fs).float()
+    mu1, mu2 = F.conv2d(x, k), F.conv2d(y, k)
+    s11 = F.conv2d(x * x, k) - mu1 ** 2
+    s22 = F.conv2d(y * y, k) - mu2 ** 2
+    s12 = F.conv2d(x * y, k) - mu1 * mu2
+    v1, v2 = 2 * s12 + c2, s11 + s22 + c2
+    ssim = ((2 * mu1 * mu2 + c1) * v1) / ((mu1 ** 2 + mu2 ** 2 + c1) * v2)
+    if ssim_map is not None:
+        ssim_map.reshape(-1)[:ssim.numel()].copy_(ssim.reshape(-1))
+    ssim_mean.reshape(-1)[:planes].copy_(ssim.mean(dim=(1, 2, 3)))
+    mse_mean.reshape(-1)[:planes].copy_(((x - y) ** 2).mean(dim=(1, 2, 3)))
+
+
+_TABLE['vs_ssim_mse_planes'] = vs_ssim_mse_planes
