@@ -9,57 +9,68 @@ from .resnet import MLPResnet, ConvResnet
 from .utils import init_net
 
 
-def get_encoder(nn_type, shape, output_size, hidden_size, n_layers, nt_cond, init_type, init_gain):
+def _flat_size(shape, nt_cond):
+    return int(nt_cond * np.prod(np.array(shape)))
+
+
+# architecture name -> (allowed image sizes or None, constructor from the factory arguments)
+_ENCODERS = {
+    'dcgan': ((64,), lambda nc, dim, a: DCGAN64Encoder(nc * a['nt_cond'], a['output_size'], a['hidden_size'])),
+    'vgg': ((32, 64), lambda nc, dim, a: VGG64Encoder(nc * a['nt_cond'], a['output_size'], a['hidden_size'], vgg32=dim == 32)),
+    'resnet': (None, lambda nc, dim, a: ResNet18(a['output_size'], nc * a['nt_cond'])),
+    'encoderSST': (None, lambda nc, dim, a: EncoderSST(nc * a['nt_cond'], a['output_size'])),
+    'mlp': (None, lambda nc, dim, a: MLPEncoder(_flat_size(a['shape'], a['nt_cond']), a['hidden_size'], a['output_size'],
+                                                a['n_layers'])),
+}
+_DECODERS = {
+    'dcgan': ((64,), lambda nc, dim, a: DCGAN64Decoder(nc, a['input_size'], a['hidden_size'], a['skipco'], a['last_activation'],
+                                                       a['mixing'])),
+    'vgg': ((32, 64), lambda nc, dim, a: VGG64Decoder(nc, a['input_size'], a['hidden_size'], a['skipco'], a['last_activation'],
+                                                      a['mixing'], vgg32=dim == 32)),
+    'mlp': (None, lambda nc, dim, a: MLPDecoder(a['input_size'], a['hidden_size'], a['shape'], a['n_layers'],
+                                                a['last_activation'], a['mixing'])),
+    'decoderSST': (None, lambda nc, dim, a: (DecoderSST_Skip if a['skipco'] else DecoderSST)(a['input_size'], nc,
+                                                                                             a['last_activation'])),
+}
+_SKIPCO_DECODERS = ('dcgan', 'vgg', 'decoderSST')
+
+
+def _build(table, kind, nn_type, shape, args):
+    if nn_type not in table:
+        raise ValueError(f'unknown {kind} architecture `{nn_type}`')
+    sizes, make = table[nn_type]
     nc, dim = shape[0], shape[-1]
-    if nn_type == 'dcgan':
-        assert dim == 64
-        encoder = DCGAN64Encoder(nc * nt_cond, output_size, hidden_size)
-    elif nn_type == 'vgg':
-        assert dim in [32, 64]
-        encoder = VGG64Encoder(nc * nt_cond, output_size, hidden_size, vgg32=dim == 32)
-    elif nn_type == 'resnet':
-        encoder = ResNet18(output_size, nc * nt_cond)
-    elif nn_type == 'encoderSST':
-        encoder = EncoderSST(nc * nt_cond, output_size)
-    elif nn_type == 'mlp':
-        encoder = MLPEncoder(int(nt_cond * np.prod(np.array(shape))), hidden_size, output_size, n_layers)
-    else:
-        raise ValueError(f'unknown encoder architecture `{nn_type}`')
+    assert sizes is None or dim in sizes                                  # factory.py:29,33,60,64
+    return make(nc, dim, args)
+
+
+def get_encoder(nn_type, shape, output_size, hidden_size, n_layers, nt_cond, init_type, init_gain):
+    """factory.py:25-44."""
+    encoder = _build(_ENCODERS, 'encoder', nn_type, shape,
+                     dict(shape=shape, output_size=output_size, hidden_size=hidden_size, n_layers=n_layers, nt_cond=nt_cond))
     init_net(encoder, init_type=init_type, init_gain=init_gain)
     return encoder
 
 
 def get_decoder(nn_type, shape, code_size_t, code_size_s, last_activation, hidden_size, n_layers, mixing, skipco,
                 init_type, init_gain):
-    assert not skipco or nn_type in ['dcgan', 'vgg', 'decoderSST']
+    """factory.py:47-76: skip connections only for the architectures that consume them, `mul` mixing needs equal code
+    sizes, the SST decoder concatenates feature maps."""
+    assert not skipco or nn_type in _SKIPCO_DECODERS                       # factory.py:49
     if mixing == 'mul':
-        assert code_size_t == code_size_s
-        input_size = code_size_t
-    else:
-        input_size = code_size_t + code_size_s
-    nc, dim = shape[0], shape[-1]
-    if nn_type == 'dcgan':
-        assert dim == 64
-        decoder = DCGAN64Decoder(nc, input_size, hidden_size, skipco, last_activation, mixing)
-    elif nn_type == 'vgg':
-        assert dim in [32, 64]
-        decoder = VGG64Decoder(nc, input_size, hidden_size, skipco, last_activation, mixing, vgg32=dim == 32)
-    elif nn_type == 'mlp':
-        decoder = MLPDecoder(input_size, hidden_size, shape, n_layers, last_activation, mixing)
-    elif nn_type == 'decoderSST':
-        assert mixing == 'concat'
-        decoder = (DecoderSST_Skip if skipco else DecoderSST)(input_size, nc, last_activation)
-    else:
-        raise ValueError(f'unknown decoder architecture `{nn_type}`')
+        assert code_size_t == code_size_s                                  # factory.py:52
+    input_size = code_size_t if mixing == 'mul' else code_size_t + code_size_s
+    assert nn_type != 'decoderSST' or mixing == 'concat'                    # factory.py:68
+    decoder = _build(_DECODERS, 'decoder', nn_type, shape,
+                     dict(shape=shape, input_size=input_size, hidden_size=hidden_size, n_layers=n_layers, mixing=mixing,
+                          skipco=skipco, last_activation=last_activation))
     init_net(decoder, init_type=init_type, init_gain=init_gain)
     return decoder
 
 
 def get_resnet(latent_size, n_blocks, hidden_size, init_type, gain_res, fully_conv=False):
-    if fully_conv:
-        resnet = ConvResnet(latent_size, n_blocks=n_blocks, nf=hidden_size)
-    else:
-        resnet = MLPResnet(latent_size, n_blocks, hidden_size)
+    """factory.py:79-87: the latent time-stepper, convolutional for feature-map codes (SST)."""
+    resnet = ConvResnet(latent_size, n_blocks=n_blocks, nf=hidden_size) if fully_conv else MLPResnet(latent_size, n_blocks, hidden_size)
     init_net(resnet, init_type=init_type, init_gain=gain_res)
     return resnet
 

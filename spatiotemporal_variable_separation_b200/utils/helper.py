@@ -58,10 +58,17 @@ def load_training_state(elem_xp_path, optimizer, scheduler=None):
 
 
 class DotDict(dict):
-    """Dot access to dictionary entries (helper.py:54-60)."""
-    __getattr__ = dict.get
-    __setattr__ = dict.__setitem__
-    __delattr__ = dict.__delitem__
+    """Dictionary whose entries can also be read, set and deleted as attributes; a missing key reads as None
+    (same behaviour as the class of that name in helper.py:54-60)."""
+
+    def __getattr__(self, key):
+        return self.get(key)
+
+    def __setattr__(self, key, value):
+        self[key] = value
+
+    def __delattr__(self, key):
+        del self[key]
 
 
 def load_json(path):

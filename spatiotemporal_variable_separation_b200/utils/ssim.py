@@ -11,11 +11,13 @@ from .._lib import ptr
 
 
 def _fspecial_gaussian(size, channel, sigma):
-    """ssim.py:84-92 — softmax of the negative squared distances: a normalised Gaussian window, one copy per channel."""
-    coords = torch.tensor([(x - (size - 1.) / 2.) for x in range(size)])
-    coords = -coords ** 2 / (2. * sigma ** 2)
-    grid = (coords.view(1, -1) + coords.view(-1, 1)).view(1, -1).softmax(-1)
-    return grid.view(1, 1, size, size).expand(channel, 1, size, size).contiguous()
+    """Normalised size x size Gaussian window (the window ssim.py:84-92 builds as a softmax of negative squared
+    distances), one copy per channel: [channel, 1, size, size]."""
+    offsets = torch.arange(size, dtype=torch.float32) - (size - 1) / 2.0
+    g = torch.exp(-offsets.pow(2) / (2.0 * sigma ** 2))
+    window = torch.outer(g, g)
+    window = window / window.sum()
+    return window.expand(channel, 1, size, size).contiguous()
 
 
 def plane_metrics(input, target, max_val, filter_size=11, k1=0.01, k2=0.03, sigma=1.5, kernel=None, want_map=False):
