@@ -117,7 +117,7 @@ def two_real_steps(cfg):
     return out
 
 
-def generate(name, small=True, extra='', tag=None):
+def generate(name, small=True, extra='', tag=None, subdir=None):
     cfg = configs.preset(name, small=small, extra=extra)
     if tag:
         cfg['name'] = tag
@@ -140,13 +140,28 @@ def generate(name, small=True, extra='', tag=None):
         grad64=np.stack([grad64[k] for k in gnames]),
         after2_names=np.array(anames), after2=np.stack([after2[k] for k in anames]),
     )
-    path = os.path.join(HERE, cfg['name'] + '.npz')
+    out_dir = os.path.join(HERE, subdir) if subdir else HERE
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, cfg['name'] + '.npz')
     np.savez_compressed(path, **out)
     print(f'{cfg["name"]}: losses {loss32}  ->  {path} ({os.path.getsize(path) / 1024:.0f} KiB)')
 
 
+# flag combinations beyond the BASELINE configurations (host-logic / oracle coverage on the CPU: tests/golden/extra/)
+EXTRA = [
+    ('mnist', '--architecture vgg --nt_pred 3', 'mnist-small-vgg64'),                     # VGG on 64x64 frames (vgg32=False)
+    ('wave', '--mixing concat --code_size_s 20 --n_blocks 1', 'wave-small-concat'),       # MLP encoder/decoder, concat mixing
+    ('chairs', '--architecture dcgan --n_blocks 3 --offset 0 --mixing mul --code_size_s 10', 'chairs-small-dcgan-mul'),
+    ('taxibj', '--skipco --nt_pred 2', 'taxibj-small-skipco'),                             # VGG skip connections at 32x32
+]
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
+    if sys.argv[1:] == ['--extra']:
+        for n, extra, tag in EXTRA:
+            generate(n, small=True, extra=extra, tag=tag, subdir='extra')
+        sys.exit(0)
     which = sys.argv[1:] or ['mnist', 'wave', 'taxibj', 'sst', 'chairs']
     for n in which:
         generate(n, small=True)

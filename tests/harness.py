@@ -17,6 +17,11 @@ def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
 
 
+def extra_golden_names():
+    """Flag combinations beyond the BASELINE configurations (tests/golden/extra/, CPU checks only so far)."""
+    return sorted('extra/' + os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, 'extra', '*.npz')))
+
+
 def load_golden(name):
     g = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False))
     g['cfg'] = json.loads(str(g['cfg']))

@@ -35,6 +35,7 @@ from tests import emu, harness
 from tests.summ import summarize, subsample, rel_err
 
 NAMES = harness.golden_names()
+EXTRA_NAMES = harness.extra_golden_names()      # more of the flag space; the GPU suite keeps to NAMES
 
 
 def build_filled(cfg, device='cpu'):
@@ -78,7 +79,7 @@ def check_against_golden(g, out, grads, rtol_loss=2e-5, rtol_grad=2e-4, kink=KIN
     return worst
 
 
-@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('name', NAMES + EXTRA_NAMES)
 def test_step_matches_reference_golden(name):
     g = harness.load_golden(name)
     cfg = g['cfg']

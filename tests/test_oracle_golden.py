@@ -15,13 +15,14 @@ from tests import harness
 from tests.summ import summarize, subsample, rel_err
 
 NAMES = harness.golden_names()
+ALL_NAMES = NAMES + harness.extra_golden_names()
 
 
 def test_goldens_exist():
     assert {'mnist-small', 'wave-small', 'taxibj-small', 'sst-small', 'chairs-small'} <= set(NAMES)
 
 
-@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('name', ALL_NAMES)
 def test_state_dict_layout_matches_reference(name):
     g = harness.load_golden(name)
     ours = shapes.model_shapes(g['cfg'])
@@ -32,7 +33,7 @@ def test_state_dict_layout_matches_reference(name):
             assert list(ours[part][k]) == ref[k], (part, k)
 
 
-@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('name', ALL_NAMES)
 def test_losses_forecasts_and_grads(name):
     g = harness.load_golden(name)
     cfg = g['cfg']
@@ -54,7 +55,7 @@ def test_losses_forecasts_and_grads(name):
         assert np.all(np.abs(s - ref) <= 5e-5 * np.abs(ref[0]) + 1e-6 * gmax), (n, s, ref)
 
 
-@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('name', ALL_NAMES)
 def test_two_adam_steps_match_reference_train_loop(name):
     g = harness.load_golden(name)
     cfg = g['cfg']
