@@ -292,6 +292,45 @@ def _grad_buffer(p):
     return z, z
 
 
+# ------------------------------------------------------------------------------------------------
+# inference-time BatchNorm folding (opt-in)
+# ------------------------------------------------------------------------------------------------
+_fold_eval_bn = False
+
+
+def set_eval_bn_folding(flag):
+    """In ``eval()`` mode under ``torch.no_grad()`` BatchNorm uses fixed running statistics, so
+    ``act(BN(conv(x)))`` == ``act(conv'(x))`` with  w' = w * s,  b' = (b - running_mean) * s + beta,
+    s = gamma / sqrt(running_var + eps)  per output channel: one launch (conv with fused bias + activation)
+    instead of three, and the pre-BatchNorm tensor is never written.  Off by default: the folded weights round
+    differently (1e-6 class in fp32), and it has not been timed yet."""
+    global _fold_eval_bn
+    _fold_eval_bn = bool(flag)
+
+
+def _folded_conv(conv, bn, kind):
+    """Persistent folded (weight, bias) of a conv + eval-mode BatchNorm pair, refreshed when any input changes."""
+    w, b = conv.weight, conv.bias
+    tag = (w._version, w.data_ptr(), None if b is None else b._version, bn.weight._version, bn.bias._version,
+           bn.running_mean._version, bn.running_var._version, _pack_epoch)
+    hit = bn.__dict__.get('_vs_fold')
+    if hit is not None and hit[0] == tag:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        s = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+        oc_dim = 1 if kind == 'convT' else 0                    # ConvTranspose weights are [C_in, C_out, kh, kw]
+        shape = [1] * w.dim()
+        shape[oc_dim] = -1
+        wf = w.detach().float() * s.view(shape)
+        bf = (-bn.running_mean.float() if b is None else b.detach().float() - bn.running_mean.float()) * s + bn.bias.float()
+        if hit is not None and hit[1].shape == wf.shape:        # keep the tensors (and their packed copies' cache keys)
+            hit[1].copy_(wf)
+            hit[2].copy_(bf)
+            wf, bf = hit[1], hit[2]
+    bn.__dict__['_vs_fold'] = (tag, wf, bf)
+    return wf, bf
+
+
 def conv_block(x, conv, bn=None, act=None, kind='conv', groups=1, wshape=None, flags=0):
     """Run ``conv`` (nn.Conv2d / nn.ConvTranspose2d / nn.Linear used as parameter containers)
     followed by the optional BatchNorm module ``bn`` and activation name ``act`` on NHWC ``x``."""
@@ -305,6 +344,10 @@ def conv_block(x, conv, bn=None, act=None, kind='conv', groups=1, wshape=None, f
     stride = conv.stride[0] if hasattr(conv, 'stride') else 1
     pad = conv.padding[0] if hasattr(conv, 'padding') else 0
     training = bool(bn.training) if bn is not None else False
+    if bn is not None and not training and _fold_eval_bn and not torch.is_grad_enabled():
+        wf, bf = _folded_conv(conv, bn, kind)
+        cfg = ConvCfg(kind, K, C, R, S, stride, pad, act, 1, False, False, 0.0, 0.0, flags)
+        return ConvBlockFn.apply(x, wf, bf, None, None, None, None, None, cfg)
     cfg = ConvCfg(kind, K, C, R, S, stride, pad, act, groups, training, bn is not None,
                   bn.eps if bn is not None else 0.0, bn.momentum if bn is not None else 0.0, flags)
     if bn is not None:

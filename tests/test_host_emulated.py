@@ -287,3 +287,33 @@ def test_eval_rollout_and_content_swap(name):
     with emu.install():
         net = build_filled(g['cfg']).eval()
         harness.check_eval_rollout(g, net, g['cfg']['skipco'])
+
+
+@pytest.mark.parametrize('name', ['mnist-small', 'taxibj-small', 'sst-small', 'chairs-small', 'mnist-small-skipco'])
+def test_eval_bn_folding_matches_reference_rollout(name):
+    """Opt-in inference path: BatchNorm folded into the convolution weights (ops.set_eval_bn_folding) gives the
+    reference's eval rollout / content swap (2e-5), refreshes when a parameter or running statistic changes, and leaves
+    the training-mode path alone."""
+    g = harness.load_eval_golden(name)
+    ops.set_compute_dtype(torch.float32)
+    with emu.install():
+        net = build_filled(g['cfg']).eval()
+        cond, _ = harness.inputs(g['cfg'])
+        with torch.no_grad():
+            plain = net.get_forecast(cond, 3)[0]
+        ops.set_eval_bn_folding(True)
+        try:
+            harness.check_eval_rollout(g, net, g['cfg']['skipco'])
+            with torch.no_grad():
+                folded = net.get_forecast(cond, 3)[0]
+                assert float((folded - plain).abs().max()) < 2e-5 * float(plain.abs().max()) + 1e-6
+                # a changed running statistic must be picked up (version counters are part of the cache tag)
+                bns = [m for m in net.decoder.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+                bns[0].running_mean.add_(0.25)
+                moved = net.get_forecast(cond, 3)[0]
+                ops.set_eval_bn_folding(False)
+                want = net.get_forecast(cond, 3)[0]
+                assert float((moved - folded).abs().max()) > 1e-4
+                assert float((moved - want).abs().max()) < 2e-5 * float(want.abs().max()) + 1e-6
+        finally:
+            ops.set_eval_bn_folding(False)
