@@ -184,9 +184,11 @@ int vs_loss_combine(const double* acc, const double* coef_host, const double* la
  * replaces: torch.optim.Adam.step (main.py:145, train.py:162): eps-outside-sqrt, bias-corrected, no decay.
  * One launch over a flat, 16-byte aligned parameter arena.  The 1-based step count is step_host, or
  * *step_dev when step_dev != NULL (device-resident counter: keeps a captured CUDA graph replayable).
- * grad is multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+ * grad is multiplied by grad_scale first (1/world_size after a sum all-reduce).  The learning rate is lr, or
+ * *lr_dev when lr_dev != NULL (device-resident: MultiStepLR, main.py:146-147, then needs no graph re-capture). */
 int vs_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
-                 float beta2, float eps, float grad_scale, int32_t step_host, const int32_t* step_dev, void* stream);
+                 float beta2, float eps, float grad_scale, int32_t step_host, const int32_t* step_dev,
+                 const float* lr_dev, void* stream);
 
 /* ---- latent rollout ------------------------------------------------------------------------
  * replaces: the loop of model.py:78-83 over MLPResnet.forward (resnet.py:42-50, mlp.py:66-71):

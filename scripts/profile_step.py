@@ -17,14 +17,16 @@ ap.add_argument('--steps', type=int, default=1)
 args = ap.parse_args()
 cfg = configs.preset(args.config)
 dev = torch.device('cuda', 0)
-tr = bench.Trainer(cfg, dev, torch.bfloat16 if args.dtype == 'bf16' else torch.float32, 1, False)
-tr.full.copy_(synthetic_batch(cfg, device=dev))
+tr = bench.build_trainer(cfg, dev, torch.bfloat16 if args.dtype == 'bf16' else torch.float32, 1, False)
+full = synthetic_batch(cfg, device=dev)
+tr.input_buffer(full.shape, dev).copy_(full)
+t_random = cfg['nt_cond'] + 2
 for _ in range(2):
-    tr.step(7)
+    tr.run(full.shape, t_random)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 for _ in range(args.steps):
-    tr.step(7)
+    tr.run(full.shape, t_random)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print('profiled', args.steps, 'step(s)')

@@ -370,10 +370,12 @@ __global__ void loss_combine_kernel(const double* __restrict__ acc, CombineArgs 
 // torch.optim.Adam single-tensor math (eps outside the bias-corrected sqrt)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float b1, float b2, float eps, float lr,
-                            float grad_scale, int step_host, const int* __restrict__ step_dev) {
+                            float grad_scale, int step_host, const int* __restrict__ step_dev,
+                            const float* __restrict__ lr_dev) {
     // bias corrections in fp64 from the (host or device-resident) step count; a device counter keeps a
     // captured CUDA graph valid across replays
     const int step = step_dev ? *step_dev : step_host;
+    if (lr_dev) lr = *lr_dev;               // device-resident learning rate: a schedule does not invalidate a captured graph
     const float step_size = (float)((double)lr / (1.0 - pow((double)b1, (double)step)));
     const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, (double)step)));
     const long long n4 = n >> 2;
@@ -576,12 +578,12 @@ extern "C" int vs_loss_combine(const double* acc, const double* coef_host, const
 
 extern "C" int vs_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
                             float beta2, float eps, float grad_scale, int32_t step_host, const int32_t* step_dev,
-                            void* stream) {
+                            const float* lr_dev, void* stream) {
     VS_REQUIRE(step_dev != nullptr || step_host >= 1, "adam_step: step must be >= 1");
     VS_REQUIRE((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) |
                 reinterpret_cast<uintptr_t>(v)) % 16 == 0, "adam_step: arenas must be 16-byte aligned");
     if (n == 0) return 0;
     int blocks = ew_grid(cdiv(n, 4));
-    adam_kernel<<<blocks, 256, 0, S_>>>(param, grad, m, v, n, beta1, beta2, eps, lr, grad_scale, step_host, step_dev);
+    adam_kernel<<<blocks, 256, 0, S_>>>(param, grad, m, v, n, beta1, beta2, eps, lr, grad_scale, step_host, step_dev, lr_dev);
     return launched("adam_kernel");
 }

@@ -28,16 +28,27 @@ def compute_dtype():
 
 # ------------------------------------------------------------------------------------------------
 # packed-weight cache.  Kernels read weights as [OC][taps][IC] in the compute dtype; the fp32
-# torch parameter stays the master copy.  Entries live on the parameter object and are invalidated by
-# the tensor version counter or by ``invalidate_packed()`` (called after the fused Adam step, which
-# writes through raw pointers and therefore does not bump version counters).
+# torch parameter stays the master copy.  Every cache entry lives on the parameter object itself
+# (``w.__dict__``), so it dies with the module; nothing process-global refers to a parameter.  An
+# entry is current while its tag (tensor version counter, address, per-parameter epoch) matches;
+# ``invalidate_params`` bumps the epoch of the parameters an optimizer has just written through raw
+# pointers (the fused Adam step does not bump version counters).
 # ------------------------------------------------------------------------------------------------
-_pack_epoch = 0
+_PACK_ROWS_PER_LAUNCH = 1024            # rows of the table one vs_pack_weights_multi launch keeps in shared memory
 
 
-def invalidate_packed():
-    global _pack_epoch
-    _pack_epoch += 1
+def _epoch(t):
+    return t.__dict__.get('_vs_epoch', 0) if t is not None else 0
+
+
+def _tag(w):
+    return (w._version, w.data_ptr(), _epoch(w))
+
+
+def invalidate_params(params):
+    """Mark every packed / padded / folded copy derived from ``params`` stale."""
+    for p in params:
+        p.__dict__['_vs_epoch'] = p.__dict__.get('_vs_epoch', 0) + 1
 
 
 def packed_weight(w, K, C, RS, swap, dtype):
@@ -45,24 +56,14 @@ def packed_weight(w, K, C, RS, swap, dtype):
     the module and can never alias another tensor that later reuses the same address)."""
     cache = w.__dict__.setdefault('_vs_pack', {})
     key = (K, C, RS, bool(swap), dtype)
-    tag = (w._version, w.data_ptr(), _pack_epoch)
+    tag = _tag(w)
     hit = cache.get(key)
     if hit is not None and hit[0] == tag:
         return hit[1]
     out = hit[1] if hit is not None else torch.empty(K * C * RS, device=w.device, dtype=dtype)
     L.call('vs_pack_weight', ptr(w), ptr(out), L.dtype_code(out), K, C, RS, int(swap), L.stream())
     cache[key] = (tag, out)
-    if hit is None:
-        _pack_registry.append((w, key, out))
-        _pack_table.clear()
     return out
-
-
-# every (parameter, layout) pair that has ever been packed; lets the optimizer refresh all of them in one launch
-_pack_registry = []
-_pack_table = {}
-# (parameter, zero-padded shadow) pairs, see ``padded_rows``
-_pad_registry = []
 
 
 def padded_rows(w, Kp):
@@ -71,48 +72,57 @@ def padded_rows(w, Kp):
     is not a multiple of 8 (the decoder's first up-convolution reads the 148-channel [S|T] code) runs on the
     tensor cores with zero input channels appended; the packed copies are made from this shadow."""
     hit = w.__dict__.get('_vs_padrows')
-    tag = (w._version, w.data_ptr(), _pack_epoch)
+    tag = _tag(w)
     if hit is not None and hit[0].shape[0] == Kp:
         if hit[1] != tag:
             hit[0][:w.shape[0]].copy_(w.detach())
+            invalidate_params([hit[0]])
             w.__dict__['_vs_padrows'] = (hit[0], tag)
         return hit[0]
     shadow = torch.zeros((Kp,) + tuple(w.shape[1:]), device=w.device, dtype=torch.float32)
     shadow[:w.shape[0]].copy_(w.detach())
     w.__dict__['_vs_padrows'] = (shadow, tag)
-    _pad_registry.append((w, shadow))
     return shadow
 
 
-def _refresh_padded():
-    for w, shadow in _pad_registry:
-        if w.is_cuda and shadow.device == w.device:
-            shadow[:w.shape[0]].copy_(w.detach())
-            w.__dict__['_vs_padrows'] = (shadow, (w._version, w.data_ptr(), _pack_epoch))
-
-
-def repack_all():
-    """Refresh every known packed copy with ONE kernel (called by FusedAdam.step after the arena update) and mark
-    them current, so the next step's forward / backward find cache hits instead of ~30 small pack launches."""
+def repack_params(params, cache):
+    """Refresh every packed copy that exists for ``params`` (and for their zero-padded shadows) with one kernel launch
+    per 1024 table rows, and mark them current, so that the next step's forward / backward find cache hits instead of
+    ~30 small pack launches.  Called by ``FusedAdam.step`` with the optimizer's OWN parameters; ``cache`` is a dict the
+    caller keeps (the device-resident table lives as long as the optimizer, not as long as the process)."""
     import struct
-    _refresh_padded()
-    live = [(w, key, out) for (w, key, out) in _pack_registry if w.is_cuda]
+    live = []
+    for p in params:
+        if not p.is_cuda:
+            continue
+        pad = p.__dict__.get('_vs_padrows')
+        if pad is not None:
+            shadow = pad[0]
+            shadow[:p.shape[0]].copy_(p.detach())
+            p.__dict__['_vs_padrows'] = (shadow, _tag(p))
+            for key, (_, out) in shadow.__dict__.get('_vs_pack', {}).items():
+                live.append((shadow, key, out))
+        for key, (_, out) in p.__dict__.get('_vs_pack', {}).items():
+            live.append((p, key, out))
     if not live:
         return
-    if 'table' not in _pack_table:
-        rows, first = [], 0
-        for w, (K, C, RS, swap, dtype), out in live:
-            rows.append(struct.pack('<QQiiiiii', w.data_ptr(), out.data_ptr(), K, C, RS, int(swap),
-                                    L.VS_F32 if dtype == torch.float32 else L.VS_BF16, first))
-            first += (K * C * RS + 1023) // 1024
-        blob = torch.frombuffer(bytearray(b''.join(rows)), dtype=torch.uint8).to(live[0][0].device)
-        _pack_table.update(table=blob, n=len(rows), blocks=first, ptrs=[(w.data_ptr(), out.data_ptr()) for w, _, out in live])
-    elif _pack_table['ptrs'] != [(w.data_ptr(), out.data_ptr()) for w, _, out in live]:
-        _pack_table.clear()
-        return repack_all()
-    L.call('vs_pack_weights_multi', ptr(_pack_table['table']), _pack_table['n'], _pack_table['blocks'], L.stream())
+    ptrs = [(w.data_ptr(), out.data_ptr()) for w, _, out in live]
+    if cache.get('ptrs') != ptrs:
+        launches = []
+        for lo in range(0, len(live), _PACK_ROWS_PER_LAUNCH):
+            rows, first = [], 0
+            for w, (K, C, RS, swap, dtype), out in live[lo:lo + _PACK_ROWS_PER_LAUNCH]:
+                rows.append(struct.pack('<QQiiiiii', w.data_ptr(), out.data_ptr(), K, C, RS, int(swap),
+                                        L.VS_F32 if dtype == torch.float32 else L.VS_BF16, first))
+                first += (K * C * RS + 1023) // 1024
+            blob = torch.frombuffer(bytearray(b''.join(rows)), dtype=torch.uint8).to(live[0][0].device)
+            launches.append((blob, len(rows), first))
+        cache.clear()
+        cache.update(ptrs=ptrs, launches=launches)
+    for blob, n, blocks in cache['launches']:
+        L.call('vs_pack_weights_multi', ptr(blob), n, blocks, L.stream())
     for w, key, out in live:
-        w.__dict__['_vs_pack'][key] = ((w._version, w.data_ptr(), _pack_epoch), out)
+        w.__dict__['_vs_pack'][key] = (_tag(w), out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -311,8 +321,8 @@ def set_eval_bn_folding(flag):
 def _folded_conv(conv, bn, kind):
     """Persistent folded (weight, bias) of a conv + eval-mode BatchNorm pair, refreshed when any input changes."""
     w, b = conv.weight, conv.bias
-    tag = (w._version, w.data_ptr(), None if b is None else b._version, bn.weight._version, bn.bias._version,
-           bn.running_mean._version, bn.running_var._version, _pack_epoch)
+    tag = (_tag(w), None if b is None else _tag(b), _tag(bn.weight), _tag(bn.bias),
+           bn.running_mean._version, bn.running_var._version)
     hit = bn.__dict__.get('_vs_fold')
     if hit is not None and hit[0] == tag:
         return hit[1], hit[2]

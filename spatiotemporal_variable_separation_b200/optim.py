@@ -36,6 +36,9 @@ class FusedAdam:
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        # the learning rate the kernel reads: device-resident so that a captured CUDA graph follows a schedule
+        self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+        self._lr_uploaded = float(lr)
         self.grad_scale = 1.0
         with torch.no_grad():
             for p, off in zip(self.params, self.offsets):
@@ -46,7 +49,8 @@ class FusedAdam:
                 g = self.flat_g[off:off + n].view(p.shape)
                 p.grad = g
                 p._vs_grad = g
-        ops.invalidate_packed()
+        ops.invalidate_params(self.params)
+        self._pack_cache = {}
 
     # torch.optim-like surface used by train()
     @property
@@ -72,12 +76,24 @@ class FusedAdam:
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
 
+    def sync_lr(self):
+        """Upload the host learning rate if a scheduler changed it (one 4-byte fill; never inside a graph capture, where
+        the value would be baked in — ``train.GraphedStep`` calls this before every replay instead)."""
+        if self._lr_uploaded != self.lr:
+            self.lr_dev.fill_(self.lr)
+            self._lr_uploaded = self.lr
+
     def step(self):
+        if not (self.flat_p.is_cuda and torch.cuda.is_current_stream_capturing()):
+            self.sync_lr()
         self.step_dev += 1
         L.call('vs_adam_step', ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.numel,
-             self.lr, self.betas[0], self.betas[1], self.eps, float(self.grad_scale), 0, ptr(self.step_dev), L.stream())
-        ops.invalidate_packed()
-        ops.repack_all()
+             self.lr, self.betas[0], self.betas[1], self.eps, float(self.grad_scale), 0, ptr(self.step_dev),
+             ptr(self.lr_dev), L.stream())
+        # the kernel wrote the weights through raw pointers: every packed copy of OUR parameters is stale now; refresh
+        # the ones that exist in one launch (a table owned by this optimizer — no process-global registry)
+        ops.invalidate_params(self.params)
+        ops.repack_params(self.params, self._pack_cache)
 
     def grad_of(self, p):
         return p._vs_grad
@@ -124,7 +140,7 @@ class FusedAdam:
 class MultiStepLR:
     """``torch.optim.lr_scheduler.MultiStepLR`` (main.py:146-147) for ``FusedAdam``: lr = initial_lr * gamma^(number of
     milestones reached), one ``step()`` per epoch (train.py:166-167).  Works on any object with ``param_groups``.
-    (A captured CUDA graph bakes the learning rate in: re-capture after a change.)"""
+    (``FusedAdam`` reads the learning rate from device memory, so a captured CUDA graph follows the schedule.)"""
 
     def __init__(self, optimizer, milestones, gamma=0.1, last_epoch=0):
         self.optimizer, self.milestones, self.gamma = optimizer, sorted(int(m) for m in milestones), float(gamma)

@@ -105,7 +105,9 @@ def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, l
     tensors = [recon, supervision, forecasts, target, t0] + olds + news
     k = len(olds)
     n_s = sum(t.numel() for t in olds)
-    t_coef = 0.5 / t0.numel() if average_tloss else 0.5 / B                          # train.py:145-148
+    # train.py:145-148: mean over everything, or sum over dim 1 (channels) then mean over the rest — for flat codes the
+    # latter is 0.5/B, for feature-map codes [B,C,H,W] it is 0.5/(B*H*W)
+    t_coef = 0.5 / t0.numel() if average_tloss else 0.5 * t_cond.shape[-1] / t0.numel()
     spec = [(1.0 / recon.numel(), lamb_ae, [(0, 1)]),
             (1.0 / n_s, lamb_s, [(5 + i, 5 + k + i) for i in range(k)]),
             (1.0 / forecasts.numel(), lamb_pred, [(2, 3)]),
@@ -135,28 +137,179 @@ def _loss_operand(h):
     return ops.to_external(h.reshape(-1, *h.shape[-3:]))
 
 
+class GraphedStep:
+    """One whole training step — ``zero_grad`` + the objective of train.py:116-149 + ``backward`` + (data-parallel)
+    gradient all-reduce + fused Adam — replayed as a captured CUDA graph.
+
+    The only host-side decision inside a step is the draw ``t_random`` (train.py:72-75), which selects frame windows,
+    so there is one graph per (batch shape, t_random) — at most ``nt_pred + 1`` per shape, all sharing one memory pool
+    and one static input buffer per shape.  Everything else a step mutates lives in device memory the graph addresses
+    directly: the parameter / gradient / moment arenas of ``FusedAdam``, its step counter and **learning rate**
+    (``MultiStepLR`` therefore needs no re-capture), BatchNorm running statistics and ``num_batches_tracked``.
+
+    ``graph=False`` runs the same body eagerly (debugging, or shapes seen once)."""
+
+    def __init__(self, sep_net, optimizer, nt_cond, nt_pred, offset, skipco, lamb_ae, lamb_s, lamb_t, lamb_pred,
+                 average_tloss=False, reducer=None, graph=True, overlap_encoders=True):
+        self.net, self.opt, self.reducer = sep_net, optimizer, reducer
+        self.args = (nt_cond, nt_pred, offset, skipco, lamb_ae, lamb_s, lamb_t, lamb_pred, average_tloss)
+        self.nt_cond, self.nt_pred, self.offset = nt_cond, nt_pred, offset
+        self.graph, self.overlap_encoders = bool(graph), overlap_encoders
+        self.inputs, self.terms, self.graphs, self.pool = {}, {}, {}, None
+        self.dtype = ops.compute_dtype()                         # the graphs bake the compute dtype in
+
+    # ---- static buffers ------------------------------------------------------------------------------------
+    def input_buffer(self, shape, device):
+        """The static [B, nt_cond+nt_pred, C, H, W] fp32 buffer the graphs of this batch shape read."""
+        key = tuple(shape)
+        if key not in self.inputs:
+            self.inputs[key] = torch.zeros(key, device=device, dtype=torch.float32)
+            self.terms[key] = torch.zeros(5, device=device, dtype=torch.float32)
+        return self.inputs[key]
+
+    def _body(self, key, t_random):
+        self.opt.zero_grad()
+        out = step_losses(self.net, self.inputs[key], *self.args, t_random=t_random, reducer=self.reducer,
+                          overlap_encoders=self.overlap_encoders)
+        out['total'].backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.opt.step()
+        self.terms[key].copy_(out['terms'].detach())
+
+    # ---- one step ---------------------------------------------------------------------------------------------
+    def run(self, shape, t_random=None):
+        """Step on whatever the static input buffer of ``shape`` holds.  Returns the static 5-vector
+        [ae, s, pred, t, total] (device memory, overwritten by the next step of this shape)."""
+        key = tuple(shape)
+        if t_random is None:
+            t_random = draw_t_random(self.nt_cond, key[1], self.offset)
+        prev = ops.compute_dtype()
+        ops.set_compute_dtype(self.dtype)
+        try:
+            if not self.graph:
+                self._body(key, t_random)
+                return self.terms[key]
+            g = self.graphs.get((key, t_random))
+            if g is None:
+                # warm up on a side stream (lazy allocations, packed-weight caches), then capture
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._body(key, t_random)
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self.pool):
+                    self._body(key, t_random)
+                if self.pool is None:
+                    self.pool = g.pool()
+                self.graphs[(key, t_random)] = g
+                return self.terms[key]             # the capture itself does not execute; the warm-up step did
+            self.opt.sync_lr()
+            g.replay()
+            return self.terms[key]
+        finally:
+            ops.set_compute_dtype(prev)
+
+    def __call__(self, cond, target, t_random=None):
+        """``cond`` [B,nt_cond,C,H,W], ``target`` [B,nt_pred,C,H,W] on the host (ideally pinned) or the device."""
+        shape = (cond.shape[0], cond.shape[1] + target.shape[1]) + tuple(cond.shape[2:])
+        buf = self.input_buffer(shape, self.opt.flat_p.device)
+        buf[:, :cond.shape[1]].copy_(cond, non_blocking=True)
+        buf[:, cond.shape[1]:].copy_(target, non_blocking=True)
+        return self.run(shape, t_random)
+
+    def close(self):
+        """Drop the captured graphs (they hold NCCL work when data-parallel: do this before destroying the group)."""
+        self.graphs.clear()
+        self.pool = None
+
+
+class DevicePrefetcher:
+    """Iterates a loader of host batches, keeping ONE batch in flight: while step k computes, batch k+1 travels
+    host -> device on a copy stream into one of two staging buffers (pinned source memory makes the copy asynchronous;
+    pageable memory still works, synchronously).  Yields device tensors that are valid until the next ``__next__``
+    (main.py:111-114 uses a DataLoader with pin_memory; the reference then copies synchronously inside the loop)."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        it = iter(self.loader)
+        slots = [None, None]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def stage(k):
+            try:
+                batch = next(it)
+            except StopIteration:
+                return False
+            single = isinstance(batch, torch.Tensor)
+            batch = (batch,) if single else tuple(batch)
+            with torch.cuda.stream(self.copy_stream):
+                if slots[k % 2] is None or any(a.shape != b.shape for a, b in zip(slots[k % 2][0], batch)):
+                    slots[k % 2] = ([torch.empty(b.shape, device=self.device, dtype=b.dtype) for b in batch], single)
+                for dst, src in zip(slots[k % 2][0], batch):
+                    dst.copy_(src, non_blocking=True)
+                ready[k % 2].record(self.copy_stream)
+            return True
+
+        k = 0
+        more = stage(0)
+        while more:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ready[k % 2])
+            tensors, single = slots[k % 2]
+            # the other slot was consumed by work already enqueued on the compute stream: the copy stream may reuse it
+            # once that work is done
+            self.copy_stream.wait_stream(cur)
+            more = stage(k + 1)
+            yield tensors[0] if single else tuple(tensors)
+            k += 1
+
+
 def train(xp_dir, train_loader, device, sep_net, optimizer, scheduler, use_apex_amp, use_torch_amp, epochs, lamb_ae,
-          lamb_s, lamb_t, lamb_pred, offset, nt_cond, nt_pred, no_s, skipco, chkpt_interval, average_tloss):
+          lamb_s, lamb_t, lamb_pred, offset, nt_cond, nt_pred, no_s, skipco, chkpt_interval, average_tloss,
+          reducer=None, graph=True):
     """train.py:91-175.  Either AMP flag selects the bf16 tensor-core compute path (the analogue of the
-    reference's fp16 autocast; bf16 needs no loss scaling)."""
+    reference's fp16 autocast; bf16 needs no loss scaling).  With a ``FusedAdam`` optimizer every step is a CUDA-graph
+    replay (``GraphedStep``) fed by a one-batch-ahead host->device prefetch; any other optimizer runs the same step
+    eagerly.  ``reducer`` (parallel.GradReducer) makes the loop data-parallel."""
+    from .optim import FusedAdam
+    prev_dtype = ops.compute_dtype()
     if use_apex_amp or use_torch_amp:
         ops.set_compute_dtype(torch.bfloat16)
     if no_s:
         lamb_t = 0
         print("No regularization on T as there is no S")
     assert offset == nt_cond or offset == 0
+    device = torch.device(device)
+    fused = isinstance(optimizer, FusedAdam) and device.type == 'cuda'
     try:
+        if fused:
+            stepper = GraphedStep(sep_net, optimizer, nt_cond, nt_pred, offset, skipco, lamb_ae, lamb_s, lamb_t,
+                                  lamb_pred, average_tloss, reducer=reducer, graph=graph)
         pb = tqdm(total=epochs * len(train_loader), ncols=0)
         for epoch in range(epochs):
             sep_net.train()
-            for cond, target in train_loader:
-                cond, target = cond.to(device, non_blocking=True), target.to(device, non_blocking=True)
-                optimizer.zero_grad()
-                full_data = torch.cat([cond, target], dim=1)
-                out = step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, lamb_s, lamb_t,
-                                  lamb_pred, average_tloss)
-                out['total'].backward()
-                optimizer.step()
+            batches = DevicePrefetcher(train_loader, device) if device.type == 'cuda' else train_loader
+            for cond, target in batches:
+                if fused:
+                    stepper(cond, target)
+                else:
+                    cond, target = cond.to(device, non_blocking=True), target.to(device, non_blocking=True)
+                    optimizer.zero_grad()
+                    full_data = torch.cat([cond, target], dim=1)
+                    out = step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, lamb_s, lamb_t,
+                                      lamb_pred, average_tloss, reducer=reducer)
+                    out['total'].backward()
+                    if reducer is not None:
+                        reducer.finish()
+                    optimizer.step()
                 pb.update()
             if scheduler is not None:
                 scheduler.step()
@@ -164,4 +317,8 @@ def train(xp_dir, train_loader, device, sep_net, optimizer, scheduler, use_apex_
                 save(xp_dir, sep_net, epoch_number=epoch + 1)
     except KeyboardInterrupt:
         pass
+    finally:
+        if fused:
+            stepper.close()
+        ops.set_compute_dtype(prev_dtype)
     save(xp_dir, sep_net)

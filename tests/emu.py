@@ -276,8 +276,10 @@ def vs_loss_combine(acc, coef, lamb, n, terms, stream):
     terms[n] = sum(float(lamb[i]) * t[i] for i in range(n))
 
 
-def vs_adam_step(p, g, m, v, n, lr, b1, b2, eps, grad_scale, step_host, step_dev, stream):
+def vs_adam_step(p, g, m, v, n, lr, b1, b2, eps, grad_scale, step_host, step_dev, lr_dev, stream):
     step = int(step_dev[0]) if step_dev is not None else step_host
+    if lr_dev is not None:
+        lr = float(lr_dev[0])
     gs = g * grad_scale
     m.mul_(b1).add_(gs, alpha=1 - b1)
     v.mul_(b2).addcmul_(gs, gs, value=1 - b2)
@@ -297,14 +299,14 @@ def emu_call(name, *args):
 def install():
     """Route the package's C-ABI calls to the emulator (CPU tensors allowed) for the duration."""
     from spatiotemporal_variable_separation_b200 import ops
-    saved = (L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array, ops.repack_all)
+    saved = (L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array, ops.repack_params)
     L.call, L.stream, L.require_cuda, L.launch_count = emu_call, (lambda: None), (lambda *a: None), (lambda: -1)
     L.pointer_array = _emu_pointer_array
-    ops.repack_all = lambda: None      # the table holds raw device pointers; the emulator repacks lazily per call instead
+    ops.repack_params = lambda params, cache: None      # the table holds raw device pointers; the emulator repacks lazily per call instead
     try:
         yield
     finally:
-        L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array, ops.repack_all = saved
+        L.call, L.stream, L.require_cuda, L.launch_count, L.pointer_array, ops.repack_params = saved
 
 
 # ---- latent rollout (appended after _TABLE is built: register explicitly) -------------------------

@@ -359,11 +359,13 @@ def test_loss_and_adam_kernels():
         pg[:n], gg[:n] = p.cuda(), g.cuda()
         pc, mc, vc = p.clone(), torch.zeros(n), torch.zeros(n)
         step_dev = torch.zeros(1, dtype=torch.int32).cuda()
+        lr_dev = torch.full((1,), 4e-4, dtype=torch.float32).cuda()
         for step in (1, 2, 3):
             step_dev += 1
-            L.call('vs_adam_step', pg, gg, mg, vg, n, 4e-4, 0.5, 0.99, 1e-8, 0.5, 0 if use_dev else step,
-                   step_dev if use_dev else None, L.stream())
-            emu.emu_call('vs_adam_step', pc, g, mc, vc, n, 4e-4, 0.5, 0.99, 1e-8, 0.5, step, None, None)
+            # device-resident counter AND learning rate (the host lr argument is then ignored)
+            L.call('vs_adam_step', pg, gg, mg, vg, n, 123.0 if use_dev else 4e-4, 0.5, 0.99, 1e-8, 0.5,
+                   0 if use_dev else step, step_dev if use_dev else None, lr_dev if use_dev else None, L.stream())
+            emu.emu_call('vs_adam_step', pc, g, mc, vc, n, 4e-4, 0.5, 0.99, 1e-8, 0.5, step, None, None, None)
         torch.cuda.synchronize()
         close(pg[:n].cpu(), pc, torch.float32, 'adam param')
         close(vg[:n].cpu(), vc, torch.float32, 'adam v')

@@ -191,3 +191,87 @@ def test_full_size_mnist_properties():
     opt.step()
     delta = (opt.flat_p - before).abs().max()
     assert 0 < float(delta) <= cfg['lr'] * 1.001
+
+
+def test_many_models_in_one_process_then_step():
+    """A sweep / evaluation script builds dozens of models in one process; the optimizer's packed-weight table must
+    cover only its OWN parameters (round 1 kept a process-global registry that overflowed the kernel's 1024-row table
+    and repacked the weights of dead models).  Builds 48 models, steps each once, then checks that the last one's step
+    still matches the reference golden and that nothing global refers to the dead models' parameters."""
+    import gc
+    import weakref
+    g = harness.load_golden('mnist-small')
+    cfg = g['cfg']
+    t_random = harness.t_random_sequence(cfg, int(g['np_seed']), 1)[0]
+    refs = []
+    for i in range(48):
+        net = build_filled(cfg, 'cuda').train()
+        opt = FusedAdam(net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
+        opt.zero_grad()
+        out = run_step(net, cfg, t_random, 'cuda')
+        out['total'].backward()
+        if i < 47:
+            opt.step()
+            refs.append(weakref.ref(next(net.parameters())))
+            del net, opt, out
+    grads = {f'{part}.{k}': p.grad.cpu() for part in harness.PARTS for k, p in getattr(net, part).named_parameters()}
+    check_against_golden(g, {k: (v.detach().cpu() if isinstance(v, torch.Tensor) else v) for k, v in out.items()},
+                         grads, rtol_grad=1e-4, kink=0.0)
+    opt.step()                                  # the call that failed in round 1
+    torch.cuda.synchronize()
+    gc.collect()
+    assert sum(r() is not None for r in refs) == 0, 'parameters of dead models are still referenced'
+
+
+def test_pack_table_chunks_beyond_1024_rows(monkeypatch):
+    """More packed copies than one launch's table holds: the refresh is split over several launches."""
+    monkeypatch.setattr(ops, '_PACK_ROWS_PER_LAUNCH', 7)
+    g = harness.load_golden('mnist-small')
+    cfg = g['cfg']
+    net = build_filled(cfg, 'cuda').train()
+    opt = FusedAdam(net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
+    for t_random in harness.t_random_sequence(cfg, int(g['np_seed']), 2):
+        opt.zero_grad()
+        run_step(net, cfg, t_random, 'cuda')['total'].backward()
+        opt.step()
+    assert len(opt._pack_cache['launches']) > 1
+    # every packed copy equals a fresh pack of the updated master weight
+    for p in net.parameters():
+        for (K, C, RS, swap, dtype), (_, out) in p.__dict__.get('_vs_pack', {}).items():
+            fresh = torch.empty_like(out)
+            from spatiotemporal_variable_separation_b200 import _lib as L
+            L.call('vs_pack_weight', p, fresh, L.dtype_code(fresh), K, C, RS, int(swap), L.stream())
+            assert torch.equal(fresh, out)
+
+
+def test_graphed_step_equals_eager_and_follows_lr_schedule():
+    """train.GraphedStep: replayed CUDA graphs produce the same weights as the eager loop, including across a
+    MultiStepLR change (the learning rate is device-resident: no re-capture)."""
+    from spatiotemporal_variable_separation_b200.optim import MultiStepLR
+    g = harness.load_golden('mnist-small')
+    cfg = g['cfg']
+    cond, target = harness.inputs(cfg)
+    draws = [6, 7, 6, 8, 7, 6]
+    finals = []
+    for graph in (False, True):
+        net = build_filled(cfg, 'cuda').train()
+        opt = FusedAdam(net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
+        sched = MultiStepLR(opt, [1], 0.1)
+        stepper = vs_train.GraphedStep(net, opt, cfg['nt_cond'], cfg['nt_pred'], cfg['offset'], cfg['skipco'],
+                                       cfg['lamb_ae'], cfg['lamb_s'], cfg['lamb_t'], cfg['lamb_pred'], graph=graph,
+                                       overlap_encoders=False)
+        terms = []
+        for i, t in enumerate(draws):
+            terms.append(stepper(cond, target, t).cpu().clone())
+            if i == 2:
+                sched.step()                     # lr drops by 10x half-way
+        torch.cuda.synchronize()
+        finals.append((opt.flat_p.clone(), torch.stack(terms), float(opt.lr_dev)))
+        stepper.close()
+    (p0, t0, lr0), (p1, t1, lr1) = finals
+    assert lr0 == lr1 and abs(lr0 - cfg['lr'] * 0.1) < 1e-9
+    # same kernels, same order; the only run-to-run differences are fp atomics in the BatchNorm statistics / weight
+    # gradients of the training path
+    assert torch.allclose(t0, t1, rtol=1e-4, atol=1e-6), (t0, t1)
+    assert float((p0 - p1).abs().max()) <= 2.5 * cfg['lr'], float((p0 - p1).abs().max())
+    assert float((p0 - p1).norm() / p0.norm()) < 1e-4
