@@ -247,6 +247,8 @@ def run_ours(args, cfg):
     n_pool = 4
     host = [synthetic_batch(cfg, device='cpu', seed=100 * rank + i).pin_memory() for i in range(n_pool)]
     dev = [h.to(device) for h in host]
+    # what a DataLoader(pin_memory=True) yields: contiguous pinned (cond, target) pairs
+    host_pairs = [(h[:, :nc].contiguous().pin_memory(), h[:, nc:].contiguous().pin_memory()) for h in host]
     np.random.seed(1234)          # same t_random sequence on every rank
     draws = [draw_t_random(cfg['nt_cond'], n_frames, cfg['offset']) for _ in range(2 * (args.steps + args.warmup) + 64)]
 
@@ -290,7 +292,7 @@ def run_ours(args, cfg):
         """``e2e``: the call a user makes — train.DevicePrefetcher over a loader of pinned HOST batches (batch k+1
         travels host->device on a copy stream while step k computes), train.GraphedStep.__call__(cond, target), and a
         device->host read of the step's five loss terms, every step."""
-        loader = [(host[i % n_pool][:, :nc], host[i % n_pool][:, nc:]) for i in range(n_warm + n_steps)]
+        loader = [host_pairs[i % n_pool] for i in range(n_warm + n_steps)]
         losses, ev0, ev1 = [], torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for k, (cond, target) in enumerate(DevicePrefetcher(loader, device)):
             if k == n_warm:
@@ -415,9 +417,10 @@ def kernel_rooflines(tr, shape, dev, draws, dtype):
             return orig(name, *a)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # an eager step is CPU bound between launches: without work ahead of it in the stream the first event fires at
-        # once and the interval would include the launch latency of the kernel.  A ~20 us spin kernel keeps the stream
-        # busy while the event pair and the kernel are enqueued behind it.
-        torch.cuda._sleep(40000)
+        # once and the interval would include the launch latency of the kernel.  A ~100 us spin kernel keeps the stream
+        # busy while the event pair and the kernel are enqueued behind it (four host-side enqueues take ~15-20 us;
+        # an interval that starts on an idle stream would include the kernel's launch latency).
+        torch.cuda._sleep(200000)
         e0.record()
         orig(name, *a)
         e1.record()

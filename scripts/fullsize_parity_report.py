@@ -26,9 +26,11 @@ for name in args.configs:
     truth = fullsize.oracle_run(name, 'float64', args.batch)
     ref32 = fullsize.oracle_run(name, 'float32', args.batch)
     t1 = time.time()
-    entry = {'oracle_seconds': t1 - t0, 'reference_fp32_vs_fp64': fullsize.summary(fullsize.compare(ref32, truth))}
-    for label, dt in (('cuda_fp32_vs_fp64', torch.float32), ('cuda_bf16_vs_fp64', torch.bfloat16)):
-        rep = fullsize.compare(fullsize.cuda_run(name, dt, args.batch), truth, ref32)
+    refbf = fullsize.oracle_run(name, 'autocast_bf16', args.batch)
+    entry = {'oracle_seconds': t1 - t0, 'reference_fp32_vs_fp64': fullsize.summary(fullsize.compare(ref32, truth)),
+             'reference_autocast_bf16_vs_fp64': fullsize.summary(fullsize.compare(refbf, truth))}
+    for label, dt, ref in (('cuda_fp32_vs_fp64', torch.float32, ref32), ('cuda_bf16_vs_fp64', torch.bfloat16, refbf)):
+        rep = fullsize.compare(fullsize.cuda_run(name, dt, args.batch), truth, ref)
         entry[label] = fullsize.summary(rep)
         entry[label]['grads_by_tensor'] = {n: [float('%.3e' % v[0]), float('%.3e' % v[1])] for n, v in rep['grads'].items()}
     report[name] = entry

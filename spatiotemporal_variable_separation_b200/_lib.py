@@ -88,11 +88,39 @@ def load():
     return _lib
 
 
+class _CurrentStream:
+    """Marker returned by ``stream()``: resolved inside ``call`` to the current stream OF THE DEVICE THE TENSOR ARGUMENTS
+    LIVE ON (which need not be the process's current device: ``train(device='cuda:1')`` without ``set_device``)."""
+
+
+_STREAM = _CurrentStream()
+
+
 def call(name, *args):
     """Invoke an entry point.  torch.Tensor arguments are passed as their device pointer (views keep
-    their offset); everything else goes through ctypes unchanged."""
+    their offset); everything else goes through ctypes unchanged.  The launch goes to the device of the tensor
+    arguments — all of them must live on the same one — on that device's current stream."""
     lib = load()
-    rc = getattr(lib, name)(*[C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else a for a in args])
+    dev = None
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise RuntimeError(f'{name}: tensor arguments on different devices ({dev} and {a.device})')
+    conv = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            conv.append(C.c_void_p(a.data_ptr()))
+        elif a is _STREAM:
+            conv.append(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        else:
+            conv.append(a)
+    if dev is not None and dev.type == 'cuda' and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = getattr(lib, name)(*conv)
+    else:
+        rc = getattr(lib, name)(*conv)
     if rc != 0:
         raise RuntimeError(f'{name} failed: {lib.vs_last_error().decode()}')
 
@@ -102,7 +130,8 @@ def launch_count():
 
 
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The stream argument of an entry point (see ``call``)."""
+    return _STREAM
 
 
 def pointer_array(tensors):

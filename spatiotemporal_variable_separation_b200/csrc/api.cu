@@ -26,11 +26,18 @@ int launched(const char* what) {
     return 0;
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return dev;
+}
+
 int num_sms() {
-    static int n = 0;
+    static int cache[64] = {};
+    const int dev = current_device();
+    int& n = cache[(dev >= 0 && dev < 64) ? dev : 0];
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
             cudaGetLastError();
             n = 148;   // B200
         }

@@ -27,7 +27,14 @@ int launched(const char* what);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
-int num_sms();
+int num_sms();                 // of the CURRENT device
+int current_device();
+// One flag per CUDA device: function attributes (cudaFuncSetAttribute) and occupancy facts belong to a device's
+// context, so a process that drives several GPUs must establish them once PER DEVICE, not once per process.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool& flag() { const int d = current_device(); return done[(d >= 0 && d < 64) ? d : 0]; }
+};
 
 // ---------------------------------------------------------------- element access
 template <typename T> __device__ __forceinline__ float ld(const T* p);

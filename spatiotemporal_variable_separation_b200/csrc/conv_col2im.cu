@@ -222,11 +222,11 @@ template <int NB, int STAGES>
 static int launch_c2i(const CUtensorMap& ma, const CUtensorMap& mb, const Col2imParams& p, const float* bias, void* out,
                       cudaStream_t stream) {
     using S = C2iSmem<NB, STAGES>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(convT_col2im_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return fail("convT_col2im_kernel smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.flag() = true;
     }
     const int grid = p.N < num_sms() ? p.N : num_sms();
     convT_col2im_kernel<NB, STAGES><<<grid, C2I_THREADS, S::TOTAL, stream>>>(ma, mb, p, bias, (__nv_bfloat16*)out);

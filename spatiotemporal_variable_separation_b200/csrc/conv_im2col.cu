@@ -409,12 +409,12 @@ template <int BN, int KC, int STAGES, bool TS>
 static int launch_imf(const CUtensorMap& mb, const CUtensorMap& mo, const Im2colParams& p, const void* wp, const float* bias,
                       void* out, double* stats, cudaStream_t stream) {
     using S = ImfSmem<BN, KC, STAGES, TS>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(im2col_fwd_kernel<BN, KC, STAGES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              S::total(IM_PATCH_STAGE));
         if (e != cudaSuccess) return fail("im2col_fwd_kernel smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.flag() = true;
     }
     const int resident = 2 * num_sms();
     const int grid = p.total_tiles < resident ? p.total_tiles : resident;
@@ -627,11 +627,11 @@ static int launch_imw(const CUtensorMap& ms, const CUtensorMap& mb, const Im2col
                       cudaStream_t stream) {
     constexpr int SMEM = STAGES * (2 * 64 * 64 * 2 + BN * 64 * 2) + 1024 + 256 + IM_MAX_KK * 4 + IM_PST * IM_PATCH_STAGE_W;
     static_assert((2 * STAGES + 2 * IM_PST + 2) * 8 <= 256, "barrier area");
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(im2col_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return fail("im2col_wgrad_kernel smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.flag() = true;
     }
     dim3 grid((unsigned)k_tiles, 1, (unsigned)splits);
     im2col_wgrad_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(ms, mb, p, dw);

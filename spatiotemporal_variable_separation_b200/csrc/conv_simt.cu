@@ -55,11 +55,13 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(GatherArgs a, const T*
 
     // ---- compute role
     const int tx = tid & 15, ty = tid >> 4;
+    constexpr bool EXACT = sizeof(T) == 4;
     float acc[4][4];
+    double tot[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.0; }
 
     int r_begin = 0, r_step = 1, s_begin = 0, s_step = 1;
     if (a.transposed) {
@@ -111,8 +113,23 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(GatherArgs a, const T*
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xs[i], ws[j], acc[i][j]);
                 }
+                if (EXACT) {
+                    // parity mode: the 16-term fp32 partial sums of this slab are added up in fp64, so the rounding
+                    // error of a K = 4608 reduction stays at the level of ONE short fp32 sum (a sequential fp32
+                    // accumulation over K terms loses ~sqrt(K) ulp, more than the blocked sums of the CPU libraries)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { tot[i][j] += (double)acc[i][j]; acc[i][j] = 0.f; }
+                }
             }
         }
+    }
+    if (EXACT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = (float)tot[i][j];
     }
 
     // ---- epilogue: bias, statistics of the pre-activation, activation, store
@@ -206,11 +223,13 @@ __global__ void __launch_bounds__(256) wgrad_kernel(vs_conv_geom g, const T* __r
 
     const int lrow = tid >> 4, lcol = (tid & 15) * 4;   // loader: 16 rows x 64 columns, 4 per thread
     const int tx = tid & 15, ty = tid >> 4;
+    constexpr bool EXACT = sizeof(T) == 4;
     float acc[4][4];
+    double tot[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.0; }
 
     for (long long mb = m_begin; mb < m_end; mb += BK) {
         const long long m = mb + lrow;
@@ -252,6 +271,18 @@ __global__ void __launch_bounds__(256) wgrad_kernel(vs_conv_geom g, const T* __r
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xs[i], ws[j], acc[i][j]);
         }
+        if (EXACT) {          // parity mode: fp64 sum of the 16-row fp32 partial sums (see gather_gemm_kernel)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { tot[i][j] += (double)acc[i][j]; acc[i][j] = 0.f; }
+        }
+    }
+    if (EXACT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = (float)tot[i][j];
     }
     const int RS = g.R * g.S;
 #pragma unroll

@@ -791,11 +791,11 @@ template <int BN, int STAGES, bool TS, bool SS = false>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMaps& om, const TcParams& p, const float* bias,
                      void* out, int classes, double* stats, cudaStream_t stream) {
     using S = TcSmem<BN, STAGES, TS>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES, TS, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return fail("tc_conv_kernel smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.flag() = true;
     }
     TcParams q = p;
     q.classes = classes;
@@ -817,11 +817,11 @@ template <int BN, int STAGES>
 static int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const float* bias, void* out, int classes,
                           double* stats, cudaStream_t stream) {
     using S = TcPairSmem<BN, STAGES>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return fail("tc_conv_pair_kernel smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.flag() = true;
     }
     TcParams q = p;
     q.classes = classes;
@@ -925,11 +925,11 @@ template <int STAGES>
 static int launch_tc_fused(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMaps& om, const TcParams& p, const TcFusedTab& tab,
                            const float* bias, double* stats, cudaStream_t stream) {
     using S = TcFusedSmem<STAGES>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(tc_convT4_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return fail("tc_convT4_kernel smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.flag() = true;
     }
     TcParams q = p;
     q.classes = 4;
@@ -1468,11 +1468,11 @@ template <int BN, int STAGES>
 static int launch_tc_wgrad_pair(const CUtensorMap& ms, const CUtensorMap& mb, const TcWgradParams& p, float* dw, int splits,
                                 cudaStream_t stream) {
     constexpr int SMEM = STAGES * (128 * 64 * 2 + (BN / 2) * 64 * 2) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(tc_wgrad_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return fail("tc_wgrad_pair_kernel smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.flag() = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1493,11 +1493,11 @@ template <int BN, int STAGES>
 static int launch_tc_wgrad(const CUtensorMap& ms, const CUtensorMap& mb, const TcWgradParams& p, float* dw, int splits,
                            cudaStream_t stream) {
     constexpr int SMEM = STAGES * (128 * 64 * 2 + BN * 64 * 2) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return fail("tc_wgrad_kernel smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.flag() = true;
     }
     dim3 grid((unsigned)(p.k_tiles * p.c_tiles), (unsigned)(p.R * p.S), (unsigned)splits);
     tc_wgrad_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(ms, mb, p, dw);
@@ -1508,11 +1508,11 @@ template <int CB, int TAPS, int STAGES>
 static int launch_tc_wgrad_taps(const CUtensorMap& ms, const CUtensorMap& mb, const TcWgradParams& p, float* dw, int splits,
                                 cudaStream_t stream) {
     constexpr int SMEM = STAGES * (128 * 64 * 2 + CB * TAPS * 64 * 2) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(tc_wgrad_taps_kernel<CB, TAPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return fail("tc_wgrad_taps_kernel smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.flag() = true;
     }
     // vector reductions need the TAPS gradients of one (k, c) aligned to their total size
     const int vec_ok = ((p.R * p.S) % TAPS == 0 && (reinterpret_cast<uintptr_t>(dw) % (TAPS * 4)) == 0) ? 1 : 0;

@@ -464,10 +464,11 @@ static int rollout_cluster(const RolloutClusterArgs& a, const RolloutWeights& rw
     static int off = -1;
     if (off < 0) { const char* e = getenv("VARSEP_DISABLE_ROLLOUT_CLUSTER"); off = (e && e[0] == '1') ? 1 : 0; }
     if (off) return -1;
-    struct Choice { int d, h, nb, cs, max8, max16; };
-    static Choice cache = {0, 0, 0, 0, 0, 0};
-    if (cache.d != a.d || cache.h != a.h || cache.nb != a.nb || cache.cs == 0) {
-        Choice c = {a.d, a.h, a.nb, -1, 0, 0};
+    struct Choice { int d, h, nb, cs, max8, max16, dev; };
+    static Choice cache = {0, 0, 0, 0, 0, 0, -1};
+    const int dev = current_device();          // occupancy is a property of the device the launch goes to
+    if (cache.d != a.d || cache.h != a.h || cache.nb != a.nb || cache.cs == 0 || cache.dev != dev) {
+        Choice c = {a.d, a.h, a.nb, -1, 0, 0, dev};
         if (rollout_cluster_fits(a.d, a.h, a.nb, 16, 8)) {
             c.max8 = rollout_cluster_max_active<BWD, 16, 8>(a.d, a.h, a.nb);
             if (c.max8 >= 8) {

@@ -154,6 +154,17 @@ def zeros_f64(n, device):
     return torch.zeros(n, device=device, dtype=torch.float64)
 
 
+# ------------------------------------------------------------------------------------------------
+# "gradient ready" notifications for data-parallel bucketing (parallel.GradReducer): forward operators announce the
+# parameters they use, backward operators announce them again once their gradient kernels are enqueued.
+# ------------------------------------------------------------------------------------------------
+_grad_hooks = [None, None]
+
+
+def set_grad_ready_hook(on_use, on_ready):
+    _grad_hooks[0], _grad_hooks[1] = on_use, on_ready
+
+
 ConvCfg = namedtuple('ConvCfg', 'kind K C R S stride pad act groups training has_bn eps momentum flags')
 
 
@@ -241,10 +252,14 @@ class ConvBlockFn(torch.autograd.Function):
             x, weight, y, mean, invstd, gamma, beta = ctx.saved_tensors
             G = ctx.G
             sums = zeros_f64(G * OC * 2, dout.device)
-            if cfg.training:
+            # the per-channel sums  sum(dz), sum(dz * xhat)  feed dy in training mode and ARE the affine gradients
+            # (dbeta, dgamma) in either mode: fine-tuning with frozen statistics (eval() + grad) still trains gamma / beta
+            affine = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
+            if cfg.training or affine:
                 L.call('vs_bn_act_backward_reduce', ptr(dout), ptr(y), L.dtype_code(y), rows, OC, G, ptr(mean),
                      ptr(invstd), ptr(gamma), ptr(beta), act, ptr(sums), L.stream())
-                dgamma, dbeta = _grad_buffer(p_gamma), _grad_buffer(p_beta)
+                if affine:
+                    dgamma, dbeta = _grad_buffer(p_gamma), _grad_buffer(p_beta)
             dy = torch.empty_like(y)
             L.call('vs_bn_act_backward_apply', ptr(dout), ptr(y), ptr(dy), L.dtype_code(y), rows, OC, G, ptr(mean),
                  ptr(invstd), ptr(gamma), ptr(beta), act, ptr(sums), int(cfg.training),
@@ -280,10 +295,13 @@ class ConvBlockFn(torch.autograd.Function):
         if p_bias is not None and ctx.needs_input_grad[2]:
             db = _grad_buffer(p_bias)
             if not (cfg.has_bn and cfg.training):
+                # (eval-mode BatchNorm is an affine map: the bias gradient is the plain column sum of dy)
                 L.call('vs_colsum', ptr(dy), L.dtype_code(dy), rows, OC, ptr(db[0]), L.stream())
             # else: BatchNorm's backward returns a dy whose per-(group, channel) sum is exactly zero, so the
             # bias gradient is mathematically 0 (the reference computes rounding noise there);
             # the (zero-initialised) buffer is left untouched instead of streaming dy once more.
+        if _grad_hooks[1] is not None:
+            _grad_hooks[1](ctx.params)
         return (dx, dw[1] if dw else None, db[1] if db else None, dgamma[1] if dgamma else None,
                 dbeta[1] if dbeta else None,
                 None, None, None, None)
@@ -360,6 +378,8 @@ def conv_block(x, conv, bn=None, act=None, kind='conv', groups=1, wshape=None, f
         return ConvBlockFn.apply(x, wf, bf, None, None, None, None, None, cfg)
     cfg = ConvCfg(kind, K, C, R, S, stride, pad, act, groups, training, bn is not None,
                   bn.eps if bn is not None else 0.0, bn.momentum if bn is not None else 0.0, flags)
+    if _grad_hooks[0] is not None and torch.is_grad_enabled():
+        _grad_hooks[0]((w, conv.bias, bn.weight, bn.bias) if bn is not None else (w, conv.bias))
     if bn is not None:
         return ConvBlockFn.apply(x, w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                  bn.num_batches_tracked, cfg)
@@ -725,7 +745,9 @@ def loss_terms(spec, tensors):
 class LatentRolloutFn(torch.autograd.Function):
     """codes[t+1] = stepper(codes[t]) for t < T-1 (model.py:78-83 / resnet.py:42-50) as one kernel; the
     backward is the adjoint recurrence as one kernel plus three (T-1)*B-row weight-gradient GEMMs per block.
-    Inputs: t0 [B,d] fp32 and, per block, W1,b1,W2,b2,W3,b3.  Returns (codes [T,B,d], res [nb,T-1,B,d])."""
+    Inputs: t0 [B,d] fp32 and, per block, W1,b1,W2,b2,W3,b3.  Returns (codes [T,B,d], res [nb,T-1,B,d]).
+    ``res`` (the reference's ``t_residuals``, model.py:80-82) is returned for inspection only and is marked
+    non-differentiable: the training objective (train.py:120-149) never differentiates through it."""
 
     @staticmethod
     def forward(ctx, T, t0, *weights):
@@ -787,6 +809,8 @@ class LatentRolloutFn(torch.autograd.Function):
             g2 = lin_grads(w2, b2, dhidden[j, 1], hidden[j, 0], h, h)
             g3 = lin_grads(w3, b3, dres[j], hidden[j, 1], d, h)
             grads += [g1[0], g1[1], g2[0], g2[1], g3[0], g3[1]]
+        if _grad_hooks[1] is not None:
+            _grad_hooks[1](ctx.params)
         return (None, dcodes[0]) + tuple(grads)
 
 
@@ -798,4 +822,6 @@ def latent_rollout(t0, stepper, T):
         assert len(lins) == 3
         for lin in lins:
             weights += [lin.weight, lin.bias]
+    if _grad_hooks[0] is not None and torch.is_grad_enabled():
+        _grad_hooks[0](weights)
     return LatentRolloutFn.apply(T, t0, *weights)

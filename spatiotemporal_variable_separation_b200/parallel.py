@@ -5,68 +5,152 @@ Semantics: every rank holds a full replica and processes its own shard of the gl
 scaling: `batch_size` sequences per GPU).  BatchNorm statistics stay per replica, so each replica's
 forward pass is bit-identical to the single-GPU path on the same shard.  The only exchange step is the
 gradient reduction: the flat gradient arena of ``FusedAdam`` is summed across ranks with NCCL
-(NVLink 5 / NVSwitch) in three buckets, each launched on a side stream as soon as autograd has
-finished the part of the model it covers — decoder, then the latent stepper, then the encoders — so
-the transfer overlaps the rest of backward; the 1/world factor is folded into the Adam kernel.
+(NVLink 5 / NVSwitch); the 1/world factor is folded into the Adam kernel.
+
+Buckets follow the order in which backward COMPLETES gradients, not the order of registration: the arena
+range of every network (Es, Et, decoder, t_resnet) is cut, from its END (the layers whose weight gradients
+are finished first), into contiguous buckets of at most ``bucket_bytes``.  The backward operators announce
+every finished parameter gradient (``ops.set_grad_ready_hook``); a bucket leaves on a side stream the moment
+its last parameter is announced, so the transfer overlaps the rest of backward and only the last small
+bucket (the first layers of the encoders, a few MB) is exposed after it.  A parameter used several times in
+one step (the convolutional stepper of the SST configuration) counts as finished after its last use.
+
 The host draw ``t_random`` must be identical on every rank (seed numpy identically, or broadcast it).
 """
 import torch
 import torch.distributed as dist
 
+from . import ops
+
 
 class GradReducer:
-    def __init__(self, sep_net, opt, group=None, overlap=True):
+    def __init__(self, sep_net, opt, group=None, overlap=True, bucket_bytes=8 << 20):
         self.opt, self.group, self.overlap = opt, group, overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         opt.grad_scale = 1.0 / self.world
-        # arena ranges of the four networks (parameters were registered Es, Et, decoder, t_resnet)
         index = {id(p): (off, p.numel()) for p, off in zip(opt.params, opt.offsets)}
-        self.ranges = {}
-        for name in ('Es', 'Et', 'decoder', 't_resnet'):
-            spans = [index[id(p)] for p in getattr(sep_net, name).parameters() if id(p) in index]
-            if spans:
-                lo = min(o for o, _ in spans)
-                hi = max(o + (n + 3) // 4 * 4 for o, n in spans)
-                self.ranges[name] = (lo, hi)
-        self.comm_stream = torch.cuda.Stream() if (overlap and opt.flat_g.is_cuda) else None
-        self.pending = []
-        self.done = set()
+        cap = max(int(bucket_bytes) // 4, 1)
+        # ---- buckets: per network, contiguous arena ranges cut from the end of the network's range
+        self.buckets = []                      # dict(lo, hi, params=set(id), name)
+        self.bucket_of = {}
+        covered = set()
+        for name in ('decoder', 't_resnet', 'Et', 'Es'):
+            net = getattr(sep_net, name, None)
+            if net is None:
+                continue
+            ps = [p for p in net.parameters() if id(p) in index and id(p) not in covered]
+            ps.sort(key=lambda p: index[id(p)][0])
+            cur = None
+            for p in reversed(ps):
+                off, n = index[id(p)]
+                end = off + (n + 3) // 4 * 4
+                if cur is None or cur['hi'] - off > cap or end != cur['lo']:
+                    cur = dict(lo=off, hi=end, params=set(), name=f'{name}[{len(self.buckets)}]')
+                    self.buckets.append(cur)
+                cur['lo'] = min(cur['lo'], off)
+                cur['params'].add(id(p))
+                self.bucket_of[id(p)] = cur
+                covered.add(id(p))
+        # parameters outside the four networks (none today) travel in one trailing bucket
+        rest = [p for p in opt.params if id(p) not in covered]
+        if rest:
+            lo = min(index[id(p)][0] for p in rest)
+            hi = max(index[id(p)][0] + (index[id(p)][1] + 3) // 4 * 4 for p in rest)
+            b = dict(lo=lo, hi=hi, params={id(p) for p in rest}, name='rest')
+            self.buckets.append(b)
+            for p in rest:
+                self.bucket_of[id(p)] = b
+        self.comm_stream = torch.cuda.Stream(device=opt.flat_g.device) if (overlap and opt.flat_g.is_cuda) else None
+        self.pending, self.done = [], set()
+        self._uses, self._left, self._streams = {}, {}, {}
+        self._armed = False
 
-    # ---- bucket launch ------------------------------------------------------------------------
-    def _reduce(self, names):
-        if self.world == 1:
+    # ---- armed for one step by the training step (train.step_losses) ------------------------------------------
+    def begin_step(self):
+        """Called before the forward pass of a step: count parameter uses in forward, release buckets in backward."""
+        self.pending.clear()
+        self.done.clear()
+        self._uses.clear()
+        self._streams.clear()
+        self._left = {id(b): len(b['params']) for b in self.buckets}
+        self._armed = self.world > 1 and self.overlap
+        ops.set_grad_ready_hook(self._on_use if self._armed else None, self._on_ready if self._armed else None)
+
+    def _on_use(self, params):
+        for p in params:
+            if p is not None:
+                self._uses[id(p)] = self._uses.get(id(p), 0) + 1
+
+    def _on_ready(self, params):
+        for p in params:
+            if p is None:
+                continue
+            k = id(p)
+            b = self.bucket_of.get(k)
+            if b is None or id(b) in self.done:
+                continue
+            left = self._uses.get(k, 1) - 1
+            self._uses[k] = left
+            if left > 0:
+                continue
+            if p.is_cuda:                                   # the stream this gradient was produced on
+                s = torch.cuda.current_stream(p.device)
+                self._streams.setdefault(id(b), {})[s.cuda_stream] = s
+            self._left[id(b)] -= 1
+            if self._left[id(b)] == 0:
+                self._launch(b)
+
+    # ---- bucket launch ----------------------------------------------------------------------------------------
+    def _launch(self, b):
+        if self.world == 1 or id(b) in self.done:
             return
-        names = [n for n in names if n in self.ranges and n not in self.done]
-        if not names:
-            return
-        self.done.update(names)
-        lo = min(self.ranges[n][0] for n in names)
-        hi = max(self.ranges[n][1] for n in names)
-        bucket = self.opt.flat_g[lo:hi]
+        self.done.add(id(b))
+        bucket = self.opt.flat_g[b['lo']:b['hi']]
         if self.comm_stream is not None:
-            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            streams = self._streams.get(id(b)) or {}
+            cur = torch.cuda.current_stream(bucket.device)
+            streams.setdefault(cur.cuda_stream, cur)
+            for s in streams.values():
+                self.comm_stream.wait_stream(s)
             with torch.cuda.stream(self.comm_stream):
                 self.pending.append(dist.all_reduce(bucket, group=self.group, async_op=True))
         else:
             dist.all_reduce(bucket, group=self.group)
 
-    # ---- hooks placed by the training step -------------------------------------------------------
+    # kept for callers of the round-1 interface: a tensor-gradient hook that flushes whole networks
     def after(self, tensor, names):
-        """Reduce the gradient buckets ``names`` once the gradient w.r.t. ``tensor`` exists, i.e. once
-        autograd has run every operator downstream of it."""
-        if self.world > 1 and self.overlap and tensor.requires_grad:
-            tensor.register_hook(lambda g: (self._reduce(names), g)[1])
+        return None
 
     def finish(self):
-        """After ``backward()``: reduce whatever is left and make the compute stream wait for all buckets."""
-        self._reduce(('decoder', 't_resnet'))
-        self._reduce(('Es', 'Et'))
+        """After ``backward()``: reduce whatever is left (parameters that received no gradient this step keep their
+        bucket waiting) and make the compute stream wait for all buckets."""
+        ops.set_grad_ready_hook(None, None)
+        self._armed = False
+        # merge the leftovers into as few contiguous calls as possible
+        left = sorted((b for b in self.buckets if id(b) not in self.done), key=lambda b: b['lo'])
+        merged = []
+        for b in left:
+            if merged and merged[-1]['hi'] == b['lo']:
+                merged[-1]['hi'] = b['hi']
+                merged[-1]['ids'].append(id(b))
+            else:
+                merged.append(dict(lo=b['lo'], hi=b['hi'], ids=[id(b)]))
+        for m in merged:
+            self.done.update(m['ids'])
+            if self.world == 1:
+                continue
+            bucket = self.opt.flat_g[m['lo']:m['hi']]
+            if self.comm_stream is not None:
+                self.comm_stream.wait_stream(torch.cuda.current_stream(bucket.device))
+                with torch.cuda.stream(self.comm_stream):
+                    self.pending.append(dist.all_reduce(bucket, group=self.group, async_op=True))
+            else:
+                dist.all_reduce(bucket, group=self.group)
         for work in self.pending:
             work.wait()
         if self.comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            torch.cuda.current_stream(self.opt.flat_g.device).wait_stream(self.comm_stream)
         self.pending.clear()
-        self.done.clear()
 
 
 def broadcast_model(sep_net, src=0, group=None):

@@ -5,6 +5,8 @@ the GPU-organised body of one step (train.py:116-149): the same arithmetic, but 
 the two Et calls and the 1 + nt_pred + offset decoder calls are each ONE grouped launch sequence
 (BatchNorm statistics per call), and all loss terms are reduced by fused kernels.
 """
+import contextlib
+
 import numpy as np
 import torch
 from tqdm import tqdm
@@ -65,12 +67,14 @@ def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, l
         t_random = draw_t_random(nt_cond, n_frames, offset)
     if full_data.is_cuda:
         ops.begin_step(full_data.device)          # one memset for all the small zeroed buffers of this step
+    if reducer is not None:
+        reducer.begin_step()                      # gradient buckets leave during backward, in completion order
     # ---- encoders: two calls each, batched as two BatchNorm groups.  Es and Et are independent until the decoder, and
     # their launches (and the 64-CTA latent rollout that follows Et) each fill only part of the GPU, so the content
     # encoder runs on a side stream next to the dynamic encoder + rollout; autograd replays the same split in backward.
     side = _side_stream(full_data) if overlap_encoders else None
     if side is not None:
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(full_data.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             s_both = sep_net.Es.encode(sep_net.encoder_input(full_data, [0, n_frames - nt_cond]), 2, skipco)
@@ -88,10 +92,6 @@ def step_losses(sep_net, full_data, nt_cond, nt_pred, offset, skipco, lamb_ae, l
     else:
         s_old, s_new, skip_old, skip_new = s_both[:B], s_both[B:], None, None
     t_rand, t_cond = t_both[:B], t_both[B:]
-    if reducer is not None:
-        # gradient buckets leave as soon as autograd is done with the networks downstream of these codes:
-        # dL/dt_both exists once the decoder AND the stepper have been back-propagated through
-        reducer.after(t_both, ('decoder', 't_resnet'))
     # ---- rollout + AE reconstruction and all forecasts in one grouped decode
     forecasts, t_codes, _, _, recon = sep_net.forecast_internal(s_old, skip_old, t_cond, nt_pred + offset, B,
                                                                 extra_t=t_rand)
@@ -186,6 +186,8 @@ class GraphedStep:
             t_random = draw_t_random(self.nt_cond, key[1], self.offset)
         prev = ops.compute_dtype()
         ops.set_compute_dtype(self.dtype)
+        guard = torch.cuda.device(self.opt.flat_p.device) if self.opt.flat_p.is_cuda else contextlib.nullcontext()
+        guard.__enter__()
         try:
             if not self.graph:
                 self._body(key, t_random)
@@ -209,6 +211,7 @@ class GraphedStep:
             g.replay()
             return self.terms[key]
         finally:
+            guard.__exit__(None, None, None)
             ops.set_compute_dtype(prev)
 
     def __call__(self, cond, target, t_random=None):

@@ -26,16 +26,30 @@ def full_cfg(name, batch=None):
 def oracle_run(name, dtype_name, batch=None):
     """One loss + backward of the oracle at full size.  -> dict(loss [5], forecasts, t_codes, grads{name: tensor})"""
     from oracle import step
-    dtype = getattr(torch, dtype_name)
     cfg = full_cfg(name, batch)
-    torch.set_num_threads(max(torch.get_num_threads(), 1))
-    net = harness.oracle_net(cfg, dtype)
-    cond, target = harness.inputs(cfg, dtype)
-    out = step.step_losses(net, cond, target, cfg, T_RANDOM[name])
-    out['total'].backward()
+    if dtype_name == 'autocast_bf16':
+        # the reference's own mixed-precision path (--torch_amp: main.py:159, train.py:151-155) with bf16 as the low
+        # precision type: fp32 master weights, convolutions / linears in bf16, BatchNorm and losses in fp32.  Calibrates
+        # the bf16 bound: how far does the REFERENCE move from its fp64 result when it computes in bf16?
+        dev = 'cuda' if torch.cuda.is_available() else 'cpu'
+        net = harness.oracle_net(cfg, torch.float32)
+        for P in net.P.values():
+            for k, v in P.items():
+                if isinstance(v, torch.Tensor):
+                    P[k] = v.detach().to(dev).requires_grad_(v.requires_grad)
+        cond, target = [t.to(dev) for t in harness.inputs(cfg, torch.float32)]
+        with torch.autocast(dev, dtype=torch.bfloat16):
+            out = step.step_losses(net, cond, target, cfg, T_RANDOM[name])
+        out['total'].backward()
+    else:
+        dtype = getattr(torch, dtype_name)
+        net = harness.oracle_net(cfg, dtype)
+        cond, target = harness.inputs(cfg, dtype)
+        out = step.step_losses(net, cond, target, cfg, T_RANDOM[name])
+        out['total'].backward()
     return dict(loss=np.array([float(out[k].detach()) for k in LOSS_KEYS]),
-                forecasts=out['forecasts'].detach(), t_codes=out['t_codes'].detach(),
-                grads={n: (p.grad.detach() if p.grad is not None else None) for n, p in net.parameters()})
+                forecasts=out['forecasts'].detach().float().cpu(), t_codes=out['t_codes'].detach().float().cpu(),
+                grads={n: (p.grad.detach().cpu() if p.grad is not None else None) for n, p in net.parameters()})
 
 
 def cuda_run(name, dtype, batch=None):

@@ -113,9 +113,77 @@ def test_reference_pickles_load_and_our_files_load_into_the_reference(name, tmp_
     for part in harness.PARTS:
         for (k, v), (k2, v2) in zip(getattr(ref_net, part).state_dict().items(), getattr(ours, part).state_dict().items()):
             assert k == k2 and torch.equal(v, v2), (part, k)
-    helper.save(str(d2), ours, epoch_number=3)                  # our files: state_dicts under the reference's names
+    helper.save_state_dicts(str(d2), ours, epoch_number=3)     # plain state_dicts under distinct names
     fresh = build_reference(cfg)
     for attr, fname in (('Et', 'ov_Et'), ('Es', 'ov_Es'), ('decoder', 'decoder'), ('t_resnet', 't_resnet')):
-        getattr(fresh, attr).load_state_dict(torch.load(str(d2 / f'{fname}_3.pt')))
+        getattr(fresh, attr).load_state_dict(torch.load(str(d2 / f'{fname}_3.state_dict.pt')))
         for (k, v), (_, v2) in zip(getattr(fresh, attr).state_dict().items(), getattr(ref_net, attr).state_dict().items()):
             assert torch.equal(v, v2), (attr, k)
+
+
+
+def test_save_writes_the_reference_format_and_the_reference_loader_procedure_works(tmp_path):
+    """helper.save pickles whole modules under the reference's file names; test/utils.py:8-16 of the reference does
+    ``torch.load(path).to(device)`` on them and must obtain working modules (of this package's classes) with the
+    trained values, free of optimizer-arena views and per-parameter caches."""
+    cfg = harness.load_golden('mnist-small')['cfg']
+    ops.set_compute_dtype(torch.float32)
+    with emu.install():
+        net = build_filled(cfg).train()
+        opt = FusedAdam(net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
+        _grads_step(net, cfg, opt, 6)                       # parameters are now views of the flat arena, caches exist
+        helper.save(str(tmp_path), net, epoch_number=2)
+        cond, _ = harness.inputs(cfg)
+        want = net.eval().get_forecast(cond, 3)[0]
+        # the reference's loader, verbatim in spirit (torch >= 2.6 needs weights_only=False for module pickles)
+        from spatiotemporal_variable_separation_b200.networks.model import SeparableNetwork
+        parts = {a: torch.load(str(tmp_path / f'{f}_2.pt'), weights_only=False).to('cpu')
+                 for a, f in (('Et', 'ov_Et'), ('Es', 'ov_Es'), ('decoder', 'decoder'), ('t_resnet', 't_resnet'))}
+        for a, m in parts.items():
+            assert type(m) is type(getattr(net, a))
+            for p in m.parameters():
+                assert p.untyped_storage().nbytes() == p.numel() * 4                 # compact, not the arena
+                assert not any(k.startswith('_vs_') for k in p.__dict__)
+        twin = SeparableNetwork(parts['Es'], parts['Et'], parts['t_resnet'], parts['decoder'], cfg['nt_cond'], cfg['skipco'])
+        got = twin.eval().get_forecast(cond, 3)[0]
+        assert torch.equal(got, want)
+    assert os.path.getsize(tmp_path / 'ov_Es_2.pt') < 2 * sum(p.numel() * 4 for p in net.Es.parameters()) + (1 << 16)
+
+
+def test_load_refuses_foreign_pickles_unless_asked(tmp_path):
+    import pickle
+
+    cfg = harness.load_golden('mnist-small')['cfg']
+    net = build_filled(cfg)
+    helper.save(str(tmp_path), net)
+    helper.load(str(tmp_path), build_filled(cfg))               # our own module pickles pass the restricted unpickler
+
+    class Evil:
+        def __reduce__(self):
+            return (os.path.join, ('pwned', 'x'))               # any callable outside the allow-list
+
+    torch.save(Evil(), str(tmp_path / 'ov_Et.pt'))
+    with pytest.raises(pickle.UnpicklingError, match='allow_pickled_modules'):
+        helper.load(str(tmp_path), build_filled(cfg))
+    with pytest.raises(TypeError):                              # opt-in: unpickled, then rejected for not being a module
+        helper.load(str(tmp_path), build_filled(cfg), allow_pickled_modules=True)
+
+
+def test_params_json_round_trip_through_load_model(tmp_path):
+    """main.py:105-106 + test/utils.py:8-16: an experiment directory written by this package (params.json + the four
+    checkpoint files) is rebuilt by load_model without any architecture flag on the command line."""
+    from spatiotemporal_variable_separation_b200 import configs
+    from spatiotemporal_variable_separation_b200.options import parser
+    from spatiotemporal_variable_separation_b200.test.utils import load_model
+    import shlex
+    argv = ['--xp_dir', str(tmp_path), '--data_dir', '.'] + shlex.split(configs.README_FLAGS['mnist']) + \
+        shlex.split(configs.SMALL_FLAGS['mnist'])
+    args = parser.parse_args(argv)
+    cfg = configs.preset('mnist', small=True)
+    net = build_filled(cfg)
+    helper.save_params(str(tmp_path), args)
+    helper.save(str(tmp_path), net)
+    twin = load_model({'xp_dir': str(tmp_path), 'device': 'cpu'})
+    assert not twin.training
+    for (k, a), (_, b) in zip(net.state_dict().items(), twin.state_dict().items()):
+        assert torch.equal(a, b), k

@@ -112,3 +112,30 @@ def test_split_first_group_backward_fills_one_buffer():
     first, rest = ops.split_first_group(y)
     rest.sum().backward()
     assert torch.equal(y.grad, torch.cat([torch.zeros(1, 2), torch.ones(2, 2)]))
+
+
+def test_eval_mode_batchnorm_still_trains_its_affine_parameters():
+    """Fine-tuning with frozen statistics (``eval()`` with grad enabled): gamma / beta receive the gradients
+    torch's batch_norm produces in eval mode, and the conv bias the plain column sum."""
+    import torch.nn as nn
+    from spatiotemporal_variable_separation_b200 import ops
+    from tests import emu
+    torch.manual_seed(0)
+    conv, bn = nn.Conv2d(3, 5, 3, 1, 1), nn.BatchNorm2d(5)
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5); bn.weight.normal_(1, 0.2); bn.bias.normal_(0, 0.2)
+    bn.eval()
+    x = torch.randn(2, 3, 6, 6)
+    ref = torch.nn.functional.leaky_relu(bn(conv(x)), 0.2)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    want = [p.grad.clone() for p in (conv.weight, conv.bias, bn.weight, bn.bias)]
+    for p in (conv.weight, conv.bias, bn.weight, bn.bias):
+        p.grad = None
+    ops.set_compute_dtype(torch.float32)
+    with emu.install():
+        out = ops.conv_block(x.permute(0, 2, 3, 1).contiguous(), conv, bn, 'leaky_relu')
+        out.backward(go.permute(0, 2, 3, 1).contiguous())
+    assert torch.allclose(out.permute(0, 3, 1, 2), ref, atol=1e-5)
+    for p, w in zip((conv.weight, conv.bias, bn.weight, bn.bias), want):
+        assert p.grad is not None and torch.allclose(p.grad, w, rtol=1e-4, atol=1e-5), (p.shape, p.grad, w)

@@ -35,7 +35,7 @@ def _worker(rank, world, port, out_dir):
         net = build_filled(cfg).train()
         broadcast_model(net)
         opt = FusedAdam(net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
-        red = GradReducer(net, opt, overlap=True)
+        red = GradReducer(net, opt, overlap=True, bucket_bytes=16 << 10)    # small buckets: several per network
         cond, target = harness.inputs(cfg)
         full = torch.cat([cond, target], 1)
         shard = full[rank * 2:(rank + 1) * 2]                       # 2 sequences per rank
@@ -48,8 +48,13 @@ def _worker(rank, world, port, out_dir):
         run(None)                          # this rank's own gradient (train-mode BN: batch statistics only)
         local = opt.flat_g.clone()
         run(red)                           # same step with the bucket hooks active
-        assert 'decoder' in red.done and 't_resnet' in red.done      # left during backward
+        # every bucket whose parameters all received a gradient left DURING backward, in completion order:
+        # the decoder's and the stepper's first
+        left_early = [b['name'] for b in red.buckets if id(b) in red.done]
+        assert any(n.startswith('decoder') for n in left_early) and any(n.startswith('t_resnet') for n in left_early), left_early
+        assert len(left_early) >= len(red.buckets) - 2, (left_early, [b['name'] for b in red.buckets])
         red.finish()
+        assert len(red.done) == len(red.buckets)
         summed = opt.flat_g.clone()
         opt.step()
         torch.save({'local': local, 'summed': summed, 'params': opt.flat_p.clone(), 'scale': opt.grad_scale},
