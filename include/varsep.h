@@ -180,6 +180,31 @@ int vs_sqdiff_backward(const float* a, int64_t a_sb, int64_t a_st, const float* 
 int vs_loss_combine(const double* acc, const double* coef_host, const double* lamb_host, int32_t n, float* terms,
                     void* stream);
 
+/* ---- fused decoder tail ---------------------------------------------------------------------
+ * replaces: the last BatchNorm + LeakyReLU of the DCGAN decoder followed by ConvTranspose2d(nf, nc, 4, 2, 1) + output
+ * activation (conv.py:255-263: `conv[2]` = make_conv_block(ConvTranspose2d(2nf, nf)), `conv[3]` = ConvTranspose2d(nf, nc)),
+ * i.e. aten::native_batch_norm + leaky_relu_ + convolution (+ sigmoid) forward and their three backward kernels, WITHOUT
+ * materialising the normalised tensor act = act_bn(gamma * (y - mean) * invstd + beta) or its gradient:
+ *   forward : out = act_out(convT(act) + bias), act built from y on the operand path of the GEMM + col2im kernel;
+ *   wgrad   : dw[K][C][4][4] += sum_pix act[pix][k] * dout[...]          (act rebuilt from y on the operand path);
+ *   backward: the gradient w.r.t. act is a direct convolution of `dout` (the gradient w.r.t. the convT's pre-activation
+ *             output, [N,H,W,C]) with wp_direct = vs_pack_weight(w, K, C, 16, swap=0); it is produced tile by tile on the
+ *             tensor cores and consumed in the epilogue: phase 0 accumulates sums[G][K][2] += {sum dz, sum dz * xhat}
+ *             (zeroed by the caller), phase 1 writes dy = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat))
+ *             (train != 0) or gamma * invstd * dz (train == 0) and adds the affine gradients from `sums`.
+ * g is the geometry of the THIN transposed convolution: big = out [N,H,W,C], small = y [N,P,Q,K]; mean / invstd are
+ * [bn_groups][K] as written by vs_bn_finalize.  vs_tail_eligible: 1 when all four kernels accept g (bf16, K == 64,
+ * C <= 2, k4 s2 p1, whole 128-pixel tiles), 0 otherwise; the other entry points fail for a non-eligible g. */
+int vs_tail_eligible(const vs_conv_geom* g);
+int vs_tail_forward(const vs_conv_geom* g, const void* y, const float* mean, const float* invstd, const float* gamma,
+                    const float* beta, int32_t bn_groups, int32_t bn_act, const void* wp, const float* bias, void* out,
+                    void* stream);
+int vs_tail_wgrad(const vs_conv_geom* g, const void* y, const float* mean, const float* invstd, const float* gamma,
+                  const float* beta, int32_t bn_groups, int32_t bn_act, const void* dout, float* dw, void* stream);
+int vs_tail_bn_backward(const vs_conv_geom* g, const void* y, const float* mean, const float* invstd, const float* gamma,
+                        const float* beta, int32_t bn_groups, int32_t bn_act, const void* dout, const void* wp_direct,
+                        int32_t phase, int32_t train, double* sums, void* dy, float* dgamma, float* dbeta, void* stream);
+
 /* ---- optimizer -----------------------------------------------------------------------------
  * replaces: torch.optim.Adam.step (main.py:145, train.py:162): eps-outside-sqrt, bias-corrected, no decay.
  * One launch over a flat, 16-byte aligned parameter arena.  The 1-based step count is step_host, or

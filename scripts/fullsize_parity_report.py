@@ -27,10 +27,13 @@ for name in args.configs:
     ref32 = fullsize.oracle_run(name, 'float32', args.batch)
     t1 = time.time()
     refbf = fullsize.oracle_run(name, 'autocast_bf16', args.batch)
+    ref32c = fullsize.oracle_run(name, 'float32_cuda', args.batch)
     entry = {'oracle_seconds': t1 - t0, 'reference_fp32_vs_fp64': fullsize.summary(fullsize.compare(ref32, truth)),
+             'reference_fp32_cudnn_vs_fp64': fullsize.summary(fullsize.compare(ref32c, truth, ref32)),
              'reference_autocast_bf16_vs_fp64': fullsize.summary(fullsize.compare(refbf, truth))}
-    for label, dt, ref in (('cuda_fp32_vs_fp64', torch.float32, ref32), ('cuda_bf16_vs_fp64', torch.bfloat16, refbf)):
-        rep = fullsize.compare(fullsize.cuda_run(name, dt, args.batch), truth, ref)
+    for label, dt, ref, refb in (('cuda_fp32_vs_fp64', torch.float32, ref32, ref32c),
+                                 ('cuda_bf16_vs_fp64', torch.bfloat16, refbf, None)):
+        rep = fullsize.compare(fullsize.cuda_run(name, dt, args.batch), truth, ref, refb)
         entry[label] = fullsize.summary(rep)
         entry[label]['grads_by_tensor'] = {n: [float('%.3e' % v[0]), float('%.3e' % v[1])] for n, v in rep['grads'].items()}
     report[name] = entry

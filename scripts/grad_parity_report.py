@@ -36,13 +36,14 @@ for name in NAMES:
     if ctx is not None:
         ctx.__exit__(None, None, None)
     gmax = np.nanmax(g['grad64'][:, 0])
-    ours, ref = [], []
+    ours, ref, names = [], [], []
     for n, r32, r64 in zip(g['grad_names'], g['grad32'], g['grad64']):
         if np.isnan(r32[0]) or r64[0] < 1e-6 * gmax:       # unused / mathematically-zero gradients
             continue
         s = summarize(str(n), grads[str(n)])
         ours.append(float(np.abs(s - r64).max() / abs(r64[0])))
         ref.append(float(np.abs(r32 - r64).max() / abs(r64[0])))
+        names.append(str(n))
     ours, ref = np.array(ours), np.array(ref)
     loss = np.array([float(out[k].detach()) for k in ('ae', 's', 'pred', 't', 'total')])
     report[name] = {
@@ -50,6 +51,7 @@ for name in NAMES:
         'ours_vs_fp64': {'median': float(np.median(ours)), 'max': float(ours.max()), 'over_1e-4': int((ours > 1e-4).sum())},
         'reference_fp32_vs_fp64': {'median': float(np.median(ref)), 'max': float(ref.max()), 'over_1e-4': int((ref > 1e-4).sum())},
         'loss_rel_err_vs_reference_fp32': float(np.abs(loss - g['loss32']).max() / np.abs(g['loss32']).max()),
+        'worst_tensors': [[names[i], float('%.3e' % ours[i]), float('%.3e' % ref[i])] for i in np.argsort(-ours)[:12]],
     }
     print(name, json.dumps(report[name]))
 os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace vs {
 
@@ -57,8 +58,14 @@ int conv_wgrad_simt(const vs_conv_geom* g, const void* small_, const void* big, 
 int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                         double* stats, cudaStream_t stream);
 int conv_forward_col2im(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
-                        double* stats, cudaStream_t stream);
-int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream);
+                        double* stats, cudaStream_t stream, const BnApplyArgs* bn = nullptr);
+int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream,
+                      const BnApplyArgs* bn = nullptr);
+int conv_forward_col2im_eligible(const vs_conv_geom* g, int mode);
+int tail_eligible(const vs_conv_geom* g);
+int tail_bn_backward(const vs_conv_geom* g, const BnBwdArgs& bb, const void* dout, const void* wp, int phase, double* sums, void* dy,
+                     cudaStream_t stream);
+void bn_param_grad(const double* sums, int G, int C, float* dgamma, float* dbeta, cudaStream_t stream);   // bn.cu
 int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                     double* stats, cudaStream_t stream);
 
@@ -131,4 +138,58 @@ extern "C" int vs_conv_wgrad(const vs_conv_geom* g, const void* small_, const vo
     rc = conv_wgrad_tc(g, small_, big, dw, as_stream(stream));
     if (rc >= 0) return rc;
     return conv_wgrad_simt(g, small_, big, dw, as_stream(stream));
+}
+
+
+// ---------------------------------------------------------------------------------------------- fused decoder tail
+static int tail_check(const vs_conv_geom* g, int32_t bn_groups) {
+    if (int rc = check_geom(g)) return rc;
+    VS_REQUIRE(bn_groups >= 1 && g->N % bn_groups == 0, "tail: N=%d not divisible by the BatchNorm groups=%d", g->N, bn_groups);
+    VS_REQUIRE(vs_tail_eligible(g) == 1, "tail: geometry not eligible for the fused kernels (query vs_tail_eligible first)");
+    return 0;
+}
+
+extern "C" int vs_tail_eligible(const vs_conv_geom* g) {
+    if (check_geom(g)) return -1;
+    return (conv_forward_col2im_eligible(g, VS_CONV_TRANSPOSED) && tail_eligible(g)) ? 1 : 0;
+}
+
+extern "C" int vs_tail_forward(const vs_conv_geom* g, const void* y, const float* mean, const float* invstd, const float* gamma,
+                               const float* beta, int32_t bn_groups, int32_t bn_act, const void* wp, const float* bias, void* out,
+                               void* stream) {
+    if (int rc = tail_check(g, bn_groups)) return rc;
+    BnApplyArgs bn = {mean, invstd, gamma, beta, g->N / bn_groups, bn_act};
+    int rc = conv_forward_col2im(g, VS_CONV_TRANSPOSED, y, wp, bias, out, nullptr, as_stream(stream), &bn);
+    VS_REQUIRE(rc >= 0, "tail_forward: operands not 16-byte aligned");
+    return rc;
+}
+
+extern "C" int vs_tail_wgrad(const vs_conv_geom* g, const void* y, const float* mean, const float* invstd, const float* gamma,
+                             const float* beta, int32_t bn_groups, int32_t bn_act, const void* dout, float* dw, void* stream) {
+    if (int rc = tail_check(g, bn_groups)) return rc;
+    BnApplyArgs bn = {mean, invstd, gamma, beta, g->N / bn_groups, bn_act};
+    int rc = conv_wgrad_im2col(g, y, dout, dw, as_stream(stream), &bn);
+    VS_REQUIRE(rc >= 0, "tail_wgrad: operands not 16-byte aligned");
+    return rc;
+}
+
+extern "C" int vs_tail_bn_backward(const vs_conv_geom* g, const void* y, const float* mean, const float* invstd, const float* gamma,
+                                   const float* beta, int32_t bn_groups, int32_t bn_act, const void* dout, const void* wp_direct,
+                                   int32_t phase, int32_t train, double* sums, void* dy, float* dgamma, float* dbeta, void* stream) {
+    if (int rc = tail_check(g, bn_groups)) return rc;
+    VS_REQUIRE(phase == 0 || phase == 1, "tail_bn_backward: phase must be 0 (reduce) or 1 (apply)");
+    VS_REQUIRE(sums != nullptr && (phase == 0 || dy != nullptr), "tail_bn_backward: null output");
+    BnBwdArgs bb;
+    bb.y = reinterpret_cast<const __nv_bfloat16*>(y);
+    bb.mean = mean; bb.invstd = invstd; bb.gamma = gamma; bb.beta = beta; bb.sums = sums;
+    bb.n_per_group = g->N / bn_groups; bb.act = bn_act; bb.train = train;
+    bb.inv_count = 1.f / (float)((long long)bb.n_per_group * g->P * g->Q);
+    int rc = tail_bn_backward(g, bb, dout, wp_direct, phase, sums, dy, as_stream(stream));
+    VS_REQUIRE(rc >= 0, "tail_bn_backward: operands not 16-byte aligned");
+    if (rc) return rc;
+    if (phase == 1 && (dgamma != nullptr || dbeta != nullptr)) {
+        bn_param_grad(sums, bn_groups, g->K, dgamma, dbeta, as_stream(stream));
+        rc = launched("bn_param_grad_kernel");
+    }
+    return rc;
 }

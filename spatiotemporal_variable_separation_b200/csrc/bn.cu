@@ -175,6 +175,9 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int G, int
     if (dgamma) dgamma[c] += (float)s2;
 }
 
+void bn_param_grad(const double* sums, int G, int C, float* dgamma, float* dbeta, cudaStream_t stream) {
+    bn_param_grad_kernel<<<(int)cdiv(C, 128), 128, 0, stream>>>(sums, G, C, dgamma, dbeta);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Fast path ("column-stationary"): every thread owns 16 bytes of channels (8 bf16 / 4 fp32) for the whole

@@ -31,7 +31,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-constexpr int C2I_THREADS = 320, C2I_MAX_TILES = 8, C2I_MAX_KCHUNKS = 4;
+constexpr int C2I_THREADS = 320, C2I_XF_THREADS = 128, C2I_MAX_TILES = 8, C2I_MAX_KCHUNKS = 4;
 
 template <int NB, int STAGES>
 struct C2iSmem {
@@ -40,14 +40,18 @@ struct C2iSmem {
     static constexpr int G_BYTES = NB * C2I_MAX_TILES * 128 * 4;
     static constexpr int BAR_OFF = G_OFF + G_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;
-    static_assert((2 * STAGES + 6) * 8 <= 256, "barrier area");
+    static_assert((3 * STAGES + 6) * 8 <= 256, "barrier area");
 };
 
-template <int NB, int STAGES>
-__global__ void __launch_bounds__(C2I_THREADS, 1) convT_col2im_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                     const __grid_constant__ CUtensorMap map_b,
-                                                                     const __grid_constant__ Col2imParams p,
-                                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+// XF: the input tensor is the PRE-BatchNorm output y of the previous layer; four extra warps apply
+//   act(gamma * (y - mean[g]) * invstd[g] + beta)   (the arithmetic of bn_act_fwd_col_kernel, bit for bit)
+// to every A stage in shared memory between its TMA landing and the MMA, so the normalised tensor (268 MB for the
+// Moving-MNIST decoder) is never written to or re-read from HBM.
+template <int NB, int STAGES, bool XF>
+__global__ void __launch_bounds__(C2I_THREADS + (XF ? C2I_XF_THREADS : 0), 1)
+convT_col2im_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ Col2imParams p, const __grid_constant__ BnApplyArgs bn,
+                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
     using S = C2iSmem<NB, STAGES>;
     constexpr int ACC_COLS = C2I_MAX_TILES * NB;
     extern __shared__ uint8_t smem_raw[];
@@ -61,6 +65,7 @@ __global__ void __launch_bounds__(C2I_THREADS, 1) convT_col2im_kernel(const __gr
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint64_t* b_full = bars + 2 * STAGES + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+    uint64_t* xready = bars + 2 * STAGES + 6;        // [STAGES] XF: stage transformed in place, ready for the MMA
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int PQ = p.P * p.Q;
@@ -71,6 +76,7 @@ __global__ void __launch_bounds__(C2I_THREADS, 1) convT_col2im_kernel(const __gr
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
         mbar_init(b_full, 1);
+        if (XF) for (int s = 0; s < STAGES; ++s) mbar_init(&xready[s], C2I_XF_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<2 * ACC_COLS>(tmem_slot);
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(C2I_THREADS, 1) convT_col2im_kernel(const __gr
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS + t * NB);
                     for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
                         const int s = it % STAGES;
-                        mbar_wait(&full[s], (it / STAGES) & 1);
+                        mbar_wait(XF ? &xready[s] : &full[s], (it / STAGES) & 1);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smem + s * S::A_BYTES), b_addr = smem_u32(b_smem + kc * NB * 128);
 #pragma unroll
@@ -120,6 +126,51 @@ __global__ void __launch_bounds__(C2I_THREADS, 1) convT_col2im_kernel(const __gr
                 }
                 umma_commit(&tmem_full[acc]);
             }
+        }
+    } else if (XF && warp >= C2I_THREADS / 32) {
+        // ===== BatchNorm + activation applied to the landed stage, in place =====
+        // 16-byte chunk id = t + 128 i: pixel row t/8 + 16 i, physical chunk t%8; the 128-byte swizzle XORs the chunk
+        // index with (row & 7) = ((t/8) & 7), so a thread always owns the SAME eight channels: parameters in registers
+        const int t = threadIdx.x - C2I_THREADS;
+        const int phys = t & 7, rsub = t >> 3;
+        const int cg = phys ^ (rsub & 7);
+        float mu[8], is[8], ga[8], be[8];
+        int cur_g = -1, cur_kc = -1, it = 0;
+        for (int img = blockIdx.x; img < p.N; img += gridDim.x) {
+            const int g = img / bn.n_per_group;
+            for (int tl = 0; tl < p.tiles; ++tl)
+                for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                    if (g != cur_g || kc != cur_kc) {
+                        cur_g = g; cur_kc = kc;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = kc * 64 + cg * 8 + e;
+                            mu[e] = __ldg(bn.mean + (long long)g * p.K + c); is[e] = __ldg(bn.invstd + (long long)g * p.K + c);
+                            ga[e] = __ldg(bn.gamma + c); be[e] = __ldg(bn.beta + c);
+                        }
+                    }
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    uint8_t* base = smem + s * S::A_BYTES + rsub * 128 + phys * 16;
+#pragma unroll
+                    for (int i = 0; i < TC_BM / 16; ++i) {
+                        uint4* q = reinterpret_cast<uint4*>(base + i * 16 * 128);
+                        uint4 v = *q;
+                        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float a0 = __uint_as_float(w[e] << 16), a1 = __uint_as_float(w[e] & 0xffff0000u);
+                            const float r0 = act_fwd(ga[2 * e] * ((a0 - mu[2 * e]) * is[2 * e]) + be[2 * e], bn.act);
+                            const float r1 = act_fwd(ga[2 * e + 1] * ((a1 - mu[2 * e + 1]) * is[2 * e + 1]) + be[2 * e + 1], bn.act);
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
+                            w[e] = *reinterpret_cast<uint32_t*>(&b2);
+                        }
+                        *q = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&xready[s]);
+                }
         }
     } else {
         // ===== epilogue (8 warps): TMEM -> G in shared memory, then the output gather =====
@@ -218,24 +269,26 @@ int conv_forward_col2im_eligible(const vs_conv_geom* g, int mode) {
     return 1;
 }
 
-template <int NB, int STAGES>
-static int launch_c2i(const CUtensorMap& ma, const CUtensorMap& mb, const Col2imParams& p, const float* bias, void* out,
-                      cudaStream_t stream) {
+template <int NB, int STAGES, bool XF>
+static int launch_c2i(const CUtensorMap& ma, const CUtensorMap& mb, const Col2imParams& p, const BnApplyArgs& bn, const float* bias,
+                      void* out, cudaStream_t stream) {
     using S = C2iSmem<NB, STAGES>;
     static DeviceOnce configured;
     if (!configured.flag()) {
-        cudaError_t e = cudaFuncSetAttribute(convT_col2im_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(convT_col2im_kernel<NB, STAGES, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return fail("convT_col2im_kernel smem attribute: %s", cudaGetErrorString(e));
         configured.flag() = true;
     }
     const int grid = p.N < num_sms() ? p.N : num_sms();
-    convT_col2im_kernel<NB, STAGES><<<grid, C2I_THREADS, S::TOTAL, stream>>>(ma, mb, p, bias, (__nv_bfloat16*)out);
+    convT_col2im_kernel<NB, STAGES, XF><<<grid, C2I_THREADS + (XF ? C2I_XF_THREADS : 0), S::TOTAL, stream>>>(
+        ma, mb, p, bn, bias, (__nv_bfloat16*)out);
     return launched("convT_col2im_kernel");
 }
 
-// returns 0 = done, -1 = geometry not eligible, >0 = error
+// returns 0 = done, -1 = geometry not eligible, >0 = error.  bn != nullptr: `in` is the pre-BatchNorm tensor y and the
+// normalisation + activation described by *bn is applied on the operand path (the fused decoder tail)
 int conv_forward_col2im(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
-                        double* stats, cudaStream_t stream) {
+                        double* stats, cudaStream_t stream, const BnApplyArgs* bn) {
     if (stats != nullptr || !conv_forward_col2im_eligible(g, mode)) return -1;
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wp) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
     EncodeTiledFn enc = encode_fn();
@@ -268,7 +321,11 @@ int conv_forward_col2im(const vs_conv_geom* g, int mode, const void* in, const v
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(col2im B) failed: %d", (int)r);
     }
-    return NB == 16 ? launch_c2i<16, 6>(ma, mb, p, bias, out, stream) : launch_c2i<32, 4>(ma, mb, p, bias, out, stream);
+    BnApplyArgs none;
+    memset(&none, 0, sizeof(none));
+    if (bn != nullptr)
+        return NB == 16 ? launch_c2i<16, 6, true>(ma, mb, p, *bn, bias, out, stream) : launch_c2i<32, 4, true>(ma, mb, p, *bn, bias, out, stream);
+    return NB == 16 ? launch_c2i<16, 6, false>(ma, mb, p, none, bias, out, stream) : launch_c2i<32, 4, false>(ma, mb, p, none, bias, out, stream);
 }
 
 }  // namespace vs

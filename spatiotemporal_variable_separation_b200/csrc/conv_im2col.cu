@@ -99,19 +99,32 @@ struct ImfSmem {
     static constexpr int OUT_BYTES = TS ? 2 * TC_BM * 128 : 0;       // two staged bf16 output tiles (BN = 64)
     static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
     static constexpr int TAB_OFF = BAR_OFF + 256, STAT_OFF = TAB_OFF + IM_MAX_KK * 4;
-    static constexpr int PATCH_OFF = (STAT_OFF + BN * 2 * 4 + 127) / 128 * 128;
+    static constexpr int PRM_OFF = (STAT_OFF + BN * 2 * 4 + 15) / 16 * 16;             // [BN][8] floats (EPI != 0)
+    static constexpr int PATCH_OFF = (PRM_OFF + BN * 8 * 4 + 127) / 128 * 128;
     static constexpr int total(int patch_stage) { return PATCH_OFF + IM_PST * patch_stage + 1024; }
     static_assert((2 * STAGES + 2 * IM_PST + 5) * 8 <= 256, "barrier area");
     static_assert(!TS || BN == 64, "the staged epilogue handles one 128-byte row per pixel");
 };
 
-template <int BN, int KC, int STAGES, bool TS>
+// EPI selects what the epilogue does with the accumulator tile D[pixel][k]:
+//   0  out = act(D + bias)  (+ BatchNorm statistics of D + bias)                                    -- a convolution
+//   1  D is the gradient w.r.t. the OUTPUT of a BatchNorm + activation block whose pre-BatchNorm tensor is bb.y:
+//      dz = D * act'(gamma * xhat + beta),  stats[g][k] += {sum dz, sum dz * xhat}; nothing is stored
+//   2  same dz, then  out = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat))  (the BatchNorm backward)
+// Modes 1 and 2 are the backward of the fused decoder tail: the gradient w.r.t. the normalised tensor (268 MB for the
+// Moving-MNIST decoder) is recomputed from the 16x smaller frame gradient in both passes instead of being written
+// once and read twice.
+template <int BN, int KC, int STAGES, bool TS, int EPI>
 __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid_constant__ CUtensorMap map_big,
                                                                    const __grid_constant__ CUtensorMap map_out,
                                                                    const __grid_constant__ Im2colParams p,
+                                                                   const __grid_constant__ BnBwdArgs bb,
                                                                    const unsigned short* __restrict__ wp,
                                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                                    double* __restrict__ stats) {
+    static_assert(EPI == 0 || (BN == 64 && KC == 1), "the BatchNorm-backward epilogues handle one 64-channel tile");
+    static_assert(EPI != 1 || !TS, "the reduction pass stores nothing");
+    static_assert(EPI != 2 || TS, "the apply pass stores through the staged tile");
     using S = ImfSmem<BN, KC, STAGES, TS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -127,6 +140,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + IM_PST);
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem + S::TAB_OFF);
     float* sstat = reinterpret_cast<float*>(smem + S::STAT_OFF);
+    float4* sprm = reinterpret_cast<float4*>(smem + S::PRM_OFF);      // EPI != 0: per channel {invstd, -mean*invstd, gamma, beta}, {gamma*invstd, mean dz, mean dz*xhat, 0}
     uint8_t* pbuf = smem + S::PATCH_OFF;             // [IM_PST][p.patch_stage]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -243,6 +257,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
         const int w = m & (p.WT - 1), h = (m >> p.wt_shift) & (p.HT - 1), n = m >> (p.wt_shift + p.ht_shift);
         int lt = 0;
         int stat_g = -1;
+        int prm_g = -1;
         double stat_acc[2 * BN / 128] = {};
         for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
             VS_IM_DECODE(idx)
@@ -250,14 +265,60 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
             const int pp = i0 + h, qq = j0 + w, nn = b0 + n;
             const bool ok = pp < p.P && qq < p.Q && nn < p.N;
             __nv_bfloat16* dst = out + (((long long)nn * p.P + pp) * p.Q + qq) * p.K;
+            uint4 yraw[EPI != 0 ? BN / 8 : 1];
+            if (EPI != 0) {
+                // this pixel's row of the pre-BatchNorm tensor (128 contiguous bytes), requested before the accumulator wait
+                const uint4* yrow = reinterpret_cast<const uint4*>(bb.y + (((long long)nn * p.P + pp) * p.Q + qq) * p.K);
+#pragma unroll
+                for (int v = 0; v < BN / 8; ++v) yraw[v] = ok ? __ldg(yrow + v) : make_uint4(0, 0, 0, 0);
+                // per-channel constants of this tile's BatchNorm group (a tile is one image: NT == 1)
+                const int g = b0 / bb.n_per_group;
+                if (g != prm_g) {                                       // uniform over the epilogue warps
+                    asm volatile("bar.sync 1, 128;" ::: "memory");      // everybody is done with the previous table
+                    const int c = threadIdx.x - 192;
+                    if (c < BN && c < p.K) {
+                        const float is = __ldg(bb.invstd + (long long)g * p.K + c), mu = __ldg(bb.mean + (long long)g * p.K + c);
+                        const float ga = __ldg(bb.gamma + c), be = __ldg(bb.beta + c);
+                        float m1 = 0.f, m2 = 0.f;
+                        if (EPI == 2 && bb.train) {
+                            m1 = (float)bb.sums[((long long)g * p.K + c) * 2] * bb.inv_count;
+                            m2 = (float)bb.sums[((long long)g * p.K + c) * 2 + 1] * bb.inv_count;
+                        }
+                        sprm[2 * c] = make_float4(is, -mu * is, ga, be);
+                        sprm[2 * c + 1] = make_float4(ga * is, m1, m2, 0.f);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    prm_g = g;
+                }
+            }
             mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
+            // (fully unrolled for the BatchNorm-backward epilogues: the y row then stays in registers)
+            constexpr int C0_UNROLL = EPI != 0 ? BN / 32 : 1;
+#pragma unroll C0_UNROLL
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
                 float xs[32];
-                if (p.has_bias) {          // uniform: dgrad launches carry no bias and skip the 32 shuffles
+                float xh[EPI == 1 ? 32 : 1];          // EPI 1: dz * xhat
+                if (EPI != 0) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const uint4 yq = yraw[(c0 + c) >> 3];
+                        const uint32_t wv = ((c >> 1) & 3) == 0 ? yq.x : ((c >> 1) & 3) == 1 ? yq.y : ((c >> 1) & 3) == 2 ? yq.z : yq.w;
+                        const float yv = (c & 1) ? __uint_as_float(wv & 0xffff0000u) : __uint_as_float(wv << 16);
+                        const float4 pa = sprm[2 * (c0 + c)];
+                        const float xhat = fmaf(yv, pa.x, pa.y);
+                        const float dz = __uint_as_float(r[c]) * act_grad_from_in(fmaf(pa.z, xhat, pa.w), bb.act);
+                        if (EPI == 2) {
+                            const float4 pb = sprm[2 * (c0 + c) + 1];
+                            xs[c] = pb.x * (dz - pb.y - xhat * pb.z);
+                        } else {
+                            xs[c] = ok ? dz : 0.f;
+                            xh[c] = ok ? dz * xhat : 0.f;
+                        }
+                    }
+                } else if (p.has_bias) {          // uniform: dgrad launches carry no bias and skip the 32 shuffles
                     const float bias_l = (p.has_bias && c0 + lane < p.K) ? __ldg(bias + c0 + lane) : 0.f;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
@@ -265,8 +326,10 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
 #pragma unroll
                     for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]);
                 }
-                if (TS) {
-                    stage_row32(obuf + (lt & 1) * (TC_BM * 128), m, c0, xs, p.act);
+                if (EPI == 1) {
+                    // reduction pass: nothing is stored
+                } else if (TS) {
+                    stage_row32(obuf + (lt & 1) * (TC_BM * 128), m, c0, xs, EPI == 2 ? (int)VS_ACT_NONE : p.act);
                 } else if (p.partial || BN > p.K) {
                     if (ok) {
 #pragma unroll
@@ -287,7 +350,13 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
                         *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
-                if (stats != nullptr) {
+                if (EPI == 1) {
+                    // {sum dz, sum dz * xhat} over the 32 rows of this warp (masked rows hold zeros), in place
+                    const float s1 = warp_transpose_sum32(xs, lane);
+                    const float s2 = warp_transpose_sum32(xh, lane);
+                    atomicAdd(&sstat[(c0 + lane) * 2], s1);
+                    atomicAdd(&sstat[(c0 + lane) * 2 + 1], s2);
+                } else if (EPI == 0 && stats != nullptr) {
                     float wk[32];
 #pragma unroll
                     for (int c = 0; c < 32; ++c) wk[c] = ok ? xs[c] : 0.f;
@@ -313,7 +382,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
                     tma_store_commit();
                 }
             }
-            if (stats != nullptr) {
+            if (EPI != 2 && stats != nullptr) {
                 // running fp64 sums per thread (entries t and t + 128), flushed when the BatchNorm group changes
                 if (!TS) asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int g = b0 / p.n_per_group;
@@ -334,7 +403,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
         }
-        if (stats != nullptr && stat_g >= 0) {
+        if (EPI != 2 && stats != nullptr && stat_g >= 0) {
             const int t = threadIdx.x - 192;
 #pragma unroll
             for (int e = 0; e < 2 * BN / 128; ++e) {
@@ -405,21 +474,23 @@ int conv_forward_im2col_eligible(const vs_conv_geom* g, int mode) {
     return im2col_plan(p, g, 128, IM_PATCH_STAGE) ? 1 : 0;
 }
 
-template <int BN, int KC, int STAGES, bool TS>
+template <int BN, int KC, int STAGES, bool TS, int EPI = 0>
 static int launch_imf(const CUtensorMap& mb, const CUtensorMap& mo, const Im2colParams& p, const void* wp, const float* bias,
-                      void* out, double* stats, cudaStream_t stream) {
+                      void* out, double* stats, cudaStream_t stream, const BnBwdArgs* bb = nullptr) {
     using S = ImfSmem<BN, KC, STAGES, TS>;
     static DeviceOnce configured;
     if (!configured.flag()) {
-        cudaError_t e = cudaFuncSetAttribute(im2col_fwd_kernel<BN, KC, STAGES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(im2col_fwd_kernel<BN, KC, STAGES, TS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              S::total(IM_PATCH_STAGE));
         if (e != cudaSuccess) return fail("im2col_fwd_kernel smem attribute: %s", cudaGetErrorString(e));
         configured.flag() = true;
     }
+    BnBwdArgs none;
+    memset(&none, 0, sizeof(none));
     const int resident = 2 * num_sms();
     const int grid = p.total_tiles < resident ? p.total_tiles : resident;
-    im2col_fwd_kernel<BN, KC, STAGES, TS><<<grid, IMF_THREADS, S::total(p.patch_stage), stream>>>(
-        mb, mo, p, (const unsigned short*)wp, bias, (__nv_bfloat16*)out, stats);
+    im2col_fwd_kernel<BN, KC, STAGES, TS, EPI><<<grid, IMF_THREADS, S::total(p.patch_stage), stream>>>(
+        mb, mo, p, bb ? *bb : none, (const unsigned short*)wp, bias, (__nv_bfloat16*)out, stats);
     return launched("im2col_fwd_kernel");
 }
 
@@ -466,10 +537,15 @@ int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const v
 // =================================================================================================== weight gradient
 // D[kk][k] += sum over 64-pixel blocks; warps: 0 = TMA producer (boxes of `small`), 1 = MMA issuer, 2..5 = im2col
 // builders during the reduction, then the epilogue (fp32 reductions into the torch-layout gradient).
-template <int BN, int STAGES>
+// XF: `small` is the PRE-BatchNorm tensor y of the layer below; the builder warps apply BatchNorm + activation to every
+// landed box of it in shared memory (bit for bit the arithmetic of bn_act_fwd_col_kernel) before the MMA reads it, so the
+// weight gradient of the fused decoder tail needs no materialised normalised tensor.
+template <int BN, int STAGES, bool XF>
 __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_constant__ CUtensorMap map_small,
                                                               const __grid_constant__ CUtensorMap map_big,
-                                                              const __grid_constant__ Im2colParams p, float* __restrict__ dw) {
+                                                              const __grid_constant__ Im2colParams p,
+                                                              const __grid_constant__ BnApplyArgs bn, float* __restrict__ dw) {
+    static_assert(!XF || BN == 64, "operand transform: one 64-channel box per stage");
     constexpr int PIX = 64, CHUNK = 64 * PIX * 2;
     constexpr int A_BYTES = 2 * CHUNK, B_BYTES = BN * PIX * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -481,6 +557,7 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
     uint64_t* pready = bars + 2 * STAGES + 1;
     uint64_t* pempty = pready + IM_PST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + IM_PST);
+    uint64_t* bfull = pempty + IM_PST + 1;           // [STAGES] XF: the box of `small` has landed (transform may start)
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256);
     uint8_t* pbuf = smem + STAGES * STAGE_BYTES + 256 + IM_MAX_KK * 4;       // [IM_PST][IM_PATCH_STAGE_W], 128-byte aligned
 
@@ -494,7 +571,8 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_small);
         prefetch_tmap(&map_big);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }     // TMA expect + 4 builder warps
+        // full: TMA expect + 4 builder warps (XF: the builders alone, after they have transformed the landed box)
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], XF ? 4 : 5); mbar_init(&empty[i], 1); if (XF) mbar_init(&bfull[i], 1); }
         for (int i = 0; i < IM_PST; ++i) { mbar_init(&pready[i], 1); mbar_init(&pempty[i], 4); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -532,9 +610,10 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
                 tma_load_3d(pbuf + ps * IM_PATCH_STAGE_W, &map_big, &pready[ps], ((q0 * p.stride - p.pad) * p.C) & ~7, p0 * p.stride - p.pad, b0);
                 mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
                 uint8_t* b_dst = smem + st * STAGE_BYTES + A_BYTES;
-                mbar_expect_tx(&full[st], B_BYTES);
+                uint64_t* bbar = XF ? &bfull[st] : &full[st];
+                mbar_expect_tx(bbar, B_BYTES);
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j) tma_load_4d(b_dst + j * CHUNK, &map_small, &full[st], kt * BN + j * 64, q0, p0, b0);
+                for (int j = 0; j < BN / 64; ++j) tma_load_4d(b_dst + j * CHUNK, &map_small, bbar, kt * BN + j * 64, q0, p0, b0);
             }
         }
     } else if (warp == 1) {
@@ -572,6 +651,11 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
             for (int i = 0; i < 8; ++i) { co.off[i] = c0.off[i]; co.off[8 + i] = c1.off[i]; }
             co.valid = (c0.valid & 0xffu) | ((c1.valid & 0xffu) << 8);
         }
+        // XF: chunk id = t + 128 i of the landed [64 pixels][128 B] box: row t/8 + 16 i, physical chunk t%8 -> always the same
+        // eight channels for this thread (the swizzle XORs the chunk index with row & 7 = (t/8) & 7)
+        const int xphys = t & 7, xrsub = t >> 3, xcg = xphys ^ (xrsub & 7);
+        float xmu[XF ? 8 : 1], xis[XF ? 8 : 1], xga[XF ? 8 : 1], xbe[XF ? 8 : 1];
+        int xg = -1;
         for (int kb = 0; kb < nkb; ++kb) {
             const int st = kb % STAGES, ps = kb % IM_PST;
             const int q0 = ((pt0 + kb) % p.tiles_w) * p.WT;
@@ -579,6 +663,18 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
             uint8_t* a_dst = smem + st * STAGE_BYTES;
             mbar_wait(&pready[ps], (kb / IM_PST) & 1);
             mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
+            if (XF) {
+                const int g = ((pt0 + kb) / (p.tiles_w * p.tiles_h)) * p.NT / bn.n_per_group;
+                if (g != xg) {
+                    xg = g;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = kt * BN + xcg * 8 + e;
+                        xmu[e] = __ldg(bn.mean + (long long)g * p.K + c); xis[e] = __ldg(bn.invstd + (long long)g * p.K + c);
+                        xga[e] = __ldg(bn.gamma + c); xbe[e] = __ldg(bn.beta + c);
+                    }
+                }
+            }
             if (cached) {
                 if (cj < p.nchunk16) *reinterpret_cast<uint4*>(a_dst + cm * 128 + ((cj ^ (cm & 7)) << 4)) = gather_cached(pb, co, 0);
                 if (cj + 2 < p.nchunk16) *reinterpret_cast<uint4*>(a_dst + cm * 128 + (((cj + 2) ^ (cm & 7)) << 4)) = gather_cached(pb, co, 1);
@@ -589,6 +685,25 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
                     const int base = h * p.stride * p.PWCp + w * p.stride * p.C;
                     const uint4 v = im2col_chunk(p, pb, tab, base, j);
                     *reinterpret_cast<uint4*>(a_dst + (j >> 3) * CHUNK + m * 128 + (((j & 7) ^ (m & 7)) << 4)) = v;
+                }
+            }
+            if (XF) {
+                mbar_wait(&bfull[st], (kb / STAGES) & 1);
+                uint8_t* base = a_dst + A_BYTES + xrsub * 128 + xphys * 16;
+#pragma unroll
+                for (int i = 0; i < PIX / 16; ++i) {
+                    uint4* qp = reinterpret_cast<uint4*>(base + i * 16 * 128);
+                    uint4 v = *qp;
+                    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a0 = __uint_as_float(wv[e] << 16), a1 = __uint_as_float(wv[e] & 0xffff0000u);
+                        const float r0 = act_fwd(xga[2 * e] * ((a0 - xmu[2 * e]) * xis[2 * e]) + xbe[2 * e], bn.act);
+                        const float r1 = act_fwd(xga[2 * e + 1] * ((a1 - xmu[2 * e + 1]) * xis[2 * e + 1]) + xbe[2 * e + 1], bn.act);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
+                        wv[e] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    *qp = make_uint4(wv[0], wv[1], wv[2], wv[3]);
                 }
             }
             fence_proxy_async();
@@ -622,24 +737,27 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
     }
 }
 
-template <int BN, int STAGES>
-static int launch_imw(const CUtensorMap& ms, const CUtensorMap& mb, const Im2colParams& p, float* dw, int k_tiles, int splits,
-                      cudaStream_t stream) {
+template <int BN, int STAGES, bool XF>
+static int launch_imw(const CUtensorMap& ms, const CUtensorMap& mb, const Im2colParams& p, const BnApplyArgs& bn, float* dw, int k_tiles,
+                      int splits, cudaStream_t stream) {
     constexpr int SMEM = STAGES * (2 * 64 * 64 * 2 + BN * 64 * 2) + 1024 + 256 + IM_MAX_KK * 4 + IM_PST * IM_PATCH_STAGE_W;
-    static_assert((2 * STAGES + 2 * IM_PST + 2) * 8 <= 256, "barrier area");
+    static_assert((3 * STAGES + 2 * IM_PST + 2) * 8 <= 256, "barrier area");
     static DeviceOnce configured;
     if (!configured.flag()) {
-        cudaError_t e = cudaFuncSetAttribute(im2col_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(im2col_wgrad_kernel<BN, STAGES, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return fail("im2col_wgrad_kernel smem attribute: %s", cudaGetErrorString(e));
         configured.flag() = true;
     }
     dim3 grid((unsigned)k_tiles, 1, (unsigned)splits);
-    im2col_wgrad_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(ms, mb, p, dw);
+    im2col_wgrad_kernel<BN, STAGES, XF><<<grid, 192, SMEM, stream>>>(ms, mb, p, bn, dw);
     return launched("im2col_wgrad_kernel");
 }
 
-int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream) {
+// bn != nullptr: `small_` is the pre-BatchNorm tensor y; BatchNorm + activation is applied on the operand path
+int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big, float* dw, cudaStream_t stream,
+                      const BnApplyArgs* bn) {
     if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || im2col_disabled()) return -1;
+    if (bn != nullptr && g->K != 64) return -1;
     if (g->K % 8 != 0 || g->K < 32) return -1;                         // TMA: 16-byte channel pitch of `small`
     if ((reinterpret_cast<uintptr_t>(small_) | reinterpret_cast<uintptr_t>(big)) & 15) return -1;
     EncodeTiledFn enc = encode_fn();
@@ -668,8 +786,50 @@ int conv_wgrad_im2col(const vs_conv_geom* g, const void* small_, const void* big
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(small) failed: %d", (int)rc);
     }
-    return BN == 128 ? launch_imw<128, 3>(ms, mb, p, dw, k_tiles, (int)splits, stream)
-                     : launch_imw<64, 4>(ms, mb, p, dw, k_tiles, (int)splits, stream);
+    BnApplyArgs none;
+    memset(&none, 0, sizeof(none));
+    if (bn != nullptr) return launch_imw<64, 4, true>(ms, mb, p, *bn, dw, k_tiles, (int)splits, stream);
+    return BN == 128 ? launch_imw<128, 3, false>(ms, mb, p, none, dw, k_tiles, (int)splits, stream)
+                     : launch_imw<64, 4, false>(ms, mb, p, none, dw, k_tiles, (int)splits, stream);
+}
+
+// ------------------------------------------------------------------------------------------ fused decoder tail, backward
+// The thin transposed convolution's input gradient (a direct convolution of the frame gradient `dout` [N,H,W,C] with the
+// DIRECT-packed weights wp [K][R*S][C]) is produced tile by tile on the tensor cores and consumed in the epilogue:
+// phase 0 accumulates the BatchNorm backward sums, phase 1 writes dy.  0 = done, -1 = not eligible, > 0 = error.
+int tail_eligible(const vs_conv_geom* g) {
+    if (g->dtype != VS_BF16 || g->K != 64 || im2col_disabled()) return 0;
+    Im2colParams p;
+    if (!im2col_plan(p, g, 128, IM_PATCH_STAGE) || p.KK > 64) return 0;
+    if (g->P % p.HT != 0 || g->Q % p.WT != 0) return 0;            // whole tiles only: every epilogue row is a pixel
+    Im2colParams pw;
+    if (!im2col_plan(pw, g, 64, IM_PATCH_STAGE_W) || g->Q % pw.WT != 0 || g->P % pw.HT != 0) return 0;
+    return 1;
+}
+
+int tail_bn_backward(const vs_conv_geom* g, const BnBwdArgs& bb, const void* dout, const void* wp, int phase, double* sums, void* dy,
+                     cudaStream_t stream) {
+    if (!tail_eligible(g) || !encode_fn()) return -1;
+    if ((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(bb.y) | reinterpret_cast<uintptr_t>(dy)) & 15) return -1;
+    Im2colParams p;
+    if (!im2col_plan(p, g, 128, IM_PATCH_STAGE)) return -1;
+    CUtensorMap mb;
+    if (int rc = im2col_big_map(mb, p, dout)) return rc;
+    p.act = VS_ACT_NONE; p.has_bias = 0; p.partial = 0;
+    p.n_per_group = bb.n_per_group;
+    CUtensorMap mo;
+    memset(&mo, 0, sizeof(mo));
+    if (phase == 0) return launch_imf<64, 1, 4, false, 1>(mb, mo, p, wp, nullptr, nullptr, sums, stream, &bb);
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g->K, (cuuint64_t)g->Q, (cuuint64_t)g->P, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)g->K * 2, (cuuint64_t)g->K * g->Q * 2, (cuuint64_t)g->K * g->Q * g->P * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.WT, (cuuint32_t)p.HT, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode_fn()(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(tail dy) failed: %d", (int)r);
+    }
+    return launch_imf<64, 1, 3, true, 2>(mb, mo, p, wp, nullptr, dy, nullptr, stream, &bb);
 }
 
 }  // namespace vs

@@ -40,11 +40,14 @@ template <int BN, int STAGES, bool TS>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int OUT_BYTES = TS ? 2 * TC_BM * 128 : 0;       // two bf16 output tiles staged for TMA stores (BN = 64)
+    // two bf16 output tiles staged for TMA stores; a tile is BN/64 half-tiles of [128 pixels][128 bytes]
+    static constexpr int TILE_BYTES = (BN / 64) * TC_BM * 128;
+    static constexpr int OUT_BYTES = TS ? 2 * TILE_BYTES : 0;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
     static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 2 * 4 /*tile statistics*/;
     static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
-    static_assert(!TS || BN == 64, "the staged epilogue handles one 128-byte row per pixel");
+    static_assert(!TS || BN == 64 || BN == 128, "the staged epilogue handles 128-byte rows: 64-column half-tiles");
+    static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
 
 // output tensor maps of the staged epilogue, one per output-parity class: [OC, OW/ost, OH/ost, N] views of the NHWC output
@@ -171,13 +174,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
         int lt = 0;
         int stat_key = -1;
         double stat_acc = 0.0;
-        float ss[4] = {0.f, 0.f, 0.f, 0.f};          // SS: sum / sum of squares of this thread's two columns
+        constexpr int HALVES = BN / 64;              // 64-column half-tiles of the staged tile
+        float ss[HALVES][4] = {};                    // SS: sum / sum of squares of this thread's two columns per half-tile
         // SS: flush the register sums of the finished BatchNorm group through the shared-memory column table
         auto ss_flush = [&](int key) {
             const int t = threadIdx.x - 64, cp = t & 31;
-            atomicAdd(&sstat[(2 * cp) * 2], ss[0]);     atomicAdd(&sstat[(2 * cp) * 2 + 1], ss[1]);
-            atomicAdd(&sstat[(2 * cp + 1) * 2], ss[2]); atomicAdd(&sstat[(2 * cp + 1) * 2 + 1], ss[3]);
-            ss[0] = ss[1] = ss[2] = ss[3] = 0.f;
+#pragma unroll
+            for (int hf = 0; hf < HALVES; ++hf) {
+                const int c = hf * 64 + 2 * cp;
+                atomicAdd(&sstat[c * 2], ss[hf][0]);       atomicAdd(&sstat[c * 2 + 1], ss[hf][1]);
+                atomicAdd(&sstat[(c + 1) * 2], ss[hf][2]); atomicAdd(&sstat[(c + 1) * 2 + 1], ss[hf][3]);
+                ss[hf][0] = ss[hf][1] = ss[hf][2] = ss[hf][3] = 0.f;
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
             if (t < 2 * BN) {
                 const int col = (key % p.n_tiles) * BN + (t >> 1);
@@ -223,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
 #pragma unroll
                         for (int c = 0; c < 32; ++c) xs[c] = 0.f;
                     }
-                    stage_row32(obuf + (lt & 1) * (TC_BM * 128), m, c0, xs, p.act);
+                    stage_row32(obuf + (lt & 1) * S::TILE_BYTES + (c0 >> 6) * (TC_BM * 128), m, c0 & 63, xs, p.act);
                 } else if (p.partial || n0 + BN > p.OC) {
                     // tail tile in OC, or rows not 16-byte aligned: predicated scalar stores
                     if (ok) {
@@ -270,7 +278,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                 if (threadIdx.x == 64) tma_store_wait_read();
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
                 if (threadIdx.x == 64) {
-                    tma_store_4d(&omaps.m[cls], obuf + (lt & 1) * (TC_BM * 128), n0, j0, i0, b0);
+#pragma unroll
+                    for (int hf = 0; hf < BN / 64; ++hf)
+                        if (n0 + hf * 64 < p.OC)
+                            tma_store_4d(&omaps.m[cls], obuf + (lt & 1) * S::TILE_BYTES + hf * (TC_BM * 128), n0 + hf * 64, j0, i0, b0);
                     tma_store_commit();
                 }
             }
@@ -278,14 +289,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
                 // columns 2cp, 2cp+1 of rows 16rg .. 16rg+15 of the tile staged above (complete since the barrier); the
                 // buffer is refilled two tiles from now, behind the next tile's barrier
                 const int t = threadIdx.x - 64, cp = t & 31, rg = t >> 5;
-                const uint8_t* tile = obuf + (lt & 1) * (TC_BM * 128) + (cp & 3) * 4;
 #pragma unroll
-                for (int rr = 0; rr < TC_BM / TC_EPI_WARPS; ++rr) {
-                    const int row = rg * (TC_BM / TC_EPI_WARPS) + rr;
-                    const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + row * 128 + (((cp >> 2) ^ (row & 7)) << 4));
-                    const float a = __uint_as_float(v << 16), b = __uint_as_float(v & 0xffff0000u);
-                    ss[0] += a; ss[1] = fmaf(a, a, ss[1]);
-                    ss[2] += b; ss[3] = fmaf(b, b, ss[3]);
+                for (int hf = 0; hf < HALVES; ++hf) {
+                    const uint8_t* tile = obuf + (lt & 1) * S::TILE_BYTES + hf * (TC_BM * 128) + (cp & 3) * 4;
+#pragma unroll
+                    for (int rr = 0; rr < TC_BM / TC_EPI_WARPS; ++rr) {
+                        const int row = rg * (TC_BM / TC_EPI_WARPS) + rr;
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + row * 128 + (((cp >> 2) ^ (row & 7)) << 4));
+                        const float a = __uint_as_float(v << 16), b = __uint_as_float(v & 0xffff0000u);
+                        ss[hf][0] += a; ss[hf][1] = fmaf(a, a, ss[hf][1]);
+                        ss[hf][2] += b; ss[hf][3] = fmaf(b, b, ss[hf][3]);
+                    }
                 }
             }
             if (!SS && stats != nullptr) {
@@ -801,7 +815,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMa
     q.classes = classes;
     q.n_tiles = (int)cdiv(p.OC, BN);
     q.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * q.n_tiles * classes;
-    const int resident = 2 * num_sms();                     // __launch_bounds__(TC_THREADS, 2)
+    // __launch_bounds__(TC_THREADS, 2); the deep-ring staged 128-column variant fills an SM's shared memory alone
+    const int resident = (S::TOTAL > 113 * 1024 ? 1 : 2) * num_sms();
     const int grid = q.total_tiles < resident ? q.total_tiles : resident;      // every CTA gets at least one work item
     tc_conv_kernel<BN, STAGES, TS, SS><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, om, q, bias, (__nv_bfloat16*)out, stats);
     return launched("tc_conv_kernel");
@@ -1055,7 +1070,9 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     // output-parity class, starting at that class's first pixel
     TcOutMaps om;
     memset(&om, 0, sizeof(om));
-    const bool staged = BN == 64 && !p.partial && classes <= TC_MAX_OUT_MAPS && !staged_epilogue_disabled();
+    // (BN = 128: only the statistics-carrying forward launches, see below; one CTA per SM with a five-stage ring)
+    const bool staged128 = BN == 128 && OC % 128 == 0 && fuse_stats && p.act == VS_ACT_NONE && !staged_stats_disabled();
+    const bool staged = (BN == 64 || staged128) && !p.partial && classes <= TC_MAX_OUT_MAPS && !staged_epilogue_disabled();
     if (staged) {
         for (int cls = 0; cls < classes; ++cls) {
             const char* base = reinterpret_cast<const char*>(out) + ((size_t)p.ca[cls] * OW + p.cb[cls]) * OC * 2;
@@ -1071,7 +1088,7 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     }
     double* stp = fuse_stats ? stats : nullptr;
     TcFusedTab ftab;
-    if (tr && staged && !pair && (stp == nullptr || p.act == VS_ACT_NONE) && !fused_classes_disabled() && build_fused_tab(p, classes, ftab)) {
+    if (tr && staged && BN == 64 && !pair && (stp == nullptr || p.act == VS_ACT_NONE) && !fused_classes_disabled() && build_fused_tab(p, classes, ftab)) {
         int rc = launch_tc_fused<3>(ma, mb, om, p, ftab, bias, stp, stream);
         if (rc) return rc;
         if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
@@ -1079,7 +1096,8 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     }
     int rc = pair ? (PBN == 256 ? launch_tc_pair<256, 6>(ma, mb, p, bias, out, classes, stp, stream)
                                 : launch_tc_pair<128, 8>(ma, mb, p, bias, out, classes, stp, stream))
-             : BN == 128 ? launch_tc<128, 3, false>(ma, mb, om, p, bias, out, classes, stp, stream)
+             : BN == 128 ? (staged ? launch_tc<128, 5, true, true>(ma, mb, om, p, bias, out, classes, stp, stream)
+                                   : launch_tc<128, 3, false>(ma, mb, om, p, bias, out, classes, stp, stream))
              : staged && stp != nullptr && p.act == VS_ACT_NONE && !staged_stats_disabled()
                        ? launch_tc<64, 3, true, true>(ma, mb, om, p, bias, out, classes, stp, stream)
              : staged  ? launch_tc<64, 3, true>(ma, mb, om, p, bias, out, classes, stp, stream)

@@ -213,6 +213,20 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32_pair(int bn) {     // M = 
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- fused decoder tail: BatchNorm (+ activation) applied on an operand path / differentiated in an epilogue ---------
+// mean / invstd are [groups][K] (per reference call), gamma / beta [K]; group of image n = n / n_per_group
+struct BnApplyArgs {
+    const float* mean; const float* invstd; const float* gamma; const float* beta;
+    int n_per_group, act;
+};
+struct BnBwdArgs {
+    const __nv_bfloat16* y;        // pre-BatchNorm tensor [N,P,Q,K]
+    const float* mean; const float* invstd; const float* gamma; const float* beta;
+    const double* sums;            // [groups][K][2] {sum dz, sum dz*xhat} (apply phase)
+    int n_per_group, act, train;
+    float inv_count;               // 1 / elements per (group, channel)
+};
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

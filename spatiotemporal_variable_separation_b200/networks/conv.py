@@ -288,6 +288,16 @@ class DCGAN64Decoder(BaseDecoder):
             ConvBlock(nn.ConvTranspose2d(nf * 2 * coef, nf, 4, 2, 1), 'leaky_relu'),
             last])
 
+    def decode(self, z1, z2, skip=None, groups=1):
+        if skip is not None:
+            return super().decode(z1, z2, skip, groups)
+        # without skip connections the last BatchNorm block feeds the thin output convolution directly: one fused
+        # operator (ops.decoder_tail) that never materialises the normalised 2*nf... -> nf tensor
+        h = self.first_upconv(_mix(z1, z2, self.mixing), groups)
+        for layer in self.conv[:2]:
+            h = layer(h, groups)
+        return ops.decoder_tail(h, self.conv[2], self.conv[3], groups)
+
 
 class VGG64Decoder(BaseDecoder):
     """conv.py:267-320."""

@@ -173,6 +173,81 @@ def _geom(cfg, dtype, N, H, W, P, Q, act, groups):
                   cfg.stride, cfg.pad, groups, act, cfg.flags)
 
 
+def _conv_forward(ctx, x, weight, bias, cfg, act_code, groups, stats_n):
+    """The convolution launch shared by ``ConvBlockFn`` and ``DecoderTailFn``.  Records on ``ctx`` what the backward
+    needs (``cfg_fwd`` the layer's own geometry, ``cfg`` the launch geometry — K zero-padded to a 16-byte channel pitch
+    when needed —, ``dims``, ``mode``).  ``stats_n`` > 0: a zeroed fp64 [stats_n] buffer receives the per-(group,
+    channel) sums of the output (BatchNorm batch statistics).  Returns (x as launched, y, stats or None)."""
+    x = x.contiguous()
+    N = x.shape[0]
+    if cfg.kind == 'conv':
+        H, W = x.shape[1], x.shape[2]
+        assert x.shape[3] == cfg.C, (x.shape, cfg)
+        P = (H + 2 * cfg.pad - cfg.R) // cfg.stride + 1
+        Q = (W + 2 * cfg.pad - cfg.S) // cfg.stride + 1
+        out_shape, OC, mode = (N, P, Q, cfg.K), cfg.K, L.DIRECT
+    else:
+        P, Q = x.shape[1], x.shape[2]
+        assert x.shape[3] == cfg.K, (x.shape, cfg)
+        H = (P - 1) * cfg.stride - 2 * cfg.pad + cfg.R
+        W = (Q - 1) * cfg.stride - 2 * cfg.pad + cfg.S
+        out_shape, OC, mode = (N, H, W, cfg.C), cfg.C, L.TRANSPOSED
+    dt = x.dtype
+    ctx.cfg_fwd = cfg
+    wsrc = weight
+    if mode == L.TRANSPOSED and dt == torch.bfloat16 and cfg.K % 8 != 0 and cfg.K >= 32 and cfg.C % 8 == 0:
+        # input channels padded with zeros to a 16-byte pitch so that the layer runs on the tensor cores
+        Kp = (cfg.K + 7) // 8 * 8
+        xp = torch.zeros((N, P, Q, Kp), device=x.device, dtype=dt)
+        L.call('vs_copy_channels', ptr(x), cfg.K, N * P * Q, ptr(xp), Kp, 0, N * P * Q, L.dtype_code(xp), L.stream())
+        x, wsrc, cfg = xp, padded_rows(weight, Kp), cfg._replace(K=Kp)
+    wp = packed_weight(wsrc, cfg.K, cfg.C, cfg.R * cfg.S, mode == L.TRANSPOSED, dt)
+    y = torch.empty(out_shape, device=x.device, dtype=dt)
+    ctx.cfg, ctx.dims, ctx.mode = cfg, (N, H, W, P, Q, OC), mode      # cfg: geometry of the launches (K padded)
+    stats = zeros_f64(stats_n, x.device) if stats_n else None
+    g = _geom(cfg, dt, N, H, W, P, Q, act_code, groups)
+    L.call('vs_conv_forward', g, mode, ptr(x), ptr(wp), ptr(bias), ptr(y), ptr(stats), L.stream())
+    return x, y, stats
+
+
+def _conv_backward(ctx, x, weight, dy, p_weight, p_bias, need_dx, need_dw, need_db, bias_is_dead):
+    """Input, weight and bias gradients of the convolution recorded by ``_conv_forward`` from the gradient ``dy`` of its
+    output.  Returns (dx, dw for autograd, db for autograd)."""
+    cfg, (N, H, W, P, Q, OC), mode = ctx.cfg, ctx.dims, ctx.mode
+    dt = dy.dtype
+    rows = dy.numel() // OC
+    g = _geom(cfg, dt, N, H, W, P, Q, 0, 1)
+    cfg0 = ctx.cfg_fwd                      # the layer's own geometry (differs from cfg when K was padded)
+    padded = cfg0.K != cfg.K
+    dx = None
+    if need_dx:
+        g0 = _geom(cfg0, dt, N, H, W, P, Q, 0, 1)
+        dx = torch.empty(x.shape[:-1] + (cfg0.K,), device=x.device, dtype=dt) if padded else torch.empty_like(x)
+        back_mode = L.TRANSPOSED if mode == L.DIRECT else L.DIRECT
+        wp = packed_weight(weight, cfg0.K, cfg0.C, cfg0.R * cfg0.S, back_mode == L.TRANSPOSED, dt)
+        L.call('vs_conv_forward', g0, back_mode, ptr(dy), ptr(wp), None, ptr(dx), None, L.stream())
+    dw = db = None
+    if need_dw:
+        dw = _grad_buffer(p_weight)
+        small, big = (dy, x) if cfg.kind == 'conv' else (x, dy)
+        if padded:
+            # gradient of the zero-padded weight; its first K rows are the layer's gradient
+            dwp = torch.zeros((cfg.K,) + tuple(weight.shape[1:]), device=x.device, dtype=torch.float32)
+            L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dwp), L.stream())
+            dw[0].add_(dwp[:cfg0.K].view_as(dw[0]))
+        else:
+            L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dw[0]), L.stream())
+    if p_bias is not None and need_db:
+        db = _grad_buffer(p_bias)
+        if not bias_is_dead:
+            # (eval-mode BatchNorm is an affine map: the bias gradient is the plain column sum of dy)
+            L.call('vs_colsum', ptr(dy), L.dtype_code(dy), rows, OC, ptr(db[0]), L.stream())
+        # else: BatchNorm's backward returns a dy whose per-(group, channel) sum is exactly zero, so the
+        # bias gradient is mathematically 0 (the reference computes rounding noise there, SURVEY H2);
+        # the (zero-initialised) buffer is left untouched instead of streaming dy once more.
+    return dx, dw[1] if dw else None, db[1] if db else None
+
+
 class ConvBlockFn(torch.autograd.Function):
     """conv/convT/linear -> [BatchNorm (grouped batch stats or running stats)] -> activation.
 
@@ -183,47 +258,18 @@ class ConvBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, rmean, rvar, nbt, cfg):
         L.require_cuda(x, weight)
-        x = x.contiguous()
-        N = x.shape[0]
-        if cfg.kind == 'conv':
-            H, W = x.shape[1], x.shape[2]
-            assert x.shape[3] == cfg.C, (x.shape, cfg)
-            P = (H + 2 * cfg.pad - cfg.R) // cfg.stride + 1
-            Q = (W + 2 * cfg.pad - cfg.S) // cfg.stride + 1
-            out_shape, OC, mode = (N, P, Q, cfg.K), cfg.K, L.DIRECT
-        else:
-            P, Q = x.shape[1], x.shape[2]
-            assert x.shape[3] == cfg.K, (x.shape, cfg)
-            H = (P - 1) * cfg.stride - 2 * cfg.pad + cfg.R
-            W = (Q - 1) * cfg.stride - 2 * cfg.pad + cfg.S
-            out_shape, OC, mode = (N, H, W, cfg.C), cfg.C, L.TRANSPOSED
-        dt = x.dtype
         act = L.ACT[cfg.act]
-        ctx.cfg_fwd = cfg
-        wsrc = weight
-        if mode == L.TRANSPOSED and dt == torch.bfloat16 and cfg.K % 8 != 0 and cfg.K >= 32 and cfg.C % 8 == 0:
-            # input channels padded with zeros to a 16-byte pitch so that the layer runs on the tensor cores
-            Kp = (cfg.K + 7) // 8 * 8
-            xp = torch.zeros((N, P, Q, Kp), device=x.device, dtype=dt)
-            L.call('vs_copy_channels', ptr(x), cfg.K, N * P * Q, ptr(xp), Kp, 0, N * P * Q, L.dtype_code(xp), L.stream())
-            x, wsrc, cfg = xp, padded_rows(weight, Kp), cfg._replace(K=Kp)
-        wp = packed_weight(wsrc, cfg.K, cfg.C, cfg.R * cfg.S, mode == L.TRANSPOSED, dt)
-        y = torch.empty(out_shape, device=x.device, dtype=dt)
-        rows = y.numel() // OC
-        ctx.cfg, ctx.dims, ctx.mode = cfg, (N, H, W, P, Q, OC), mode      # cfg: geometry of the launches (K padded)
         if cfg.has_bn:
             G = cfg.groups if cfg.training else 1
+            OC = cfg.K if cfg.kind == 'conv' else cfg.C
+            x, y, stats = _conv_forward(ctx, x, weight, bias, cfg, 0, G, G * OC * 2 if cfg.training else 0)
+            rows = y.numel() // OC
             mean = torch.empty(G * OC, device=x.device, dtype=torch.float32)
             invstd = torch.empty_like(mean)
             if cfg.training:
-                stats = zeros_f64(G * OC * 2, x.device)
-                g = _geom(cfg, dt, N, H, W, P, Q, 0, G)
-                L.call('vs_conv_forward', g, mode, ptr(x), ptr(wp), ptr(bias), ptr(y), ptr(stats), L.stream())
                 L.call('vs_bn_finalize', ptr(stats), G, OC, rows // G, cfg.eps, cfg.momentum, ptr(mean), ptr(invstd),
                      ptr(rmean), ptr(rvar), ptr(nbt), L.stream())
             else:
-                g = _geom(cfg, dt, N, H, W, P, Q, 0, 1)
-                L.call('vs_conv_forward', g, mode, ptr(x), ptr(wp), ptr(bias), ptr(y), None, L.stream())
                 L.call('vs_bn_eval_stats', ptr(rmean), ptr(rvar), OC, cfg.eps, ptr(mean), ptr(invstd), L.stream())
             out = torch.empty_like(y)
             L.call('vs_bn_act_forward', ptr(y), ptr(out), L.dtype_code(y), rows, OC, G, ptr(mean), ptr(invstd),
@@ -231,9 +277,7 @@ class ConvBlockFn(torch.autograd.Function):
             ctx.save_for_backward(x, weight, y, mean, invstd, gamma, beta)
             ctx.G = G
         else:
-            g = _geom(cfg, dt, N, H, W, P, Q, act, 1)
-            L.call('vs_conv_forward', g, mode, ptr(x), ptr(wp), ptr(bias), ptr(y), None, L.stream())
-            out = y
+            x, out, _ = _conv_forward(ctx, x, weight, bias, cfg, act, 1, 0)
             ctx.save_for_backward(x, weight, out)
         # python references to the leaf parameters (their ``_vs_grad`` arena views are looked up in backward)
         ctx.params = (weight, bias, gamma, beta)
@@ -241,9 +285,8 @@ class ConvBlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        cfg, (N, H, W, P, Q, OC), mode = ctx.cfg, ctx.dims, ctx.mode
+        cfg, (N, H, W, P, Q, OC) = ctx.cfg, ctx.dims
         dout = dout.contiguous()
-        dt = dout.dtype
         rows = dout.numel() // OC
         act = L.ACT[cfg.act]
         dgamma = dbeta = None
@@ -271,40 +314,126 @@ class ConvBlockFn(torch.autograd.Function):
                 L.call('vs_act_backward', ptr(dout), ptr(out), ptr(dy), L.dtype_code(out), out.numel(), act, L.stream())
             else:
                 dy = dout
-        g = _geom(cfg, dt, N, H, W, P, Q, 0, 1)
-        cfg0 = ctx.cfg_fwd                      # the layer's own geometry (differs from cfg when K was padded)
-        padded = cfg0.K != cfg.K
-        dx = None
-        if ctx.needs_input_grad[0]:
-            g0 = _geom(cfg0, dt, N, H, W, P, Q, 0, 1)
-            dx = torch.empty(x.shape[:-1] + (cfg0.K,), device=x.device, dtype=dt) if padded else torch.empty_like(x)
-            back_mode = L.TRANSPOSED if mode == L.DIRECT else L.DIRECT
-            wp = packed_weight(weight, cfg0.K, cfg0.C, cfg0.R * cfg0.S, back_mode == L.TRANSPOSED, dt)
-            L.call('vs_conv_forward', g0, back_mode, ptr(dy), ptr(wp), None, ptr(dx), None, L.stream())
-        dw = db = None
-        if ctx.needs_input_grad[1]:
-            dw = _grad_buffer(p_weight)
-            small, big = (dy, x) if cfg.kind == 'conv' else (x, dy)
-            if padded:
-                # gradient of the zero-padded weight; its first K rows are the layer's gradient
-                dwp = torch.zeros((cfg.K,) + tuple(weight.shape[1:]), device=x.device, dtype=torch.float32)
-                L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dwp), L.stream())
-                dw[0].add_(dwp[:cfg0.K].view_as(dw[0]))
-            else:
-                L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dw[0]), L.stream())
-        if p_bias is not None and ctx.needs_input_grad[2]:
-            db = _grad_buffer(p_bias)
-            if not (cfg.has_bn and cfg.training):
-                # (eval-mode BatchNorm is an affine map: the bias gradient is the plain column sum of dy)
-                L.call('vs_colsum', ptr(dy), L.dtype_code(dy), rows, OC, ptr(db[0]), L.stream())
-            # else: BatchNorm's backward returns a dy whose per-(group, channel) sum is exactly zero, so the
-            # bias gradient is mathematically 0 (the reference computes rounding noise there);
-            # the (zero-initialised) buffer is left untouched instead of streaming dy once more.
+        dx, dw, db = _conv_backward(ctx, x, weight, dy, p_weight, p_bias, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                    ctx.needs_input_grad[2], cfg.has_bn and cfg.training)
         if _grad_hooks[1] is not None:
             _grad_hooks[1](ctx.params)
-        return (dx, dw[1] if dw else None, db[1] if db else None, dgamma[1] if dgamma else None,
-                dbeta[1] if dbeta else None,
-                None, None, None, None)
+        return (dx, dw, db, dgamma[1] if dgamma else None, dbeta[1] if dbeta else None, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused decoder tail: [conv + BatchNorm + activation] -> thin ConvTranspose2d(nf, nc <= 2, 4, 2, 1) + output activation
+# (DCGAN64Decoder.conv[2], conv[3]; conv.py:255-263).  The normalised tensor between the two layers — the largest
+# activation of the step, 268 MB for the Moving-MNIST configuration — and its gradient are never written to HBM:
+# BatchNorm + activation ride the operand path of the thin layer's kernels, and the thin layer's input gradient is
+# recomputed in the epilogues of the two BatchNorm-backward passes (include/varsep.h, "fused decoder tail").
+# ------------------------------------------------------------------------------------------------
+def _tail_eligible(geom):
+    """1 when libvarsep's fused tail kernels accept the thin transposed convolution ``geom`` (host-side query)."""
+    return L.load().vs_tail_eligible(geom) == 1
+
+
+def tail_geom(cfg3, dtype, N, P, Q):
+    H = (P - 1) * cfg3.stride - 2 * cfg3.pad + cfg3.R
+    W = (Q - 1) * cfg3.stride - 2 * cfg3.pad + cfg3.S
+    return _geom(cfg3, dtype, N, H, W, P, Q, L.ACT[cfg3.act], 1), H, W
+
+
+class DecoderTailFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, w2, b2, gamma, beta, rmean, rvar, nbt, w3, b3, cfg2, cfg3):
+        L.require_cuda(x, w2, w3)
+        G = cfg2.groups if cfg2.training else 1
+        OC = cfg2.K if cfg2.kind == 'conv' else cfg2.C
+        x, y, stats = _conv_forward(ctx, x, w2, b2, cfg2, 0, G, G * OC * 2 if cfg2.training else 0)
+        rows = y.numel() // OC
+        mean = torch.empty(G * OC, device=x.device, dtype=torch.float32)
+        invstd = torch.empty_like(mean)
+        if cfg2.training:
+            L.call('vs_bn_finalize', ptr(stats), G, OC, rows // G, cfg2.eps, cfg2.momentum, ptr(mean), ptr(invstd),
+                   ptr(rmean), ptr(rvar), ptr(nbt), L.stream())
+        else:
+            L.call('vs_bn_eval_stats', ptr(rmean), ptr(rvar), OC, cfg2.eps, ptr(mean), ptr(invstd), L.stream())
+        N, P3, Q3 = y.shape[0], y.shape[1], y.shape[2]
+        g3, H3, W3 = tail_geom(cfg3, y.dtype, N, P3, Q3)
+        wp3 = packed_weight(w3, cfg3.K, cfg3.C, cfg3.R * cfg3.S, True, y.dtype)
+        out = torch.empty((N, H3, W3, cfg3.C), device=x.device, dtype=y.dtype)
+        L.call('vs_tail_forward', g3, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), G, L.ACT[cfg2.act], ptr(wp3),
+               ptr(b3), ptr(out), L.stream())
+        ctx.save_for_backward(x, w2, y, mean, invstd, gamma, beta, w3, out)
+        ctx.G, ctx.cfg2, ctx.cfg3, ctx.g3 = G, cfg2, cfg3, g3
+        ctx.params = (w2, b2, gamma, beta, w3, b3)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w2, y, mean, invstd, gamma, beta, w3, out = ctx.saved_tensors
+        p_w2, p_b2, p_gamma, p_beta, p_w3, p_b3 = ctx.params
+        cfg2, cfg3, g3, G = ctx.cfg2, ctx.cfg3, ctx.g3, ctx.G
+        OC = y.shape[-1]
+        act2, act3 = L.ACT[cfg2.act], L.ACT[cfg3.act]
+        dout = dout.contiguous()
+        # ---- the thin layer: activation backward, bias gradient, weight gradient (act rebuilt from y on the operand path)
+        if act3 != 0:
+            dz3 = torch.empty_like(out)
+            L.call('vs_act_backward', ptr(dout), ptr(out), ptr(dz3), L.dtype_code(out), out.numel(), act3, L.stream())
+        else:
+            dz3 = dout
+        dw3 = db3 = None
+        if p_b3 is not None and ctx.needs_input_grad[9]:
+            db3 = _grad_buffer(p_b3)
+            L.call('vs_colsum', ptr(dz3), L.dtype_code(dz3), dz3.numel() // cfg3.C, cfg3.C, ptr(db3[0]), L.stream())
+        if ctx.needs_input_grad[8]:
+            dw3 = _grad_buffer(p_w3)
+            L.call('vs_tail_wgrad', g3, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), G, act2, ptr(dz3), ptr(dw3[0]),
+                   L.stream())
+        # ---- BatchNorm backward; the thin layer's input gradient is recomputed tile by tile inside both passes
+        wp3d = packed_weight(w3, cfg3.K, cfg3.C, cfg3.R * cfg3.S, False, y.dtype)
+        sums = zeros_f64(G * OC * 2, dout.device)
+        dgamma = dbeta = None
+        affine = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
+        bn_args = (g3, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), G, act2, ptr(dz3), ptr(wp3d))
+        if cfg2.training or affine:
+            L.call('vs_tail_bn_backward', *bn_args, 0, int(cfg2.training), ptr(sums), None, None, None, L.stream())
+            if affine:
+                dgamma, dbeta = _grad_buffer(p_gamma), _grad_buffer(p_beta)
+        dy = torch.empty_like(y)
+        L.call('vs_tail_bn_backward', *bn_args, 1, int(cfg2.training), ptr(sums), ptr(dy),
+               ptr(dgamma[0]) if dgamma else None, ptr(dbeta[0]) if dbeta else None, L.stream())
+        # ---- the convolution of the BatchNorm block
+        dx, dw2, db2 = _conv_backward(ctx, x, w2, dy, p_w2, p_b2, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                      ctx.needs_input_grad[2], cfg2.training)
+        if _grad_hooks[1] is not None:
+            _grad_hooks[1](ctx.params)
+        return (dx, dw2, db2, dgamma[1] if dgamma else None, dbeta[1] if dbeta else None, None, None, None,
+                dw3[1] if dw3 else None, db3[1] if db3 else None, None, None)
+
+
+def decoder_tail(x, block, last, groups=1):
+    """``last(block(x))`` for a BatchNorm ConvBlock ``block`` followed by the thin transposed convolution ``last``
+    (networks.conv.DCGAN64Decoder), fused when the kernels accept the geometry; the two plain launches otherwise."""
+    conv2, bn2 = block[0], block[1]
+    w2 = conv2.weight
+    K2, C2, R2, S2 = tuple(w2.shape)
+    cfg2 = ConvCfg(block.kind, K2, C2, R2, S2, conv2.stride[0], conv2.padding[0], block.act, groups, bool(bn2.training), True,
+                   bn2.eps, bn2.momentum, 0)
+    K3, C3, R3, S3 = tuple(last.weight.shape)
+    cfg3 = ConvCfg('convT', K3, C3, R3, S3, last.stride[0], last.padding[0], last._act, 1, False, False, 0.0, 0.0, 0)
+    N = x.shape[0]
+    if block.kind == 'convT':
+        P3 = (x.shape[1] - 1) * cfg2.stride - 2 * cfg2.pad + R2
+        Q3 = (x.shape[2] - 1) * cfg2.stride - 2 * cfg2.pad + S2
+    else:
+        P3 = (x.shape[1] + 2 * cfg2.pad - R2) // cfg2.stride + 1
+        Q3 = (x.shape[2] + 2 * cfg2.pad - S2) // cfg2.stride + 1
+    folded = not bn2.training and _fold_eval_bn and not torch.is_grad_enabled()
+    if folded or not _tail_eligible(tail_geom(cfg3, x.dtype, N, P3, Q3)[0]):
+        return last(block(x, groups), groups)
+    if _grad_hooks[0] is not None and torch.is_grad_enabled():
+        _grad_hooks[0]((w2, conv2.bias, bn2.weight, bn2.bias, last.weight, last.bias))
+    return DecoderTailFn.apply(x, w2, conv2.bias, bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var,
+                               bn2.num_batches_tracked, last.weight, last.bias, cfg2, cfg3)
 
 
 def _grad_buffer(p):

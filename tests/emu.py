@@ -181,6 +181,44 @@ def vs_bn_act_backward_apply(dout, y, dy, dtype, rows, C, G, mean, invstd, gamma
         dbeta += sums.reshape(G, C, 2)[..., 0].sum(0).float().reshape(dbeta.shape)
 
 
+# ---- fused decoder tail: the composition of the plain entry points it replaces (include/varsep.h) ------------------
+def _tail_act(g, y, mean, invstd, gamma, beta, G, bn_act):
+    gg = _geo(g)
+    rows, K = gg['N'] * gg['P'] * gg['Q'], gg['K']
+    act = torch.empty(rows, K, dtype=y.dtype)                 # rounded to the storage type, as the unfused path stores it
+    vs_bn_act_forward(y, act, None, rows, K, G, mean, invstd, gamma, beta, bn_act, None)
+    return act, rows, K
+
+
+def _geom_with(g, **kw):
+    d = _geo(g)
+    d.update(kw)
+    return L.Geom(*[d[k] for k, _ in L.Geom._fields_])
+
+
+def vs_tail_forward(g, y, mean, invstd, gamma, beta, G, bn_act, wp, bias, out, stream):
+    act, _, _ = _tail_act(g, y, mean, invstd, gamma, beta, G, bn_act)
+    vs_conv_forward(g, L.TRANSPOSED, act, wp, bias, out, None, None)
+
+
+def vs_tail_wgrad(g, y, mean, invstd, gamma, beta, G, bn_act, dout, dw, stream):
+    act, _, _ = _tail_act(g, y, mean, invstd, gamma, beta, G, bn_act)
+    vs_conv_wgrad(g, act, dout, dw, None)
+
+
+def vs_tail_bn_backward(g, y, mean, invstd, gamma, beta, G, bn_act, dout, wp_direct, phase, train, sums, dy, dgamma,
+                        dbeta, stream):
+    gg = _geo(g)
+    rows, K = gg['N'] * gg['P'] * gg['Q'], gg['K']
+    dact = torch.empty(rows, K, dtype=torch.float32)          # the fp32 accumulator tile, never rounded to bf16
+    vs_conv_forward(_geom_with(g, act=0, groups=1), L.DIRECT, dout, wp_direct, None, dact, None, None)
+    if phase == 0:
+        vs_bn_act_backward_reduce(dact, y, None, rows, K, G, mean, invstd, gamma, beta, bn_act, sums, None)
+    else:
+        vs_bn_act_backward_apply(dact, y, dy, None, rows, K, G, mean, invstd, gamma, beta, bn_act, sums, train, dgamma,
+                                 dbeta, None)
+
+
 def vs_act_backward(dout, out, dx, dtype, n, act, stream):
     _store(dx, _f(dout) * _act_grad_out(_f(out), act))
 

@@ -27,7 +27,7 @@ def oracle_run(name, dtype_name, batch=None):
     """One loss + backward of the oracle at full size.  -> dict(loss [5], forecasts, t_codes, grads{name: tensor})"""
     from oracle import step
     cfg = full_cfg(name, batch)
-    if dtype_name == 'autocast_bf16':
+    if dtype_name in ('autocast_bf16', 'float32_cuda'):
         # the reference's own mixed-precision path (--torch_amp: main.py:159, train.py:151-155) with bf16 as the low
         # precision type: fp32 master weights, convolutions / linears in bf16, BatchNorm and losses in fp32.  Calibrates
         # the bf16 bound: how far does the REFERENCE move from its fp64 result when it computes in bf16?
@@ -38,9 +38,18 @@ def oracle_run(name, dtype_name, batch=None):
                 if isinstance(v, torch.Tensor):
                     P[k] = v.detach().to(dev).requires_grad_(v.requires_grad)
         cond, target = [t.to(dev) for t in harness.inputs(cfg, torch.float32)]
-        with torch.autocast(dev, dtype=torch.bfloat16):
-            out = step.step_losses(net, cond, target, cfg, T_RANDOM[name])
-        out['total'].backward()
+        # 'float32_cuda': the reference's plain fp32 step executed by cuDNN / cuBLAS instead of oneDNN (TF32 off) — a
+        # second stock execution of the same arithmetic, whose distance from the CPU run shows how much of the
+        # fp32-vs-fp64 gradient error is summation-order noise (activation kinks flipping) rather than a property of
+        # the implementation
+        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.autocast(dev, dtype=torch.bfloat16, enabled=dtype_name == 'autocast_bf16'):
+                out = step.step_losses(net, cond, target, cfg, T_RANDOM[name])
+            out['total'].backward()
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     else:
         dtype = getattr(torch, dtype_name)
         net = harness.oracle_net(cfg, dtype)
@@ -76,9 +85,9 @@ def rel_l2(a, b):
     return float((a - b).norm() / max(float(b.norm()), 1e-300))
 
 
-def compare(run, truth, ref32=None):
+def compare(run, truth, ref32=None, ref32b=None):
     """Per-quantity relative L2 error of ``run`` against ``truth`` (the fp64 oracle); with ``ref32`` (the fp32 oracle)
-    also the reference's own error, tensor by tensor.  Gradients that are mathematically zero (conv biases feeding a
+    also the reference's own error, tensor by tensor (the larger of two stock executions when ``ref32b`` is given).  Gradients that are mathematically zero (conv biases feeding a
     train-mode BatchNorm, parameters the step never touches) are reported separately as |g| / max|g|."""
     rep = {'loss': float(np.abs(run['loss'] - truth['loss']).max() / np.abs(truth['loss']).max()),
            'loss_terms': [float(x) for x in np.abs(run['loss'] - truth['loss']) / np.maximum(np.abs(truth['loss']), 1e-30)],
@@ -95,7 +104,13 @@ def compare(run, truth, ref32=None):
             rep['zero_grads'][n] = float(ours.double().norm()) / gmax
             continue
         e = rel_l2(ours, g64)
-        rep['grads'][n] = (e, rel_l2(ref32['grads'][n], g64)) if ref32 is not None else (e, None)
+        if ref32 is None:
+            rep['grads'][n] = (e, None)
+        else:
+            er = rel_l2(ref32['grads'][n], g64)
+            if ref32b is not None:
+                er = max(er, rel_l2(ref32b['grads'][n], g64))
+            rep['grads'][n] = (e, er)
     return rep
 
 

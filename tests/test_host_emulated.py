@@ -317,3 +317,23 @@ def test_eval_bn_folding_matches_reference_rollout(name):
                 assert float((moved - want).abs().max()) < 2e-5 * float(want.abs().max()) + 1e-6
         finally:
             ops.set_eval_bn_folding(False)
+
+
+@pytest.mark.parametrize('name', ['mnist-small', 'mnist-small-mul', 'mnist-small-no_s'])
+def test_fused_decoder_tail_host_path_matches_reference_golden(name, monkeypatch):
+    """ops.DecoderTailFn (the last BatchNorm block of the DCGAN decoder fused with the thin output convolution): the host
+    wiring over the emulated ABI, forced on for these fp32 cases (the CUDA kernels accept bf16 only), against the same
+    goldens as the unfused path — losses, forecasts, latent rollout and every gradient."""
+    g = harness.load_golden(name)
+    cfg = g['cfg']
+    ops.set_compute_dtype(torch.float32)
+    used = []
+    monkeypatch.setattr(ops, '_tail_eligible', lambda geom: used.append(1) or True)
+    with emu.install():
+        net = build_filled(cfg).train()
+        t_random = harness.t_random_sequence(cfg, int(g['np_seed']), 1)[0]
+        out = run_step(net, cfg, t_random)
+        out['total'].backward()
+        grads = {f'{part}.{k}': p.grad for part in harness.PARTS for k, p in getattr(net, part).named_parameters()}
+        check_against_golden(g, out, grads, rtol_grad=1e-4 if name in STRICT else 2e-4, kink=0.0 if name in STRICT else KINK)
+    assert used, 'the fused path was not taken'

@@ -509,3 +509,47 @@ def test_fused_class_transposed_conv_opt_in():
     env = dict(os.environ, VARSEP_ENABLE_FUSED_CLASSES='1')
     r = subprocess.run([sys.executable, '-c', _FUSED_CLASSES_SNIPPET % root], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'fused classes ok' in r.stdout, r.stdout + r.stderr
+
+
+# (N, P, Q, C, bn_groups): the thin transposed convolution ConvTranspose2d(64, C, 4, 2, 1) behind a BatchNorm + LeakyReLU
+TAIL_CASES = [(6, 32, 32, 1, 3), (4, 16, 16, 2, 2), (5, 32, 32, 1, 1), (8, 16, 32, 1, 4)]
+
+
+@pytest.mark.parametrize('case', TAIL_CASES)
+def test_fused_decoder_tail_kernels(case):
+    """vs_tail_forward / vs_tail_wgrad / vs_tail_bn_backward (both phases, train and eval) against their specification
+    = the composition of the plain entry points they replace."""
+    N, P, Q, C, G = case
+    K, dtype = 64, torch.bfloat16
+    H, W = 2 * P, 2 * Q
+    torch.manual_seed(11)
+    g = L.Geom(1, N, H, W, C, P, Q, K, 4, 4, 2, 1, 1, 4, 0)                    # output activation: sigmoid
+    assert L.load().vs_tail_eligible(g) == 1
+    y = (torch.randn(N, P, Q, K) * 1.5 + 0.3).to(dtype)
+    mean, invstd = torch.randn(G * K) * 0.2 + 0.3, torch.rand(G * K) * 0.5 + 0.4
+    gamma, beta = torch.randn(K) * 0.3 + 1.0, torch.randn(K) * 0.2
+    w = torch.randn(K, C, 4, 4) / np.sqrt(K * 4)
+    wp_t, wp_d = torch.zeros(K * C * 16).to(dtype), torch.zeros(K * C * 16).to(dtype)
+    emu.emu_call('vs_pack_weight', w, wp_t, 1, K, C, 16, 1, None)
+    emu.emu_call('vs_pack_weight', w, wp_d, 1, K, C, 16, 0, None)
+    bias = torch.randn(C)
+    out = torch.zeros(N, H, W, C).to(dtype)
+    gpu, cpu = run_both('vs_tail_forward', [g, y, mean, invstd, gamma, beta, G, 2, wp_t, bias, out, None])
+    close(gpu[10], cpu[10], dtype, 'tail forward', outliers=1e-4)
+    dout = (torch.randn(N, H, W, C) * 0.1).to(dtype)
+    dw = torch.randn(K, C, 4, 4)
+    gpu, cpu = run_both('vs_tail_wgrad', [g, y, mean, invstd, gamma, beta, G, 2, dout, dw, None])
+    close(gpu[9], cpu[9], torch.float32, 'tail wgrad', scale=float(cpu[9].abs().max()) * 50)   # bf16 operands, fp32 sums
+    for train in (1, 0):
+        sums = torch.zeros(G * K * 2, dtype=torch.float64)
+        gpu, cpu = run_both('vs_tail_bn_backward', [g, y, mean, invstd, gamma, beta, G, 2, dout, wp_d, 0, train, sums, None,
+                                                    None, None, None])
+        close(gpu[12].float(), cpu[12].float(), torch.float32, 'tail bn sums', scale=float(cpu[12].abs().max()) * 50)
+        dy = torch.full((N, P, Q, K), float('nan')).to(dtype)
+        dgamma, dbeta = torch.randn(K), torch.randn(K)
+        # phase 1 on the SAME sums on both sides (the specification's), so that only this phase is compared
+        args = [g, y, mean, invstd, gamma, beta, G, 2, dout, wp_d, 1, train, cpu[12].clone(), dy, dgamma, dbeta, None]
+        gpu1, cpu1 = run_both('vs_tail_bn_backward', args)
+        close(gpu1[13], cpu1[13], dtype, f'tail dy train={train}', outliers=2e-3, scale=float(cpu1[13].float().abs().max()))
+        close(gpu1[14], cpu1[14], torch.float32, 'tail dgamma', scale=float(cpu1[14].abs().max()))
+        close(gpu1[15], cpu1[15], torch.float32, 'tail dbeta', scale=float(cpu1[15].abs().max()))
