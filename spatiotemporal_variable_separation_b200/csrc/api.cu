@@ -142,8 +142,9 @@ extern "C" int vs_conv_wgrad(const vs_conv_geom* g, const void* small_, const vo
 
 
 // ---------------------------------------------------------------------------------------------- fused decoder tail
-static int tail_check(const vs_conv_geom* g, int32_t bn_groups) {
+static int tail_check(const vs_conv_geom* g, int32_t bn_groups, int32_t bn_act) {
     if (int rc = check_geom(g)) return rc;
+    VS_REQUIRE(bn_act_supported(bn_act), "tail: the BatchNorm block's activation must be none, ReLU or LeakyReLU (got %d)", bn_act);
     VS_REQUIRE(bn_groups >= 1 && g->N % bn_groups == 0, "tail: N=%d not divisible by the BatchNorm groups=%d", g->N, bn_groups);
     VS_REQUIRE(vs_tail_eligible(g) == 1, "tail: geometry not eligible for the fused kernels (query vs_tail_eligible first)");
     return 0;
@@ -157,8 +158,8 @@ extern "C" int vs_tail_eligible(const vs_conv_geom* g) {
 extern "C" int vs_tail_forward(const vs_conv_geom* g, const void* y, const float* mean, const float* invstd, const float* gamma,
                                const float* beta, int32_t bn_groups, int32_t bn_act, const void* wp, const float* bias, void* out,
                                void* stream) {
-    if (int rc = tail_check(g, bn_groups)) return rc;
-    BnApplyArgs bn = {mean, invstd, gamma, beta, g->N / bn_groups, bn_act};
+    if (int rc = tail_check(g, bn_groups, bn_act)) return rc;
+    BnApplyArgs bn = {mean, invstd, gamma, beta, g->N / bn_groups, bn_act_neg_slope(bn_act)};
     int rc = conv_forward_col2im(g, VS_CONV_TRANSPOSED, y, wp, bias, out, nullptr, as_stream(stream), &bn);
     VS_REQUIRE(rc >= 0, "tail_forward: operands not 16-byte aligned");
     return rc;
@@ -166,8 +167,8 @@ extern "C" int vs_tail_forward(const vs_conv_geom* g, const void* y, const float
 
 extern "C" int vs_tail_wgrad(const vs_conv_geom* g, const void* y, const float* mean, const float* invstd, const float* gamma,
                              const float* beta, int32_t bn_groups, int32_t bn_act, const void* dout, float* dw, void* stream) {
-    if (int rc = tail_check(g, bn_groups)) return rc;
-    BnApplyArgs bn = {mean, invstd, gamma, beta, g->N / bn_groups, bn_act};
+    if (int rc = tail_check(g, bn_groups, bn_act)) return rc;
+    BnApplyArgs bn = {mean, invstd, gamma, beta, g->N / bn_groups, bn_act_neg_slope(bn_act)};
     int rc = conv_wgrad_im2col(g, y, dout, dw, as_stream(stream), &bn);
     VS_REQUIRE(rc >= 0, "tail_wgrad: operands not 16-byte aligned");
     return rc;
@@ -176,13 +177,13 @@ extern "C" int vs_tail_wgrad(const vs_conv_geom* g, const void* y, const float* 
 extern "C" int vs_tail_bn_backward(const vs_conv_geom* g, const void* y, const float* mean, const float* invstd, const float* gamma,
                                    const float* beta, int32_t bn_groups, int32_t bn_act, const void* dout, const void* wp_direct,
                                    int32_t phase, int32_t train, double* sums, void* dy, float* dgamma, float* dbeta, void* stream) {
-    if (int rc = tail_check(g, bn_groups)) return rc;
+    if (int rc = tail_check(g, bn_groups, bn_act)) return rc;
     VS_REQUIRE(phase == 0 || phase == 1, "tail_bn_backward: phase must be 0 (reduce) or 1 (apply)");
     VS_REQUIRE(sums != nullptr && (phase == 0 || dy != nullptr), "tail_bn_backward: null output");
     BnBwdArgs bb;
     bb.y = reinterpret_cast<const __nv_bfloat16*>(y);
     bb.mean = mean; bb.invstd = invstd; bb.gamma = gamma; bb.beta = beta; bb.sums = sums;
-    bb.n_per_group = g->N / bn_groups; bb.act = bn_act; bb.train = train;
+    bb.n_per_group = g->N / bn_groups; bb.neg_slope = bn_act_neg_slope(bn_act); bb.train = train;
     bb.inv_count = 1.f / (float)((long long)bb.n_per_group * g->P * g->Q);
     int rc = tail_bn_backward(g, bb, dout, wp_direct, phase, sums, dy, as_stream(stream));
     VS_REQUIRE(rc >= 0, "tail_bn_backward: operands not 16-byte aligned");

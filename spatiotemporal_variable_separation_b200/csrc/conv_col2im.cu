@@ -44,7 +44,8 @@ struct C2iSmem {
 };
 
 // XF: the input tensor is the PRE-BatchNorm output y of the previous layer; four extra warps apply
-//   act(gamma * (y - mean[g]) * invstd[g] + beta)   (the arithmetic of bn_act_fwd_col_kernel, bit for bit)
+//   act(gamma * (y - mean[g]) * invstd[g] + beta)   (as one fused multiply-add per element: bn_act_fwd_col_kernel's result
+// up to the fp32 rounding before the bf16 rounding)
 // to every A stage in shared memory between its TMA landing and the MMA, so the normalised tensor (268 MB for the
 // Moving-MNIST decoder) is never written to or re-read from HBM.
 template <int NB, int STAGES, bool XF>
@@ -134,7 +135,7 @@ convT_col2im_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int t = threadIdx.x - C2I_THREADS;
         const int phys = t & 7, rsub = t >> 3;
         const int cg = phys ^ (rsub & 7);
-        float mu[8], is[8], ga[8], be[8];
+        float sc[8], sh[8];                     // z = y * sc + sh with sc = gamma * invstd, sh = beta - mean * sc
         int cur_g = -1, cur_kc = -1, it = 0;
         for (int img = blockIdx.x; img < p.N; img += gridDim.x) {
             const int g = img / bn.n_per_group;
@@ -145,8 +146,8 @@ convT_col2im_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const int c = kc * 64 + cg * 8 + e;
-                            mu[e] = __ldg(bn.mean + (long long)g * p.K + c); is[e] = __ldg(bn.invstd + (long long)g * p.K + c);
-                            ga[e] = __ldg(bn.gamma + c); be[e] = __ldg(bn.beta + c);
+                            sc[e] = __ldg(bn.gamma + c) * __ldg(bn.invstd + (long long)g * p.K + c);
+                            sh[e] = __ldg(bn.beta + c) - __ldg(bn.mean + (long long)g * p.K + c) * sc[e];
                         }
                     }
                     const int s = it % STAGES;
@@ -160,8 +161,9 @@ convT_col2im_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float a0 = __uint_as_float(w[e] << 16), a1 = __uint_as_float(w[e] & 0xffff0000u);
-                            const float r0 = act_fwd(ga[2 * e] * ((a0 - mu[2 * e]) * is[2 * e]) + be[2 * e], bn.act);
-                            const float r1 = act_fwd(ga[2 * e + 1] * ((a1 - mu[2 * e + 1]) * is[2 * e + 1]) + be[2 * e + 1], bn.act);
+                            // act(z) = max(z, neg_slope * z) for neg_slope in [0, 1]: none / ReLU / LeakyReLU without a branch
+                            const float z0 = fmaf(a0, sc[2 * e], sh[2 * e]), z1 = fmaf(a1, sc[2 * e + 1], sh[2 * e + 1]);
+                            const float r0 = fmaxf(z0, bn.neg_slope * z0), r1 = fmaxf(z1, bn.neg_slope * z1);
                             __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
                             w[e] = *reinterpret_cast<uint32_t*>(&b2);
                         }

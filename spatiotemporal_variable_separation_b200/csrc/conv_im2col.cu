@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(IMF_THREADS, 2) im2col_fwd_kernel(const __grid
                         const float yv = (c & 1) ? __uint_as_float(wv & 0xffff0000u) : __uint_as_float(wv << 16);
                         const float4 pa = sprm[2 * (c0 + c)];
                         const float xhat = fmaf(yv, pa.x, pa.y);
-                        const float dz = __uint_as_float(r[c]) * act_grad_from_in(fmaf(pa.z, xhat, pa.w), bb.act);
+                        const float dz = fmaf(pa.z, xhat, pa.w) > 0.f ? __uint_as_float(r[c]) : __uint_as_float(r[c]) * bb.neg_slope;
                         if (EPI == 2) {
                             const float4 pb = sprm[2 * (c0 + c) + 1];
                             xs[c] = pb.x * (dz - pb.y - xhat * pb.z);
@@ -538,7 +538,7 @@ int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const v
 // D[kk][k] += sum over 64-pixel blocks; warps: 0 = TMA producer (boxes of `small`), 1 = MMA issuer, 2..5 = im2col
 // builders during the reduction, then the epilogue (fp32 reductions into the torch-layout gradient).
 // XF: `small` is the PRE-BatchNorm tensor y of the layer below; the builder warps apply BatchNorm + activation to every
-// landed box of it in shared memory (bit for bit the arithmetic of bn_act_fwd_col_kernel) before the MMA reads it, so the
+// landed box of it in shared memory (one fused multiply-add + max per element) before the MMA reads it, so the
 // weight gradient of the fused decoder tail needs no materialised normalised tensor.
 template <int BN, int STAGES, bool XF>
 __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_constant__ CUtensorMap map_small,
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
         // XF: chunk id = t + 128 i of the landed [64 pixels][128 B] box: row t/8 + 16 i, physical chunk t%8 -> always the same
         // eight channels for this thread (the swizzle XORs the chunk index with row & 7 = (t/8) & 7)
         const int xphys = t & 7, xrsub = t >> 3, xcg = xphys ^ (xrsub & 7);
-        float xmu[XF ? 8 : 1], xis[XF ? 8 : 1], xga[XF ? 8 : 1], xbe[XF ? 8 : 1];
+        float xsc[XF ? 8 : 1], xsh[XF ? 8 : 1];          // z = y * sc + sh with sc = gamma * invstd, sh = beta - mean * sc
         int xg = -1;
         for (int kb = 0; kb < nkb; ++kb) {
             const int st = kb % STAGES, ps = kb % IM_PST;
@@ -670,8 +670,8 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int c = kt * BN + xcg * 8 + e;
-                        xmu[e] = __ldg(bn.mean + (long long)g * p.K + c); xis[e] = __ldg(bn.invstd + (long long)g * p.K + c);
-                        xga[e] = __ldg(bn.gamma + c); xbe[e] = __ldg(bn.beta + c);
+                        xsc[e] = __ldg(bn.gamma + c) * __ldg(bn.invstd + (long long)g * p.K + c);
+                        xsh[e] = __ldg(bn.beta + c) - __ldg(bn.mean + (long long)g * p.K + c) * xsc[e];
                     }
                 }
             }
@@ -698,8 +698,8 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float a0 = __uint_as_float(wv[e] << 16), a1 = __uint_as_float(wv[e] & 0xffff0000u);
-                        const float r0 = act_fwd(xga[2 * e] * ((a0 - xmu[2 * e]) * xis[2 * e]) + xbe[2 * e], bn.act);
-                        const float r1 = act_fwd(xga[2 * e + 1] * ((a1 - xmu[2 * e + 1]) * xis[2 * e + 1]) + xbe[2 * e + 1], bn.act);
+                        const float z0 = fmaf(a0, xsc[2 * e], xsh[2 * e]), z1 = fmaf(a1, xsc[2 * e + 1], xsh[2 * e + 1]);
+                        const float r0 = fmaxf(z0, bn.neg_slope * z0), r1 = fmaxf(z1, bn.neg_slope * z1);
                         __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
                         wv[e] = *reinterpret_cast<uint32_t*>(&b2);
                     }

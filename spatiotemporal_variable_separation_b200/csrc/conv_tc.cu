@@ -1052,7 +1052,9 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     // (measured: 256-column pair tiles reach 1.2-1.4 PFLOP/s on the decoder layers; 128-column pair tiles lose to two
     // single CTAs per SM except for long reduction loops, where the deeper ring of the pair kernel hides the latency)
     const int PBN = OC % 256 == 0 ? 256 : 128;
-    const bool pair = OC % 128 == 0 && IC >= 64 && !p.partial && !pair_disabled() && (PBN == 256 || p.ntaps * p.kchunks >= 64);
+    static int pair128_min = -1;       // (tap, 64-channel chunk) steps from which 128-column layers use CTA pairs
+    if (pair128_min < 0) { const char* e = getenv("VARSEP_PAIR128_MIN_STEPS"); pair128_min = e ? atoi(e) : 64; }
+    const bool pair = OC % 128 == 0 && IC >= 64 && !p.partial && !pair_disabled() && (PBN == 256 || p.ntaps * p.kchunks >= pair128_min);
     {
         cuuint64_t dims[2] = {(cuuint64_t)g->R * g->S * IC, (cuuint64_t)OC};
         cuuint64_t strides[1] = {(cuuint64_t)g->R * g->S * IC * 2};

@@ -215,15 +215,22 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // ---- fused decoder tail: BatchNorm (+ activation) applied on an operand path / differentiated in an epilogue ---------
 // mean / invstd are [groups][K] (per reference call), gamma / beta [K]; group of image n = n / n_per_group
+// The activation is none / ReLU / LeakyReLU only, expressed branch-free as  z > 0 ? z : neg_slope * z  with
+// neg_slope = 1 / 0 / 0.2 (a per-element switch over all six activations compiles to an indirect branch per element and
+// made the fused kernels 8x slower than the HBM traffic they save).
 struct BnApplyArgs {
     const float* mean; const float* invstd; const float* gamma; const float* beta;
-    int n_per_group, act;
+    int n_per_group;
+    float neg_slope;
 };
+__host__ __device__ inline bool bn_act_supported(int act) { return act == VS_ACT_NONE || act == VS_ACT_RELU || act == VS_ACT_LEAKY; }
+__host__ __device__ inline float bn_act_neg_slope(int act) { return act == VS_ACT_NONE ? 1.f : act == VS_ACT_RELU ? 0.f : 0.2f; }
 struct BnBwdArgs {
     const __nv_bfloat16* y;        // pre-BatchNorm tensor [N,P,Q,K]
     const float* mean; const float* invstd; const float* gamma; const float* beta;
     const double* sums;            // [groups][K][2] {sum dz, sum dz*xhat} (apply phase)
-    int n_per_group, act, train;
+    int n_per_group, train;
+    float neg_slope;               // see BnApplyArgs
     float inv_count;               // 1 / elements per (group, channel)
 };
 

@@ -333,6 +333,11 @@ def _tail_eligible(geom):
     return L.load().vs_tail_eligible(geom) == 1
 
 
+def _tail_fused_backward():
+    import os
+    return os.environ.get('VARSEP_TAIL_FUSED_BACKWARD', '0') == '1'
+
+
 def tail_geom(cfg3, dtype, N, P, Q):
     H = (P - 1) * cfg3.stride - 2 * cfg3.pad + cfg3.R
     W = (Q - 1) * cfg3.stride - 2 * cfg3.pad + cfg3.S
@@ -388,19 +393,35 @@ class DecoderTailFn(torch.autograd.Function):
             dw3 = _grad_buffer(p_w3)
             L.call('vs_tail_wgrad', g3, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), G, act2, ptr(dz3), ptr(dw3[0]),
                    L.stream())
-        # ---- BatchNorm backward; the thin layer's input gradient is recomputed tile by tile inside both passes
+        # ---- BatchNorm backward.  Default: the thin layer's input gradient is materialised once (bf16) and the two column
+        # kernels stream it.  ``VARSEP_TAIL_FUSED_BACKWARD=1`` recomputes it inside both passes instead
+        # (vs_tail_bn_backward: correct, less HBM traffic, but its one-row-per-thread epilogue costs more issue slots than
+        # the traffic it saves — 281 + 269 us against 109 + 105 + 126 us on the B200).
         wp3d = packed_weight(w3, cfg3.K, cfg3.C, cfg3.R * cfg3.S, False, y.dtype)
         sums = zeros_f64(G * OC * 2, dout.device)
         dgamma = dbeta = None
         affine = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
-        bn_args = (g3, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), G, act2, ptr(dz3), ptr(wp3d))
-        if cfg2.training or affine:
-            L.call('vs_tail_bn_backward', *bn_args, 0, int(cfg2.training), ptr(sums), None, None, None, L.stream())
-            if affine:
-                dgamma, dbeta = _grad_buffer(p_gamma), _grad_buffer(p_beta)
+        if affine:
+            dgamma, dbeta = _grad_buffer(p_gamma), _grad_buffer(p_beta)
         dy = torch.empty_like(y)
-        L.call('vs_tail_bn_backward', *bn_args, 1, int(cfg2.training), ptr(sums), ptr(dy),
-               ptr(dgamma[0]) if dgamma else None, ptr(dbeta[0]) if dbeta else None, L.stream())
+        if _tail_fused_backward():
+            bn_args = (g3, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), G, act2, ptr(dz3), ptr(wp3d))
+            if cfg2.training or affine:
+                L.call('vs_tail_bn_backward', *bn_args, 0, int(cfg2.training), ptr(sums), None, None, None, L.stream())
+            L.call('vs_tail_bn_backward', *bn_args, 1, int(cfg2.training), ptr(sums), ptr(dy),
+                   ptr(dgamma[0]) if dgamma else None, ptr(dbeta[0]) if dbeta else None, L.stream())
+        else:
+            N, P3, Q3 = y.shape[0], y.shape[1], y.shape[2]
+            rows = N * P3 * Q3
+            g3d = L.Geom(g3.dtype, N, g3.H, g3.W, g3.C, P3, Q3, g3.K, g3.R, g3.S, g3.stride, g3.pad, 1, 0, 0)
+            dact = torch.empty_like(y)
+            L.call('vs_conv_forward', g3d, L.DIRECT, ptr(dz3), ptr(wp3d), None, ptr(dact), None, L.stream())
+            if cfg2.training or affine:
+                L.call('vs_bn_act_backward_reduce', ptr(dact), ptr(y), L.dtype_code(y), rows, OC, G, ptr(mean), ptr(invstd),
+                       ptr(gamma), ptr(beta), act2, ptr(sums), L.stream())
+            L.call('vs_bn_act_backward_apply', ptr(dact), ptr(y), ptr(dy), L.dtype_code(y), rows, OC, G, ptr(mean), ptr(invstd),
+                   ptr(gamma), ptr(beta), act2, ptr(sums), int(cfg2.training),
+                   ptr(dgamma[0]) if dgamma else None, ptr(dbeta[0]) if dbeta else None, L.stream())
         # ---- the convolution of the BatchNorm block
         dx, dw2, db2 = _conv_backward(ctx, x, w2, dy, p_w2, p_b2, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
                                       ctx.needs_input_grad[2], cfg2.training)
@@ -428,7 +449,8 @@ def decoder_tail(x, block, last, groups=1):
         P3 = (x.shape[1] + 2 * cfg2.pad - R2) // cfg2.stride + 1
         Q3 = (x.shape[2] + 2 * cfg2.pad - S2) // cfg2.stride + 1
     folded = not bn2.training and _fold_eval_bn and not torch.is_grad_enabled()
-    if folded or not _tail_eligible(tail_geom(cfg3, x.dtype, N, P3, Q3)[0]):
+    if folded or block.act not in (None, 'none', 'identity', 'relu', 'leaky_relu') or \
+            not _tail_eligible(tail_geom(cfg3, x.dtype, N, P3, Q3)[0]):
         return last(block(x, groups), groups)
     if _grad_hooks[0] is not None and torch.is_grad_enabled():
         _grad_hooks[0]((w2, conv2.bias, bn2.weight, bn2.bias, last.weight, last.bias))

@@ -319,8 +319,9 @@ def test_eval_bn_folding_matches_reference_rollout(name):
             ops.set_eval_bn_folding(False)
 
 
+@pytest.mark.parametrize('fused_backward', [False, True])
 @pytest.mark.parametrize('name', ['mnist-small', 'mnist-small-mul', 'mnist-small-no_s'])
-def test_fused_decoder_tail_host_path_matches_reference_golden(name, monkeypatch):
+def test_fused_decoder_tail_host_path_matches_reference_golden(name, fused_backward, monkeypatch):
     """ops.DecoderTailFn (the last BatchNorm block of the DCGAN decoder fused with the thin output convolution): the host
     wiring over the emulated ABI, forced on for these fp32 cases (the CUDA kernels accept bf16 only), against the same
     goldens as the unfused path — losses, forecasts, latent rollout and every gradient."""
@@ -329,6 +330,7 @@ def test_fused_decoder_tail_host_path_matches_reference_golden(name, monkeypatch
     ops.set_compute_dtype(torch.float32)
     used = []
     monkeypatch.setattr(ops, '_tail_eligible', lambda geom: used.append(1) or True)
+    monkeypatch.setattr(ops, '_tail_fused_backward', lambda: fused_backward)
     with emu.install():
         net = build_filled(cfg).train()
         t_random = harness.t_random_sequence(cfg, int(g['np_seed']), 1)[0]
