@@ -367,6 +367,74 @@ def run_ours(args, cfg):
     _shutdown(tr, world)
 
 
+def run_rollout(args, cfg):
+    """SURVEY section 8d 'rollout-95' / BASELINE configs[4]: eval-mode ``get_forecast(cond, 100)`` (5 conditioning frames
+    -> 100 forecast frames, test/mnist/test.py:99-133), no gradient, bf16, with and without BatchNorm folded into the
+    inference weights; captured as one CUDA graph.  Prints one JSON line (metric: forecast sequences / second)."""
+    from spatiotemporal_variable_separation_b200 import _lib, ops
+    from spatiotemporal_variable_separation_b200.data import synthetic_batch
+    from spatiotemporal_variable_separation_b200.networks.factory import build_model
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    device = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    ops.set_compute_dtype(dtype)
+    torch.manual_seed(0)
+    net = build_model(cfg, device).eval()
+    B, horizon = cfg['batch_size'], args.horizon
+    cond = synthetic_batch(cfg, device=device)[:, :cfg['nt_cond']].contiguous()
+    out = {}
+    for fold in (False, True):
+        ops.set_eval_bn_folding(fold)
+        with torch.no_grad():
+            for _ in range(2):
+                f = net.get_forecast(cond, horizon)[0]
+            torch.cuda.synchronize()
+            l0 = _lib.launch_count()
+            f = net.get_forecast(cond, horizon)[0]
+            torch.cuda.synchronize()
+            launches = _lib.launch_count() - l0
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                f = net.get_forecast(cond, horizon)[0]
+            for _ in range(args.warmup):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        assert torch.isfinite(f).all()
+        out['folded_bn' if fold else 'plain'] = {'value': B / (ms * 1e-3), 'ms_per_rollout': ms, 'launches': launches,
+                                                  'frames_per_s': B * horizon / (ms * 1e-3), 'checksum': float(f.double().mean())}
+    ops.set_eval_bn_folding(False)
+    best = max(out.values(), key=lambda v: v['value'])
+    line = {'metric': 'rollout_sequences_per_sec', 'value': best['value'], 'unit': 'sequences/s', 'n_gpus': 1, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': best['ms_per_rollout'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': f'{workload_name(cfg)} eval get_forecast(cond, {horizon})', 'batch_per_gpu': B},
+            'variants': out, 'gpu_launches': best['launches'] * args.steps}
+    if not args.no_cpu_baseline:
+        from oracle import detfill, functional, shapes
+        torch.set_num_threads(os.cpu_count() or 1)
+        sh = shapes.model_shapes(cfg)
+        P = {part: detfill.fill_state(sh[part], part + '.') for part in ('Es', 'Et', 'decoder', 't_resnet')}
+        onet = functional.Net(cfg, P['Es'], P['Et'], P['decoder'], P['t_resnet'])
+        onet.train = False
+        c = cond[:16].cpu()
+        with torch.no_grad():
+            onet.get_forecast(c, 10)
+            t0 = time.perf_counter()
+            onet.get_forecast(c, horizon)
+            dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': 16 / dt, 'unit': 'sequences/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                'sample': f'one eval get_forecast(cond, {horizon}) of 16 sequences, {dt:.2f} s'}
+    print(json.dumps(line), flush=True)
+
+
 def _max_over_ranks(ms, world, device):
     if world > 1:
         import torch.distributed as dist
@@ -484,6 +552,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-baseline', action='store_true')
     ap.add_argument('--cpu-budget', type=float, default=15.0)
+    ap.add_argument('--mode', default='train', choices=['train', 'rollout'], help="'rollout': the eval-mode long-horizon forecast")
+    ap.add_argument('--horizon', type=int, default=100, help='frames to forecast in --mode rollout (5 + 95)')
     args = ap.parse_args()
     from spatiotemporal_variable_separation_b200 import configs
     cfg = configs.preset(args.config, extra=f'--batch_size {args.batch}' if args.batch else '')
@@ -491,6 +561,8 @@ def main():
         run_reference(args, cfg)
     elif args.impl == 'reference-gpu':
         run_reference_gpu(args, cfg)
+    elif args.mode == 'rollout':
+        run_rollout(args, cfg)
     else:
         run_ours(args, cfg)
 

@@ -205,6 +205,14 @@ int vs_tail_bn_backward(const vs_conv_geom* g, const void* y, const float* mean,
                         const float* beta, int32_t bn_groups, int32_t bn_act, const void* dout, const void* wp_direct,
                         int32_t phase, int32_t train, double* sums, void* dy, float* dgamma, float* dbeta, void* stream);
 
+/* ---- synthetic Moving-MNIST sequences (the step before the hot path) ----
+ * replaces: MovingMNIST.__getitem__ (train branch) + _compute_trajectory + _process_collision of
+ * data/moving_mnist.py:112-253, deterministic variant: frames[b][t][0] = min(255, sum over the n_obj objects of the glyph
+ * blitted at its bounced position) / 255.  objs [B][n_obj][5] int32 = {glyph index, sx, sy, dx, dy} drawn by the host in
+ * the reference's order (sx: first row, sy: first column); glyphs [n_glyphs][gh][gw] uint8; frames [B][T][1][F][F] fp32. */
+int vs_moving_sequences(const uint8_t* glyphs, int32_t n_glyphs, int32_t gh, int32_t gw, const int32_t* objs,
+                        int32_t n_obj, int32_t B, int32_t T, int32_t F, float* frames, void* stream);
+
 /* ---- optimizer -----------------------------------------------------------------------------
  * replaces: torch.optim.Adam.step (main.py:145, train.py:162): eps-outside-sqrt, bias-corrected, no decay.
  * One launch over a flat, 16-byte aligned parameter arena.  The 1-based step count is step_host, or

@@ -1,4 +1,5 @@
-"""Synthetic input sequences of each configuration's shape and value statistics.
+"""Synthetic input sequences of each configuration's shape and value statistics, and the device-side
+Moving-MNIST training generator (``MovingSequences``: the reference's bounce semantics, one kernel per batch).
 
 No dataset can be downloaded here, and the metric is defined on synthetic data: Moving-MNIST-shaped
 sequences are two procedural 28x28 glyphs bouncing elastically in a 64x64 frame (positions U{0..36},
@@ -6,7 +7,10 @@ velocities U{-4..4}, summed and clipped to [0,1] as /root/reference/var_sep/data
 does with real digits); the other datasets are matched in shape and range only.  Everything is
 vectorised torch code that runs on the device it is asked for.
 """
+import numpy as np
 import torch
+
+from . import _lib as L
 
 
 def _glyphs(n, gen, device):
@@ -74,3 +78,67 @@ def synthetic_batch(cfg, batch=None, device='cpu', seed=0):
         return torch.randn(B, T, C, H, W, generator=gen, device=device)
     x = torch.rand(B, T, C, H, W, generator=gen, device=device)
     return x * x if data == 'taxibj' else x
+
+
+class MovingSequences:
+    """Training batches of bouncing glyphs generated ON THE DEVICE: counterpart of ``MovingMNIST`` in
+    /root/reference/var_sep/data/moving_mnist.py (train branch of ``__getitem__`` :112-130, ``_compute_trajectory``
+    :131-170, ``_process_collision`` :172-253; deterministic variant) used the way main.py:111-114 uses its DataLoader.
+
+    The reference builds every sample with Python loops over digits and frames on the host (a few hundred samples per
+    second and core); here the host only draws five integers per object — glyph index, start position, speed — from
+    numpy's global RNG **in the reference's order**, so that after ``np.random.seed(s)`` the batches are bit-identical
+    to ``batch_size`` consecutive ``dataset[i]`` calls of the reference, and one kernel (``vs_moving_sequences``) renders
+    all frames of the batch straight into device memory.  Iterating yields ``(cond, target)`` like the reference loader.
+
+    ``glyphs``: uint8 [G, h, w] (the MNIST digits in the reference; any glyph bank here)."""
+
+    def __init__(self, glyphs, frame_size=64, nt_cond=5, seq_len=15, max_speed=4, num_digits=2, batch_size=128,
+                 batches_per_epoch=None, device='cuda'):
+        g = torch.as_tensor(np.ascontiguousarray(glyphs))
+        assert g.dtype == torch.uint8 and g.dim() == 3, 'glyphs: uint8 [G, h, w]'
+        self.device = torch.device(device)
+        self.glyphs = g.to(self.device)
+        self.n_glyphs, self.gh, self.gw = (int(v) for v in g.shape)
+        self.frame_size, self.nt_cond, self.seq_len = frame_size, nt_cond, seq_len
+        self.max_speed, self.num_digits, self.batch_size = max_speed, num_digits, batch_size
+        # the reference's __len__ is an arbitrary 200000 samples per epoch (moving_mnist.py:103-110)
+        self.batches_per_epoch = batches_per_epoch if batches_per_epoch is not None else 200000 // batch_size
+        lo = np.array([0, 0, 0, -max_speed, -max_speed])
+        hi = np.array([self.n_glyphs, frame_size - self.gh + 1, frame_size - self.gw + 1, max_speed + 1, max_speed + 1])
+        self._lo, self._hi = lo, hi
+
+    def draw(self, batch_size=None):
+        """int32 [B, num_digits, 5] = (glyph, sx, sy, dx, dy) per object: one vectorised ``np.random.randint`` call that
+        consumes the global RNG stream exactly like the reference's scalar calls (moving_mnist.py:119-120, 147-150)."""
+        B = batch_size or self.batch_size
+        n = B * self.num_digits
+        v = np.random.randint(np.tile(self._lo, n), np.tile(self._hi, n))
+        return v.reshape(B, self.num_digits, 5).astype(np.int32)
+
+    def render(self, objs):
+        """objs (host int32 [B, n, 5]) -> frames [B, seq_len, 1, F, F] fp32 on the device."""
+        L.require_cuda(self.glyphs)
+        objs_d = torch.as_tensor(np.ascontiguousarray(objs, dtype=np.int32)).to(self.device, non_blocking=True)
+        B = objs_d.shape[0]
+        frames = torch.empty((B, self.seq_len, 1, self.frame_size, self.frame_size), device=self.device, dtype=torch.float32)
+        L.call('vs_moving_sequences', self.glyphs, self.n_glyphs, self.gh, self.gw, objs_d, objs_d.shape[1], B, self.seq_len,
+               self.frame_size, frames, L.stream())
+        return frames
+
+    def batch(self, batch_size=None):
+        frames = self.render(self.draw(batch_size))
+        return frames[:, :self.nt_cond], frames[:, self.nt_cond:]
+
+    def __len__(self):
+        return self.batches_per_epoch
+
+    def __iter__(self):
+        for _ in range(self.batches_per_epoch):
+            yield self.batch()
+
+
+def procedural_glyphs(n=256, size=28, seed=0):
+    """A bank of digit-like uint8 strokes (MNIST cannot be downloaded here)."""
+    gen = torch.Generator().manual_seed(seed)
+    return (255 * _glyphs(n, gen, 'cpu')).round().to(torch.uint8).numpy()

@@ -325,6 +325,12 @@ def vs_adam_step(p, g, m, v, n, lr, b1, b2, eps, grad_scale, step_host, step_dev
     p.addcdiv_(m, (v.sqrt() / (bc2 ** 0.5)).add_(eps), value=-lr / bc1)
 
 
+def vs_moving_sequences(glyphs, n_glyphs, gh, gw, objs, n_obj, B, T, F, frames, stream):
+    from oracle import moving_mnist
+    out = moving_mnist.render(glyphs.numpy().reshape(n_glyphs, gh, gw), objs.numpy().reshape(B, n_obj, 5), T, F)
+    frames.copy_(torch.from_numpy(out).reshape(frames.shape))
+
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith('vs_')}
 
 

@@ -275,3 +275,78 @@ def test_graphed_step_equals_eager_and_follows_lr_schedule():
     assert torch.allclose(t0, t1, rtol=1e-4, atol=1e-6), (t0, t1)
     assert float((p0 - p1).abs().max()) <= 2.5 * cfg['lr'], float((p0 - p1).abs().max())
     assert float((p0 - p1).norm() / p0.norm()) < 1e-4
+
+
+@pytest.mark.parametrize('name', ['mnist-small', 'taxibj-small', 'sst-small'])
+def test_eval_bn_folding_matches_reference_on_the_gpu(name):
+    """BatchNorm folded into the inference weights (conv + fused bias / activation, one launch per block)
+    against the eval goldens of the reference; fp32, 5e-5 (the folded weights round differently)."""
+    g = harness.load_eval_golden(name)
+    net = build_filled(g['cfg'], 'cuda').eval()
+    ops.set_eval_bn_folding(True)
+    try:
+        harness.check_eval_rollout(g, net, g['cfg']['skipco'], device='cuda', rtol=5e-5)
+    finally:
+        ops.set_eval_bn_folding(False)
+
+
+def test_long_horizon_rollout_95_frames_bf16():
+    """configs[4]: 5 conditioning frames -> 100 forecast frames in eval mode, full-size DCGAN, bf16: finite, in [0, 1],
+    bit-reproducible, and the first nt_pred frames equal a short-horizon forecast (the rollout is causal)."""
+    cfg = configs.preset('mnist', extra='--batch_size 8')
+    from spatiotemporal_variable_separation_b200.networks.factory import build_model
+    from spatiotemporal_variable_separation_b200.data import synthetic_batch
+    ops.set_compute_dtype(torch.bfloat16)
+    torch.manual_seed(0)
+    net = build_model(cfg, 'cuda').eval()
+    cond = synthetic_batch(cfg, device='cuda')[:, :cfg['nt_cond']].contiguous()
+    with torch.no_grad():
+        f100, t100, _, _ = net.get_forecast(cond, 100)
+        f100b = net.get_forecast(cond, 100)[0]
+        f10 = net.get_forecast(cond, 10)[0]
+    assert f100.shape == (8, 100, 1, 64, 64) and t100.shape == (8, 100, cfg['code_size_t'])
+    assert torch.isfinite(f100).all() and float(f100.min()) >= 0 and float(f100.max()) <= 1
+    assert torch.equal(f100, f100b)
+    assert torch.equal(f100[:, :10].contiguous(), f10.contiguous())
+
+
+def test_checkpoint_resume_on_the_gpu(tmp_path):
+    """SURVEY 8f N3 on the device: save (reference-format module pickles + training state) after two graphed steps,
+    reload into a fresh model / optimizer / stepper and continue: identical arenas as the uninterrupted run up to the
+    float-atomic noise of the training kernels, and the lr schedule survives without re-capturing graphs."""
+    from spatiotemporal_variable_separation_b200.optim import MultiStepLR
+    from spatiotemporal_variable_separation_b200.utils import helper
+    g = harness.load_golden('mnist-small')
+    cfg = g['cfg']
+    cond, target = harness.inputs(cfg)
+    draws = [6, 7, 6, 7]
+
+    def make():
+        net = build_filled(cfg, 'cuda').train()
+        opt = FusedAdam(net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
+        sched = MultiStepLR(opt, [1], 0.5)
+        st = vs_train.GraphedStep(net, opt, cfg['nt_cond'], cfg['nt_pred'], cfg['offset'], cfg['skipco'], cfg['lamb_ae'],
+                                  cfg['lamb_s'], cfg['lamb_t'], cfg['lamb_pred'], overlap_encoders=False)
+        return net, opt, sched, st
+
+    net, opt, sched, st = make()
+    for t in draws[:2]:
+        st(cond, target, t)
+    sched.step()
+    helper.save(str(tmp_path), net)
+    helper.save_training_state(str(tmp_path), opt, sched, epoch=1)
+    for t in draws[2:]:
+        st(cond, target, t)
+    torch.cuda.synchronize()
+    want = opt.flat_p.clone()
+    st.close()
+    net2, opt2, sched2, st2 = make()
+    helper.load(str(tmp_path), net2)
+    assert helper.load_training_state(str(tmp_path), opt2, sched2) == 1
+    assert int(opt2.step_dev) == 2 and opt2.lr == cfg['lr'] * 0.5
+    for t in draws[2:]:
+        st2(cond, target, t)
+    torch.cuda.synchronize()
+    assert float(opt2.lr_dev) == pytest.approx(cfg['lr'] * 0.5)
+    assert float((opt2.flat_p - want).norm() / want.norm()) < 1e-5
+    st2.close()
