@@ -203,7 +203,7 @@ def workload_name(cfg):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def build_trainer(cfg, device, dtype, world, use_graph, overlap=True):
+def build_trainer(cfg, device, dtype, world, use_graph, overlap=True, bucket_mb=None, early=None, transport='peer'):
     """Model + fused Adam + the package's graphed stepper (train.GraphedStep) — what train() itself builds."""
     from spatiotemporal_variable_separation_b200 import ops, train as vs_train
     from spatiotemporal_variable_separation_b200.networks.factory import build_model
@@ -215,7 +215,10 @@ def build_trainer(cfg, device, dtype, world, use_graph, overlap=True):
     if world > 1:
         broadcast_model(net)          # identical replicas
     opt = FusedAdam(net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
-    reducer = GradReducer(net, opt, overlap=overlap) if world > 1 else None
+    kw = {'bucket_bytes': int(bucket_mb * (1 << 20))} if bucket_mb else {}
+    if early is not None:
+        kw['early'] = tuple(n for n in early.split(',') if n)
+    reducer = GradReducer(net, opt, overlap=overlap, transport=transport, **kw) if world > 1 else None
     c = cfg
     return vs_train.GraphedStep(net, opt, c['nt_cond'], c['nt_pred'], c['offset'], c['skipco'], c['lamb_ae'], c['lamb_s'],
                                 0 if c['no_s'] else c['lamb_t'], c['lamb_pred'], c['architecture'] == 'encoderSST',
@@ -238,7 +241,7 @@ def run_ours(args, cfg):
         dist.init_process_group('nccl', device_id=device)
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
     use_graph = not args.no_graph
-    tr = build_trainer(cfg, device, dtype, world, use_graph, overlap=not args.no_overlap)
+    tr = build_trainer(cfg, device, dtype, world, use_graph, overlap=not args.no_overlap, bucket_mb=args.bucket_mb, early=args.dp_early, transport=args.transport)
     B, n_frames, nc = cfg['batch_size'], cfg['nt_cond'] + cfg['nt_pred'], cfg['nt_cond']
     shape = (B, n_frames) + tuple(cfg['shape'])
     static_in = tr.input_buffer(shape, device)
@@ -331,6 +334,8 @@ def run_ours(args, cfg):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
         'config': config,
         'run': {'global_batch': world * B, 'parallelism': f'dp{world}', 'cuda_graph': bool(use_graph),
+                'gradient_exchange': ('none' if world == 1 else 'peer-memory all-reduce kernel (vs_peer_allreduce)'
+                                      if getattr(tr.reducer, 'peer', None) is not None else 'nccl all-reduce, bucketed'),
                 'stepper': 'spatiotemporal_variable_separation_b200.train.GraphedStep'},
         'e2e': {'value': e2e_value, 'unit': 'sequences/s', 'h2d_bytes_per_step': host[0].numel() * 4,
                 'd2h_bytes_per_step': 5 * 4, 'ms_per_step': ms_e2e / args.steps},
@@ -549,6 +554,9 @@ def main():
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-overlap', action='store_true', help='all-reduce after backward instead of overlapped buckets')
+    ap.add_argument('--bucket-mb', type=float, default=None, help='gradient bucket size of the encoders (parallel.GradReducer)')
+    ap.add_argument('--transport', default='peer', choices=['peer', 'nccl'], help='gradient exchange: NVLink peer-memory kernel or NCCL')
+    ap.add_argument('--dp-early', default=None, help='networks whose gradient buckets may leave during backward (comma list)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-baseline', action='store_true')
     ap.add_argument('--cpu-budget', type=float, default=15.0)

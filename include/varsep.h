@@ -213,6 +213,18 @@ int vs_tail_bn_backward(const vs_conv_geom* g, const void* y, const float* mean,
 int vs_moving_sequences(const uint8_t* glyphs, int32_t n_glyphs, int32_t gh, int32_t gw, const int32_t* objs,
                         int32_t n_obj, int32_t B, int32_t T, int32_t F, float* frames, void* stream);
 
+/* ---- gradient exchange over NVLink peer memory (data-parallel training) ----
+ * replaces: ncclAllReduce of the gradient arena (the reference has no multi-GPU path; this is the exchange step of the
+ * batch-sharded design).  Every rank's arena (and a `world`-word flag array) is mapped into every process (CUDA IPC);
+ * *_ptrs_host are HOST arrays of `world` device pointers, entry r = rank r's buffer as addressable from this process.
+ * vs_peer_allreduce: rank `rank` sums slice `rank` of all arenas in rank order and writes the sum into all arenas
+ * (fused reduce-scatter + all-gather; n fp32 elements, n % 4 == 0; max_blocks caps the grid, 0 = 2 per SM).
+ * vs_peer_barrier : all ranks' preceding work on their streams is complete and visible before any rank's following
+ * work starts; *epoch_dev (device, zero-initialised, same history on all ranks) counts the barriers. */
+int vs_peer_barrier(void* const* flag_ptrs_host, int32_t rank, int32_t world, uint32_t* epoch_dev, void* stream);
+int vs_peer_allreduce(void* const* arena_ptrs_host, int32_t rank, int32_t world, int64_t n, int32_t max_blocks,
+                      void* stream);
+
 /* ---- optimizer -----------------------------------------------------------------------------
  * replaces: torch.optim.Adam.step (main.py:145, train.py:162): eps-outside-sqrt, bias-corrected, no decay.
  * One launch over a flat, 16-byte aligned parameter arena.  The 1-based step count is step_host, or

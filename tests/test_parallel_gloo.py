@@ -35,7 +35,7 @@ def _worker(rank, world, port, out_dir):
         net = build_filled(cfg).train()
         broadcast_model(net)
         opt = FusedAdam(net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
-        red = GradReducer(net, opt, overlap=True, bucket_bytes=16 << 10)    # small buckets: several per network
+        red = GradReducer(net, opt, overlap=True, bucket_bytes=16 << 10, early=('decoder', 't_resnet', 'Es', 'Et'))   # small buckets, all leave early
         cond, target = harness.inputs(cfg)
         full = torch.cat([cond, target], 1)
         shard = full[rank * 2:(rank + 1) * 2]                       # 2 sequences per rank

@@ -24,7 +24,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, transport):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
@@ -40,7 +40,9 @@ def _worker(rank, world, port, out_dir):
     net = build_filled(cfg, dev).train()
     broadcast_model(net)
     opt = FusedAdam(net.parameters(), cfg['lr'], (cfg['beta1'], cfg['beta2']))
-    red = GradReducer(net, opt, overlap=True, bucket_bytes=16 << 10)
+    red = GradReducer(net, opt, overlap=True, bucket_bytes=16 << 10, early=('decoder', 't_resnet', 'Es', 'Et'),
+                      transport=transport)
+    assert (red.peer is not None) == (transport == 'peer')
     cond, target = harness.inputs(cfg)
     full = torch.cat([cond, target], 1)
     shard = full[rank * 2:(rank + 1) * 2].to(dev)
@@ -75,11 +77,13 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(600)
-def test_nccl_bucketed_allreduce_world2(tmp_path):
+@pytest.mark.parametrize('transport', ['peer', 'nccl'])
+def test_gradient_exchange_world2(tmp_path, transport):
+    """'peer': the hand-written all-reduce over NVLink peer memory (csrc/peer.cu); 'nccl': bucketed ncclAllReduce."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs (gpurun --gpus 2)')
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), transport), nprocs=2, join=True)
     r0, r1 = (torch.load(tmp_path / f'rank{r}.pt') for r in (0, 1))
     assert r0['scale'] == r1['scale'] == 0.5
     want = r0['local'] + r1['local']
@@ -91,4 +95,5 @@ def test_nccl_bucketed_allreduce_world2(tmp_path):
     assert torch.equal(r0['params'], r1['params'])            # replicas stay bit-identical after Adam
     assert torch.equal(r0['graphed'], r1['graphed'])          # ... and after graph-replayed steps
     assert not torch.equal(r0['local'], r1['local'])          # the shards really differed
-    assert len(r0['early']) >= r0['n_buckets'] - 2 and any(n.startswith('decoder') for n in r0['early'])
+    if transport == 'nccl':
+        assert len(r0['early']) >= r0['n_buckets'] - 2 and any(n.startswith('decoder') for n in r0['early'])
