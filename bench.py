@@ -203,7 +203,7 @@ def workload_name(cfg):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def build_trainer(cfg, device, dtype, world, use_graph, overlap=True, bucket_mb=None, early=None, transport='peer'):
+def build_trainer(cfg, device, dtype, world, use_graph, overlap=True, bucket_mb=None, early=None, transport='peer', early_blocks=None, wire=None):
     """Model + fused Adam + the package's graphed stepper (train.GraphedStep) — what train() itself builds."""
     from spatiotemporal_variable_separation_b200 import ops, train as vs_train
     from spatiotemporal_variable_separation_b200.networks.factory import build_model
@@ -218,6 +218,10 @@ def build_trainer(cfg, device, dtype, world, use_graph, overlap=True, bucket_mb=
     kw = {'bucket_bytes': int(bucket_mb * (1 << 20))} if bucket_mb else {}
     if early is not None:
         kw['early'] = tuple(n for n in early.split(',') if n)
+    if early_blocks is not None:
+        kw['early_blocks'] = early_blocks
+    if wire is not None:
+        kw['wire_dtype'] = torch.bfloat16 if wire == 'bf16' else torch.float32
     reducer = GradReducer(net, opt, overlap=overlap, transport=transport, **kw) if world > 1 else None
     c = cfg
     return vs_train.GraphedStep(net, opt, c['nt_cond'], c['nt_pred'], c['offset'], c['skipco'], c['lamb_ae'], c['lamb_s'],
@@ -241,7 +245,7 @@ def run_ours(args, cfg):
         dist.init_process_group('nccl', device_id=device)
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
     use_graph = not args.no_graph
-    tr = build_trainer(cfg, device, dtype, world, use_graph, overlap=not args.no_overlap, bucket_mb=args.bucket_mb, early=args.dp_early, transport=args.transport)
+    tr = build_trainer(cfg, device, dtype, world, use_graph, overlap=not args.no_overlap, bucket_mb=args.bucket_mb, early=args.dp_early, transport=args.transport, early_blocks=args.early_blocks, wire=args.wire)
     B, n_frames, nc = cfg['batch_size'], cfg['nt_cond'] + cfg['nt_pred'], cfg['nt_cond']
     shape = (B, n_frames) + tuple(cfg['shape'])
     static_in = tr.input_buffer(shape, device)
@@ -334,7 +338,7 @@ def run_ours(args, cfg):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
         'config': config,
         'run': {'global_batch': world * B, 'parallelism': f'dp{world}', 'cuda_graph': bool(use_graph),
-                'gradient_exchange': ('none' if world == 1 else 'peer-memory all-reduce kernel (vs_peer_allreduce)'
+                'gradient_exchange': ('none' if world == 1 else f'peer-memory all-reduce kernel (vs_peer_allreduce, wire {"bf16" if tr.reducer.peer is not None and tr.reducer.peer.wire is not None else "fp32"})'
                                       if getattr(tr.reducer, 'peer', None) is not None else 'nccl all-reduce, bucketed'),
                 'stepper': 'spatiotemporal_variable_separation_b200.train.GraphedStep'},
         'e2e': {'value': e2e_value, 'unit': 'sequences/s', 'h2d_bytes_per_step': host[0].numel() * 4,
@@ -556,6 +560,8 @@ def main():
     ap.add_argument('--no-overlap', action='store_true', help='all-reduce after backward instead of overlapped buckets')
     ap.add_argument('--bucket-mb', type=float, default=None, help='gradient bucket size of the encoders (parallel.GradReducer)')
     ap.add_argument('--transport', default='peer', choices=['peer', 'nccl'], help='gradient exchange: NVLink peer-memory kernel or NCCL')
+    ap.add_argument('--wire', default=None, choices=['fp32', 'bf16'], help='wire format of the peer gradient exchange (default: the compute dtype)')
+    ap.add_argument('--early-blocks', type=int, default=None, help='CTAs of an early (overlapped) peer exchange')
     ap.add_argument('--dp-early', default=None, help='networks whose gradient buckets may leave during backward (comma list)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-baseline', action='store_true')

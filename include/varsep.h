@@ -224,6 +224,14 @@ int vs_moving_sequences(const uint8_t* glyphs, int32_t n_glyphs, int32_t gh, int
 int vs_peer_barrier(void* const* flag_ptrs_host, int32_t rank, int32_t world, uint32_t* epoch_dev, void* stream);
 int vs_peer_allreduce(void* const* arena_ptrs_host, int32_t rank, int32_t world, int64_t n, int32_t max_blocks,
                       void* stream);
+/* bf16 transport of the same exchange (half the NVLink bytes; the usual compressed gradient all-reduce of bf16 training):
+ * vs_grad_compress rounds n fp32 gradients to bf16 into a peer-mapped buffer, vs_peer_allreduce_bf16 sums slice `rank` of
+ * the `world` bf16 buffers in fp32 and writes the bf16-rounded sum into all of them, vs_grad_expand widens the result
+ * back into the fp32 arena.  n % 8 == 0. */
+int vs_grad_compress(const float* grad, void* out_bf16, int64_t n, void* stream);
+int vs_grad_expand(const void* in_bf16, float* grad, int64_t n, void* stream);
+int vs_peer_allreduce_bf16(void* const* buf_ptrs_host, int32_t rank, int32_t world, int64_t n, int32_t max_blocks,
+                           void* stream);
 
 /* ---- optimizer -----------------------------------------------------------------------------
  * replaces: torch.optim.Adam.step (main.py:145, train.py:162): eps-outside-sqrt, bias-corrected, no decay.

@@ -5,5 +5,6 @@ run() { echo "== $*"; env $ENVV timeout 600 python -m torch.distributed.run --nn
 import json,sys
 d=json.loads(sys.stdin.read()); print({k:round(d[k],3) for k in ('value','ms_per_step')})"; }
 ENVV="X=0" run
-ENVV="X=0" run --transport nccl
-ENVV="X=0" run --transport nccl --no-overlap
+ENVV="X=0" run --wire fp32
+ENVV="X=0" run --no-overlap
+ENVV="X=0" run --early-blocks 12

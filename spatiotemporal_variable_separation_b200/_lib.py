@@ -65,6 +65,9 @@ SIGNATURES = {
     'vs_moving_sequences': [_p, _i32, _i32, _i32, _p, _i32, _i32, _i32, _i32, _p, _p],
     'vs_peer_barrier': [_PP, _i32, _i32, _p, _p],
     'vs_peer_allreduce': [_PP, _i32, _i32, _i64, _i32, _p],
+    'vs_peer_allreduce_bf16': [_PP, _i32, _i32, _i64, _i32, _p],
+    'vs_grad_compress': [_p, _p, _i64, _p],
+    'vs_grad_expand': [_p, _p, _i64, _p],
     'vs_adam_step': [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i32, _p, _p, _p],
     'vs_tail_eligible': [_PG],
     'vs_tail_forward': [_PG, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p],

@@ -29,7 +29,7 @@ class FusedAdam:
         self.offsets, total = [], 0
         for p in self.params:
             self.offsets.append(total)
-            total += (p.numel() + 3) // 4 * 4            # keep every tensor 16-byte aligned
+            total += (p.numel() + 7) // 8 * 8            # every tensor starts on a 32-byte boundary (8 fp32 / 16 bytes of bf16)
         self.numel = total
         self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
