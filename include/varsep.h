@@ -67,7 +67,9 @@ int vs_pack_weight(const float* w, void* out, int32_t dtype, int32_t K, int32_t 
 
 /* All packed copies of a model in one launch (after the optimizer step).  table: DEVICE array of n rows
  * { const float* src; void* dst; int32 K, C, RS, swap, dtype, first_block; } (40 bytes, 8-byte aligned), rows ordered
- * by first_block; row i owns blocks [first_block_i, first_block_{i+1}) of 1024 elements each. */
+ * by first_block; row i owns blocks [first_block_i, first_block_{i+1}) of VS_PACK_BLOCK_ELEMS elements each (four
+ * 1024-element transpose tiles: their loads are issued together). */
+#define VS_PACK_BLOCK_ELEMS 4096
 int vs_pack_weights_multi(const void* table, int32_t n, int32_t total_blocks, void* stream);
 
 /* ---- convolution / linear -------------------------------------------------------------------

@@ -16,6 +16,7 @@ VS_F32, VS_BF16 = 0, 1
 ACT = {None: 0, 'none': 0, 'identity': 0, 'relu': 1, 'leaky_relu': 2, 'elu': 3, 'sigmoid': 4, 'tanh': 5}
 DIRECT, TRANSPOSED = 0, 1
 FLAG_FORCE_SIMT = 1
+VS_PACK_BLOCK_ELEMS = 4096          # include/varsep.h
 
 
 class Geom(C.Structure):

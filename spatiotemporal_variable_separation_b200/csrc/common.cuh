@@ -65,38 +65,40 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p,
 }
 
 // ---------------------------------------------------------------- activations (networks/utils.py:50-72)
+// none / ReLU / LeakyReLU are evaluated branch-free as  max(z, s*z)  with s = 1 / 0 / 0.2 (loop-invariant): a switch over all
+// six activations inside an unrolled epilogue compiles to one indirect branch PER ELEMENT (BRX + the exp / tanh code paths
+// replicated per call site), which cost the fused-activation epilogues several times their memory time.
+__device__ __forceinline__ float act_pl_slope(int act) { return act == VS_ACT_NONE ? 1.f : act == VS_ACT_RELU ? 0.f : 0.2f; }
+// (the transcendental activations sit behind a real call: kept out of line, the common path stays straight-line code)
+static __device__ __noinline__ float act_fwd_slow(float z, int act) {
+    if (act == VS_ACT_SIGMOID) return 1.f / (1.f + expf(-z));
+    if (act == VS_ACT_TANH) return tanhf(z);
+    return z > 0.f ? z : expm1f(z);                                     // VS_ACT_ELU
+}
 __device__ __forceinline__ float act_fwd(float z, int act) {
-    switch (act) {
-        case VS_ACT_RELU: return z > 0.f ? z : 0.f;
-        case VS_ACT_LEAKY: return z > 0.f ? z : 0.2f * z;
-        case VS_ACT_ELU: return z > 0.f ? z : expm1f(z);
-        case VS_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
-        case VS_ACT_TANH: return tanhf(z);
-        default: return z;
-    }
+    if (act <= VS_ACT_LEAKY) return fmaxf(z, act_pl_slope(act) * z);
+    return act_fwd_slow(z, act);
+}
+static __device__ __noinline__ float act_grad_from_out_slow(float a, int act) {
+    if (act == VS_ACT_SIGMOID) return a * (1.f - a);
+    if (act == VS_ACT_TANH) return 1.f - a * a;
+    return a > 0.f ? 1.f : a + 1.f;                                     // VS_ACT_ELU
+}
+static __device__ __noinline__ float act_grad_from_in_slow(float z, int act) {
+    if (act == VS_ACT_SIGMOID) { float s = 1.f / (1.f + expf(-z)); return s * (1.f - s); }
+    if (act == VS_ACT_TANH) { float t = tanhf(z); return 1.f - t * t; }
+    return z > 0.f ? 1.f : expf(z);                                     // VS_ACT_ELU
 }
 // derivative expressed with the activation OUTPUT a = act(z) (all six are invertible enough for that;
 // ReLU/LeakyReLU use the sign, which the in-place reference ops also do)
 __device__ __forceinline__ float act_grad_from_out(float a, int act) {
-    switch (act) {
-        case VS_ACT_RELU: return a > 0.f ? 1.f : 0.f;
-        case VS_ACT_LEAKY: return a > 0.f ? 1.f : 0.2f;
-        case VS_ACT_ELU: return a > 0.f ? 1.f : a + 1.f;
-        case VS_ACT_SIGMOID: return a * (1.f - a);
-        case VS_ACT_TANH: return 1.f - a * a;
-        default: return 1.f;
-    }
+    if (act <= VS_ACT_LEAKY) return a > 0.f ? 1.f : act_pl_slope(act);
+    return act_grad_from_out_slow(a, act);
 }
 // derivative expressed with the pre-activation z
 __device__ __forceinline__ float act_grad_from_in(float z, int act) {
-    switch (act) {
-        case VS_ACT_RELU: return z > 0.f ? 1.f : 0.f;
-        case VS_ACT_LEAKY: return z > 0.f ? 1.f : 0.2f;
-        case VS_ACT_ELU: return z > 0.f ? 1.f : expf(z);
-        case VS_ACT_SIGMOID: { float s = 1.f / (1.f + expf(-z)); return s * (1.f - s); }
-        case VS_ACT_TANH: { float t = tanhf(z); return 1.f - t * t; }
-        default: return 1.f;
-    }
+    if (act <= VS_ACT_LEAKY) return z > 0.f ? 1.f : act_pl_slope(act);
+    return act_grad_from_in_slow(z, act);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -540,8 +540,9 @@ int conv_forward_im2col(const vs_conv_geom* g, int mode, const void* in, const v
 // XF: `small` is the PRE-BatchNorm tensor y of the layer below; the builder warps apply BatchNorm + activation to every
 // landed box of it in shared memory (one fused multiply-add + max per element) before the MMA reads it, so the
 // weight gradient of the fused decoder tail needs no materialised normalised tensor.
+constexpr int IMW_THREADS = 192, IMW_XF_THREADS = 128;
 template <int BN, int STAGES, bool XF>
-__global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_constant__ CUtensorMap map_small,
+__global__ void __launch_bounds__(IMW_THREADS + (XF ? IMW_XF_THREADS : 0), 2) im2col_wgrad_kernel(const __grid_constant__ CUtensorMap map_small,
                                                               const __grid_constant__ CUtensorMap map_big,
                                                               const __grid_constant__ Im2colParams p,
                                                               const __grid_constant__ BnApplyArgs bn, float* __restrict__ dw) {
@@ -571,8 +572,8 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_small);
         prefetch_tmap(&map_big);
-        // full: TMA expect + 4 builder warps (XF: the builders alone, after they have transformed the landed box)
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], XF ? 4 : 5); mbar_init(&empty[i], 1); if (XF) mbar_init(&bfull[i], 1); }
+        // full: TMA expect + 4 builder warps (XF: 4 builder warps + 4 transform warps, the latter after the box has landed)
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], XF ? 8 : 5); mbar_init(&empty[i], 1); if (XF) mbar_init(&bfull[i], 1); }
         for (int i = 0; i < IM_PST; ++i) { mbar_init(&pready[i], 1); mbar_init(&pempty[i], 4); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -633,6 +634,47 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
             }
             umma_commit(tmem_full);
         }
+    } else if (XF && warp >= IMW_THREADS / 32) {
+        // ===== XF: BatchNorm + activation applied in place to every landed box of `small` =====
+        // chunk id = t + 128 i of the [64 pixels][128 B] box: row t/8 + 16 i, physical chunk t%8 -> always the same eight
+        // channels for this thread (the swizzle XORs the chunk index with row & 7 = (t/8) & 7)
+        const int t = threadIdx.x - IMW_THREADS;
+        const int xphys = t & 7, xrsub = t >> 3, xcg = xphys ^ (xrsub & 7);
+        float xsc[8], xsh[8];          // z = y * sc + sh with sc = gamma * invstd, sh = beta - mean * sc
+        int xg = -1;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % STAGES;
+            const int g = ((pt0 + kb) / (p.tiles_w * p.tiles_h)) * p.NT / bn.n_per_group;
+            if (g != xg) {
+                xg = g;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = kt * BN + xcg * 8 + e;
+                    xsc[e] = __ldg(bn.gamma + c) * __ldg(bn.invstd + (long long)g * p.K + c);
+                    xsh[e] = __ldg(bn.beta + c) - __ldg(bn.mean + (long long)g * p.K + c) * xsc[e];
+                }
+            }
+            mbar_wait(&bfull[st], (kb / STAGES) & 1);
+            uint8_t* base = smem + st * STAGE_BYTES + A_BYTES + xrsub * 128 + xphys * 16;
+#pragma unroll
+            for (int i = 0; i < PIX / 16; ++i) {
+                uint4* qp = reinterpret_cast<uint4*>(base + i * 16 * 128);
+                uint4 v = *qp;
+                uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float a0 = __uint_as_float(wv[e] << 16), a1 = __uint_as_float(wv[e] & 0xffff0000u);
+                    const float z0 = fmaf(a0, xsc[2 * e], xsh[2 * e]), z1 = fmaf(a1, xsc[2 * e + 1], xsh[2 * e + 1]);
+                    const float r0 = fmaxf(z0, bn.neg_slope * z0), r1 = fmaxf(z1, bn.neg_slope * z1);
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
+                    wv[e] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                *qp = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[st]);
+        }
     } else {
         // ===== builders: items = (16-byte chunk j, pixel m), m fastest =====
         const int t = threadIdx.x - 64;                   // 0..127
@@ -651,11 +693,6 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
             for (int i = 0; i < 8; ++i) { co.off[i] = c0.off[i]; co.off[8 + i] = c1.off[i]; }
             co.valid = (c0.valid & 0xffu) | ((c1.valid & 0xffu) << 8);
         }
-        // XF: chunk id = t + 128 i of the landed [64 pixels][128 B] box: row t/8 + 16 i, physical chunk t%8 -> always the same
-        // eight channels for this thread (the swizzle XORs the chunk index with row & 7 = (t/8) & 7)
-        const int xphys = t & 7, xrsub = t >> 3, xcg = xphys ^ (xrsub & 7);
-        float xsc[XF ? 8 : 1], xsh[XF ? 8 : 1];          // z = y * sc + sh with sc = gamma * invstd, sh = beta - mean * sc
-        int xg = -1;
         for (int kb = 0; kb < nkb; ++kb) {
             const int st = kb % STAGES, ps = kb % IM_PST;
             const int q0 = ((pt0 + kb) % p.tiles_w) * p.WT;
@@ -663,18 +700,6 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
             uint8_t* a_dst = smem + st * STAGE_BYTES;
             mbar_wait(&pready[ps], (kb / IM_PST) & 1);
             mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
-            if (XF) {
-                const int g = ((pt0 + kb) / (p.tiles_w * p.tiles_h)) * p.NT / bn.n_per_group;
-                if (g != xg) {
-                    xg = g;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int c = kt * BN + xcg * 8 + e;
-                        xsc[e] = __ldg(bn.gamma + c) * __ldg(bn.invstd + (long long)g * p.K + c);
-                        xsh[e] = __ldg(bn.beta + c) - __ldg(bn.mean + (long long)g * p.K + c) * xsc[e];
-                    }
-                }
-            }
             if (cached) {
                 if (cj < p.nchunk16) *reinterpret_cast<uint4*>(a_dst + cm * 128 + ((cj ^ (cm & 7)) << 4)) = gather_cached(pb, co, 0);
                 if (cj + 2 < p.nchunk16) *reinterpret_cast<uint4*>(a_dst + cm * 128 + (((cj + 2) ^ (cm & 7)) << 4)) = gather_cached(pb, co, 1);
@@ -685,25 +710,6 @@ __global__ void __launch_bounds__(192, 2) im2col_wgrad_kernel(const __grid_const
                     const int base = h * p.stride * p.PWCp + w * p.stride * p.C;
                     const uint4 v = im2col_chunk(p, pb, tab, base, j);
                     *reinterpret_cast<uint4*>(a_dst + (j >> 3) * CHUNK + m * 128 + (((j & 7) ^ (m & 7)) << 4)) = v;
-                }
-            }
-            if (XF) {
-                mbar_wait(&bfull[st], (kb / STAGES) & 1);
-                uint8_t* base = a_dst + A_BYTES + xrsub * 128 + xphys * 16;
-#pragma unroll
-                for (int i = 0; i < PIX / 16; ++i) {
-                    uint4* qp = reinterpret_cast<uint4*>(base + i * 16 * 128);
-                    uint4 v = *qp;
-                    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float a0 = __uint_as_float(wv[e] << 16), a1 = __uint_as_float(wv[e] & 0xffff0000u);
-                        const float z0 = fmaf(a0, xsc[2 * e], xsh[2 * e]), z1 = fmaf(a1, xsc[2 * e + 1], xsh[2 * e + 1]);
-                        const float r0 = fmaxf(z0, bn.neg_slope * z0), r1 = fmaxf(z1, bn.neg_slope * z1);
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
-                        wv[e] = *reinterpret_cast<uint32_t*>(&b2);
-                    }
-                    *qp = make_uint4(wv[0], wv[1], wv[2], wv[3]);
                 }
             }
             fence_proxy_async();
@@ -749,7 +755,7 @@ static int launch_imw(const CUtensorMap& ms, const CUtensorMap& mb, const Im2col
         configured.flag() = true;
     }
     dim3 grid((unsigned)k_tiles, 1, (unsigned)splits);
-    im2col_wgrad_kernel<BN, STAGES, XF><<<grid, 192, SMEM, stream>>>(ms, mb, p, bn, dw);
+    im2col_wgrad_kernel<BN, STAGES, XF><<<grid, IMW_THREADS + (XF ? IMW_XF_THREADS : 0), SMEM, stream>>>(ms, mb, p, bn, dw);
     return launched("im2col_wgrad_kernel");
 }
 

@@ -323,7 +323,10 @@ __global__ void pack_multi_kernel(const PackEntry* __restrict__ gtable, int n, i
     PackEntry* table = reinterpret_cast<PackEntry*>(pack_smem);
     for (int i = threadIdx.x; i < n * (int)(sizeof(PackEntry) / 8); i += blockDim.x)
         reinterpret_cast<unsigned long long*>(table)[i] = reinterpret_cast<const unsigned long long*>(gtable)[i];
-    __shared__ float tile[PACK_BT * (PACK_MAX_RS + 1)];
+    // PACK_U tiles per iteration of the fast paths: four 16-byte loads per thread in flight before the first barrier (one
+    // tile per iteration left the kernel latency-bound: 93 us for 22 M elements, 0.7 TB/s)
+    constexpr int PACK_U = 4, TILE_F = PACK_BT * (PACK_MAX_RS + 1);
+    __shared__ float tile[PACK_U * TILE_F];
     __syncthreads();
     for (int vb = blockIdx.x; vb < total_blocks; vb += gridDim.x) {
         int lo = 0, hi = n - 1;
@@ -344,22 +347,36 @@ __global__ void pack_multi_kernel(const PackEntry* __restrict__ gtable, int n, i
                 // full 128-byte line (the 64-value form read 64-byte pieces 8+ KB apart: DRAM-page bound at 0.5 TB/s), every
                 // (c, tap) row of the output receives one 64-byte run of k.
                 const int tiles_k = e.K / 32, ntl = (e.C / 2) * tiles_k;
-                for (int tl = vb - e.first_block; tl < ntl; tl += nblk) {
-                    const int c0 = (tl / tiles_k) * 2, k0 = (tl % tiles_k) * 32;
-                    {
-                        const int kl = threadIdx.x >> 3, f = threadIdx.x & 7;
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(e.src + ((long long)(k0 + kl) * e.C + c0) * 16) + f);
-                        float* d = tile + kl * 33 + f * 4;
-                        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                for (int tl0 = vb - e.first_block; tl0 < ntl; tl0 += PACK_U * nblk) {
+                    const int kl = threadIdx.x >> 3, f = threadIdx.x & 7;
+                    float4 v[PACK_U];
+#pragma unroll
+                    for (int u = 0; u < PACK_U; ++u) {
+                        const int tl = tl0 + u * nblk;
+                        if (tl < ntl) {
+                            const int c0 = (tl / tiles_k) * 2, k0 = (tl % tiles_k) * 32;
+                            v[u] = __ldg(reinterpret_cast<const float4*>(e.src + ((long long)(k0 + kl) * e.C + c0) * 16) + f);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PACK_U; ++u) {
+                        float* d = tile + u * TILE_F + kl * 33 + f * 4;
+                        if (tl0 + u * nblk < ntl) { d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w; }
                     }
                     __syncthreads();
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int idx2 = threadIdx.x + h * 256, kp = idx2 & 15, ct = idx2 >> 4;       // ct = c_local * 16 + tap
-                        const float v0 = tile[(2 * kp) * 33 + ct], v1 = tile[(2 * kp + 1) * 33 + ct];
-                        const long long o = ((long long)c0 * 16 + ct) * e.K + k0 + 2 * kp;
-                        if (e.dtype == VS_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(e.dst) + o) = make_float2(v0, v1);
-                        else *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(e.dst) + o) = __floats2bfloat162_rn(v0, v1);
+                    for (int u = 0; u < PACK_U; ++u) {
+                        const int tl = tl0 + u * nblk;
+                        if (tl >= ntl) break;
+                        const int c0 = (tl / tiles_k) * 2, k0 = (tl % tiles_k) * 32;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int idx2 = threadIdx.x + h * 256, kp = idx2 & 15, ct = idx2 >> 4;       // ct = c_local * 16 + tap
+                            const float v0 = tile[u * TILE_F + (2 * kp) * 33 + ct], v1 = tile[u * TILE_F + (2 * kp + 1) * 33 + ct];
+                            const long long o = ((long long)c0 * 16 + ct) * e.K + k0 + 2 * kp;
+                            if (e.dtype == VS_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(e.dst) + o) = make_float2(v0, v1);
+                            else *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(e.dst) + o) = __floats2bfloat162_rn(v0, v1);
+                        }
                     }
                     __syncthreads();
                 }
@@ -369,6 +386,46 @@ __global__ void pack_multi_kernel(const PackEntry* __restrict__ gtable, int n, i
             const int pitch = RS | 1;
             const int tiles_b = (B + PACK_BT - 1) / PACK_BT, ntiles = A * tiles_b;
             const long long row_pitch = e.swap ? (long long)e.C * RS : RS;
+            if (RS == 16 && B % PACK_BT == 0 && ((reinterpret_cast<uintptr_t>(e.src) | (uintptr_t)(row_pitch * 4)) & 15) == 0 &&
+                (((uintptr_t)e.dst | (uintptr_t)(B * 2)) & 7) == 0) {
+                // 4x4 filters, whole tiles only: PACK_U tiles per iteration (see above)
+                for (int tl0 = vb - e.first_block; tl0 < ntiles; tl0 += PACK_U * nblk) {
+                    const int row = threadIdx.x >> 2, quad = threadIdx.x & 3;
+                    float4 v[PACK_U];
+#pragma unroll
+                    for (int u = 0; u < PACK_U; ++u) {
+                        const int tl = tl0 + u * nblk;
+                        if (tl < ntiles) {
+                            const int a = tl / tiles_b, b0 = (tl - a * tiles_b) * PACK_BT;
+                            const float* src = e.src + (e.swap ? ((long long)b0 * e.C + a) * RS : ((long long)a * e.C + b0) * RS);
+                            v[u] = __ldg(reinterpret_cast<const float4*>(src + row * row_pitch) + quad);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PACK_U; ++u) {
+                        float* d = tile + u * TILE_F + row * pitch + quad * 4;
+                        if (tl0 + u * nblk < ntiles) { d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w; }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int u = 0; u < PACK_U; ++u) {
+                        const int tl = tl0 + u * nblk;
+                        if (tl >= ntiles) break;
+                        const int a = tl / tiles_b, b0 = (tl - a * tiles_b) * PACK_BT;
+                        const long long obase = (long long)a * RS * B + b0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int idx2 = threadIdx.x + h * 256, tap = idx2 >> 5, bp = idx2 & 31;
+                            const float v0 = tile[u * TILE_F + (2 * bp) * pitch + tap], v1 = tile[u * TILE_F + (2 * bp + 1) * pitch + tap];
+                            const long long o = obase + (long long)tap * B + 2 * bp;
+                            if (e.dtype == VS_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(e.dst) + o) = make_float2(v0, v1);
+                            else *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(e.dst) + o) = __floats2bfloat162_rn(v0, v1);
+                        }
+                    }
+                    __syncthreads();
+                }
+                continue;
+            }
             for (int tl = vb - e.first_block; tl < ntiles; tl += nblk) {
                 const int a = tl / tiles_b, b0 = (tl - a * tiles_b) * PACK_BT;
                 const int nb = B - b0 < PACK_BT ? B - b0 : PACK_BT;
@@ -413,8 +470,8 @@ __global__ void pack_multi_kernel(const PackEntry* __restrict__ gtable, int n, i
             }
             continue;
         }
-        const long long base = (long long)(vb - e.first_block) * 1024;
-        for (int t = threadIdx.x; t < 1024; t += blockDim.x) {
+        const long long base = (long long)(vb - e.first_block) * VS_PACK_BLOCK_ELEMS;
+        for (int t = threadIdx.x; t < VS_PACK_BLOCK_ELEMS; t += blockDim.x) {
             const long long i = base + t;
             if (i >= total) break;
             const int B = e.swap ? e.K : e.C;
@@ -446,6 +503,43 @@ __global__ void colsum_kernel(const T* __restrict__ a, long long rows, int C, fl
         float t = 0.f;
 #pragma unroll
         for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+        atomicAdd(&db[c], t);
+    }
+}
+
+// Column sums of a wide, long matrix (bias gradient of a layer without BatchNorm: 33 MB for the first encoder layer):
+// every thread owns 16 bytes of channels, four rows in flight, fp32 partial sums, one shared-memory reduction and one
+// atomic per column and block.  (The 32-column form above issues one 2-byte load per thread at a time: 1.3 TB/s.)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ a, long long rows, int C, float* __restrict__ db) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const int tpr = C / V;                               // threads per row (C % V == 0, tpr divides 256)
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rpi = 256 / tpr;
+    float s[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = 0.f;
+    const long long step = (long long)gridDim.x * rpi;
+    for (long long r = (long long)blockIdx.x * rpi + rl; r < rows; r += 4 * step) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long rr = r + u * step;
+            v[u] = rr < rows ? __ldg(reinterpret_cast<const uint4*>(a + rr * C) + cg) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const T* e = reinterpret_cast<const T*>(&v[u]);
+#pragma unroll
+            for (int j = 0; j < V; ++j) s[j] += ld<T>(e + j);
+        }
+    }
+    __shared__ float red[256 * 8];
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[(rl * tpr + cg) * V + j] = s[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+        for (int y = 0; y < rpi; ++y) t += red[y * C + c];
         atomicAdd(&db[c], t);
     }
 }
@@ -585,6 +679,15 @@ extern "C" int vs_colsum(const void* a, int32_t dtype, int64_t rows, int32_t C, 
         if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
         VS_DISPATCH_DTYPE(dtype, T, (colsum_narrow_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const T*)a, rows, C, db)));
         return launched("colsum_narrow_kernel");
+    }
+    {
+        const int V = dtype == VS_F32 ? 4 : 8;
+        if (C % V == 0 && 256 % (C / V) == 0 && C / V <= 256 && rows >= 4096 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+            long long blocks = cdiv(rows, (256 / (C / V)) * 8);
+            if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+            VS_DISPATCH_DTYPE(dtype, T, (colsum_vec_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const T*)a, rows, C, db)));
+            return launched("colsum_vec_kernel");
+        }
     }
     const int cx = (int)cdiv(C, 32);
     long long by = cdiv(2LL * num_sms(), cx);

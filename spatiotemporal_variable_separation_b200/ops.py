@@ -114,7 +114,7 @@ def repack_params(params, cache):
             for w, (K, C, RS, swap, dtype), out in live[lo:lo + _PACK_ROWS_PER_LAUNCH]:
                 rows.append(struct.pack('<QQiiiiii', w.data_ptr(), out.data_ptr(), K, C, RS, int(swap),
                                         L.VS_F32 if dtype == torch.float32 else L.VS_BF16, first))
-                first += (K * C * RS + 1023) // 1024
+                first += (K * C * RS + L.VS_PACK_BLOCK_ELEMS - 1) // L.VS_PACK_BLOCK_ELEMS
             blob = torch.frombuffer(bytearray(b''.join(rows)), dtype=torch.uint8).to(live[0][0].device)
             launches.append((blob, len(rows), first))
         cache.clear()

@@ -311,7 +311,8 @@ def test_elementwise_kernels(dt):
         gpu, cpu = run_both('vs_nchw_to_nhwc', [cpu[2], torch.zeros(N_, H_, W_, C_).to(dtype), code, N_, C_, H_, W_, None])
         assert torch.equal(gpu[1], cpu[1])
     # column sums (general, narrow, and the flat single-column form with a tail)
-    for rows, C_ in [(1000, 37), (5000, 3), (70001, 1), (100, 1)]:
+    # ... and the vectorised wide form (>= 4096 rows, 16-byte channel groups), with a row count that is not a multiple of anything
+    for rows, C_ in [(1000, 37), (5000, 3), (70001, 1), (100, 1), (40003, 64), (8191, 128), (5000, 8)]:
         m = torch.randn(rows, C_).to(dtype)
         gpu, cpu = run_both('vs_colsum', [m, code, rows, C_, torch.randn(C_), None])
         close(gpu[4], cpu[4], torch.float32, 'colsum', scale=float(cpu[4].abs().max()) + float(m.float().abs().sum(0).max()) * 1e-3)
