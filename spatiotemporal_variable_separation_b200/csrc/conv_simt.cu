@@ -628,7 +628,9 @@ int conv_wgrad_simt(const vs_conv_geom* g, const void* small_, const void* big, 
     const long long M = (long long)g->N * g->P * g->Q;
     const long long base = (long long)k_tiles * c_tiles * g->R * g->S;
     long long splits = cdiv(4LL * num_sms(), base);
-    const long long max_splits = cdiv(M, 256);
+    // few output tiles (the stepper's 512 x 20 linears: 8 tiles): the reduction over the rows is one dependent chain of
+    // load -> barrier -> FMA -> barrier per 16 rows, so short ranges (64 rows) on many CTAs beat 256-row ranges on 56
+    const long long max_splits = cdiv(M, base < num_sms() ? 64 : 256);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     long long rps = cdiv(cdiv(M, splits), BK) * BK;
