@@ -106,6 +106,12 @@ int vs_colsum(const void* a, int32_t dtype, int64_t rows, int32_t C, float* db, 
 int vs_bn_finalize(const double* stats, int32_t G, int32_t C, int64_t count, float eps, float momentum,
                    float* mean, float* invstd, float* running_mean, float* running_var,
                    int64_t* num_batches_tracked, void* stream);
+/* vs_bn_finalize followed by vs_bn_act_forward in ONE launch where the column kernel applies (identical results: every
+ * CTA derives mean / invstd of its channels from the fp64 sums; one CTA per group publishes them, one applies the EMA) */
+int vs_bn_finalize_act_forward(const double* stats, int32_t G, int32_t C, int64_t count, float eps, float momentum,
+                               float* mean, float* invstd, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, const void* y, void* out, int32_t dtype, int64_t rows,
+                               const float* gamma, const float* beta, int32_t act, void* stream);
 /* eval mode: mean = running_mean, invstd = rsqrt(running_var + eps) */
 int vs_bn_eval_stats(const float* running_mean, const float* running_var, int32_t C, float eps, float* mean,
                      float* invstd, void* stream);

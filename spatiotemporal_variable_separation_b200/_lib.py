@@ -42,6 +42,7 @@ SIGNATURES = {
     'vs_conv_wgrad': [_PG, _p, _p, _p, _p],
     'vs_colsum': [_p, _i32, _i64, _i32, _p, _p],
     'vs_bn_finalize': [_p, _i32, _i32, _i64, _f, _f, _p, _p, _p, _p, _p, _p],
+    'vs_bn_finalize_act_forward': [_p, _i32, _i32, _i64, _f, _f, _p, _p, _p, _p, _p, _p, _p, _i32, _i64, _p, _p, _i32, _p],
     'vs_bn_eval_stats': [_p, _p, _i32, _f, _p, _p, _p],
     'vs_bn_act_forward': [_p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _p],
     'vs_bn_act_backward_reduce': [_p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p],

@@ -298,16 +298,58 @@ static bool col_plan(long long rows, int C, int G, ColPlan& pl, int blocks_per_s
     long long r1 = r0 + pl.per;                                                           \
     if (r1 > (long long)(g + 1) * pl.rpg) r1 = (long long)(g + 1) * pl.rpg;
 
+// Optional fused vs_bn_finalize: with fin.stats != nullptr every thread derives mean / invstd of its channels from the fp64
+// sums itself (the arithmetic of bn_finalize_kernel), the chunk-0 block of every group publishes them for the backward
+// pass, and the (group 0, chunk 0) block applies the running-statistics EMA group by group: one launch less per layer.
+struct BnFinArgs {
+    const double* stats; double count; float eps, momentum;
+    float* mean_out; float* invstd_out; float* rmean; float* rvar; long long* nbt; int G;
+};
+
 // ACT >= 0: activation known at compile time (no per-element switch); ACT < 0: use the runtime argument
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bn_act_fwd_col_kernel(const T* __restrict__ y, T* __restrict__ out, int C, ColPlan pl,
                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int act_rt) {
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int act_rt,
+                                                             const BnFinArgs fin) {
     const int act = ACT >= 0 ? ACT : act_rt;
     VS_COL_SETUP
     float mu[W], is[W], ga[W], be[W];
+    if (fin.stats != nullptr) {
 #pragma unroll
-    for (int k = 0; k < W; ++k) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
+        for (int k = 0; k < W; ++k) {
+            const double s1 = fin.stats[((long long)g * C + c + k) * 2], s2 = fin.stats[((long long)g * C + c + k) * 2 + 1];
+            const double m = s1 / fin.count;
+            double var = s2 / fin.count - m * m;
+            if (var < 0.0) var = 0.0;
+            mu[k] = (float)m; is[k] = (float)(1.0 / sqrt(var + (double)fin.eps));
+            ga[k] = gamma[c + k]; be[k] = beta[c + k];
+        }
+        if (chunk == 0 && rl == 0) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) { fin.mean_out[g * C + c + k] = mu[k]; fin.invstd_out[g * C + c + k] = is[k]; }
+            if (g == 0) {
+                if (threadIdx.x == 0 && fin.nbt != nullptr) *fin.nbt += fin.G;
+#pragma unroll
+                for (int k = 0; k < W; ++k) {
+                    float rm = fin.rmean ? fin.rmean[c + k] : 0.f, rv = fin.rvar ? fin.rvar[c + k] : 0.f;
+                    for (int gg = 0; gg < fin.G; ++gg) {           // in the order of the reference's calls
+                        const double s1 = fin.stats[((long long)gg * C + c + k) * 2], s2 = fin.stats[((long long)gg * C + c + k) * 2 + 1];
+                        const double m = s1 / fin.count;
+                        double var = s2 / fin.count - m * m;
+                        if (var < 0.0) var = 0.0;
+                        rm = (1.f - fin.momentum) * rm + fin.momentum * (float)m;
+                        rv = (1.f - fin.momentum) * rv + fin.momentum * (float)(fin.count > 1.0 ? var * fin.count / (fin.count - 1.0) : var);
+                    }
+                    if (fin.rmean) fin.rmean[c + k] = rm;
+                    if (fin.rvar) fin.rvar[c + k] = rv;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
+    }
     // several independent rows in flight per thread (all raw 16-byte loads of a group are issued before any is
     // consumed; the group loop is branch-free so that the compiler keeps them back to back): the kernel is bound by
     // the bytes in flight per SM, not by arithmetic
@@ -343,11 +385,22 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_col_kernel(const T* __restri
                                                                int C, ColPlan pl, const float* __restrict__ mean,
                                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, int act_rt,
-                                                               const double* __restrict__ sums, int train) {
+                                                               const double* __restrict__ sums, int train,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta, int G) {
     const int act = ACT >= 0 ? ACT : act_rt;
     VS_COL_SETUP
     float mu[W], is[W], ga[W], be[W], m1[W], m2[W];
     const float inv_count = 1.f / (float)pl.rpg;
+    if ((dgamma != nullptr || dbeta != nullptr) && g == 0 && chunk == 0 && rl == 0) {
+        // the affine gradients (bn_param_grad_kernel folded in): sum of the per-group sums, one thread per channel slice
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int gg = 0; gg < G; ++gg) { s1 += sums[((long long)gg * C + c + k) * 2]; s2 += sums[((long long)gg * C + c + k) * 2 + 1]; }
+            if (dbeta) dbeta[c + k] += (float)s1;
+            if (dgamma) dgamma[c + k] += (float)s2;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < W; ++k) {
         mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k];
@@ -528,7 +581,9 @@ extern "C" int vs_bn_act_forward(const void* y, void* out, int32_t dtype, int64_
         ColPlan pl;
         if (col_plan<T>(rows, C, G, pl)) {
             VS_DISPATCH_ACT(act, A, {
-                bn_act_fwd_col_kernel<T, A><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)y, (T*)out, C, pl, mean, invstd, gamma, beta, act);
+                BnFinArgs none;
+                memset(&none, 0, sizeof(none));
+                bn_act_fwd_col_kernel<T, A><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)y, (T*)out, C, pl, mean, invstd, gamma, beta, act, none);
             });
             return launched("bn_act_fwd_col_kernel");
         }
@@ -540,6 +595,30 @@ extern "C" int vs_bn_act_forward(const void* y, void* out, int32_t dtype, int64_
         else bn_act_fwd_kernel<T, false><<<blocks, 256, 0, as_stream(stream)>>>((const T*)y, (T*)out, rows, C, rpg, mean, invstd, gamma, beta, act);
     });
     return launched("bn_act_fwd_kernel");
+}
+
+extern "C" int vs_bn_finalize_act_forward(const double* stats, int32_t G, int32_t C, int64_t count, float eps, float momentum,
+                                          float* mean, float* invstd, float* running_mean, float* running_var,
+                                          int64_t* num_batches_tracked, const void* y, void* out, int32_t dtype, int64_t rows,
+                                          const float* gamma, const float* beta, int32_t act, void* stream) {
+    VS_REQUIRE(G >= 1 && C >= 1 && count >= 1 && rows % G == 0, "bn_finalize_act_forward: bad sizes");
+    if (rows > 0) {
+        bool done = false;
+        VS_DISPATCH_DTYPE(dtype, T, {
+            ColPlan pl;
+            if (col_plan<T>(rows, C, G, pl)) {
+                BnFinArgs fin = {stats, (double)count, eps, momentum, mean, invstd, running_mean, running_var,
+                                 reinterpret_cast<long long*>(num_batches_tracked), G};
+                VS_DISPATCH_ACT(act, A, {
+                    bn_act_fwd_col_kernel<T, A><<<(unsigned)(G * pl.chunks), 256, 0, as_stream(stream)>>>((const T*)y, (T*)out, C, pl, mean, invstd, gamma, beta, act, fin);
+                });
+                done = true;
+            }
+        });
+        if (done) return launched("bn_act_fwd_col_kernel");
+    }
+    if (int rc = vs_bn_finalize(stats, G, C, count, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked, stream)) return rc;
+    return vs_bn_act_forward(y, out, dtype, rows, C, G, mean, invstd, gamma, beta, act, stream);
 }
 
 extern "C" int vs_bn_act_backward_reduce(const void* dout, const void* y, int32_t dtype, int64_t rows, int32_t C,
@@ -582,7 +661,7 @@ extern "C" int vs_bn_act_backward_apply(const void* dout, const void* y, void* d
         if (col_plan<T>(rows, C, G, pl)) {
             VS_DISPATCH_ACT(act, A, {
                 if (int rc = reduce_smem_attr(bn_bwd_apply_col_kernel<T, A>)) return rc;
-                bn_bwd_apply_col_kernel<T, A><<<(unsigned)(G * pl.chunks), 256, REDUCE_SMEM, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, C, pl, mean, invstd, gamma, beta, act, sums, train);
+                bn_bwd_apply_col_kernel<T, A><<<(unsigned)(G * pl.chunks), 256, REDUCE_SMEM, as_stream(stream)>>>((const T*)dout, (const T*)y, (T*)dy, C, pl, mean, invstd, gamma, beta, act, sums, train, dgamma, dbeta, G);
             });
             done = true;
         }
@@ -595,7 +674,7 @@ extern "C" int vs_bn_act_backward_apply(const void* dout, const void* y, void* d
     });
     int rc = launched("bn_bwd_apply_kernel");
     if (rc) return rc;
-    if (dgamma != nullptr || dbeta != nullptr) {
+    if (!done && (dgamma != nullptr || dbeta != nullptr)) {          // (the column kernel adds them itself)
         bn_param_grad_kernel<<<(int)cdiv(C, 128), 128, 0, as_stream(stream)>>>(sums, G, C, dgamma, dbeta);
         rc = launched("bn_param_grad_kernel");
     }

@@ -266,14 +266,16 @@ class ConvBlockFn(torch.autograd.Function):
             rows = y.numel() // OC
             mean = torch.empty(G * OC, device=x.device, dtype=torch.float32)
             invstd = torch.empty_like(mean)
+            out = torch.empty_like(y)
             if cfg.training:
-                L.call('vs_bn_finalize', ptr(stats), G, OC, rows // G, cfg.eps, cfg.momentum, ptr(mean), ptr(invstd),
-                     ptr(rmean), ptr(rvar), ptr(nbt), L.stream())
+                # statistics -> mean / invstd / running-stat EMA and normalise + activation in one launch
+                L.call('vs_bn_finalize_act_forward', ptr(stats), G, OC, rows // G, cfg.eps, cfg.momentum, ptr(mean),
+                       ptr(invstd), ptr(rmean), ptr(rvar), ptr(nbt), ptr(y), ptr(out), L.dtype_code(y), rows, ptr(gamma),
+                       ptr(beta), act, L.stream())
             else:
                 L.call('vs_bn_eval_stats', ptr(rmean), ptr(rvar), OC, cfg.eps, ptr(mean), ptr(invstd), L.stream())
-            out = torch.empty_like(y)
-            L.call('vs_bn_act_forward', ptr(y), ptr(out), L.dtype_code(y), rows, OC, G, ptr(mean), ptr(invstd),
-                 ptr(gamma), ptr(beta), act, L.stream())
+                L.call('vs_bn_act_forward', ptr(y), ptr(out), L.dtype_code(y), rows, OC, G, ptr(mean), ptr(invstd),
+                     ptr(gamma), ptr(beta), act, L.stream())
             ctx.save_for_backward(x, weight, y, mean, invstd, gamma, beta)
             ctx.G = G
         else:

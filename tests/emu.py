@@ -132,6 +132,12 @@ def vs_bn_finalize(stats, G, C, count, eps, momentum, mean, invstd, rmean, rvar,
         nbt += G
 
 
+def vs_bn_finalize_act_forward(stats, G, C, count, eps, momentum, mean, invstd, rmean, rvar, nbt, y, out, dtype, rows, gamma,
+                               beta, act, stream):
+    vs_bn_finalize(stats, G, C, count, eps, momentum, mean, invstd, rmean, rvar, nbt, None)
+    vs_bn_act_forward(y, out, dtype, rows, C, G, mean, invstd, gamma, beta, act, None)
+
+
 def vs_bn_eval_stats(rmean, rvar, C, eps, mean, invstd, stream):
     mean.copy_(rmean)
     invstd.copy_(1.0 / torch.sqrt(rvar + eps))

@@ -219,6 +219,14 @@ def test_bn_kernels(rows, C, G, dt):
     assert int(gpu[10]) == int(cpu[10]) == 3 + G
     mean, invstd = cpu[6], cpu[7]
     gamma, beta = torch.randn(C) * 0.1 + 1, torch.randn(C) * 0.1
+    # the fused form (finalize + normalise + activation in one launch where the column kernel applies)
+    m2_, i2_ = torch.zeros(G * C), torch.zeros(G * C)
+    gpu, cpu2 = run_both('vs_bn_finalize_act_forward', [stats, G, C, rows // G, 1e-5, 0.1, m2_, i2_, rmean, rvar, nbt, y,
+                                                        torch.zeros(rows, C).to(dtype), L.dtype_code(y), rows, gamma, beta, 2, None])
+    for i, n in ((6, 'mean'), (7, 'invstd'), (8, 'running_mean'), (9, 'running_var')):
+        close(gpu[i], cpu2[i], torch.float32, 'fused ' + n)
+    assert int(gpu[10]) == int(cpu2[10]) == 3 + G
+    close(gpu[12], cpu2[12], dtype, 'fused bn_act_forward', outliers=1e-4)
     for act in (0, 1, 2, 3, 4, 5):
         out = torch.zeros(rows, C).to(dtype)
         gpu, cpu = run_both('vs_bn_act_forward', [y, out, L.dtype_code(y), rows, C, G, mean, invstd, gamma, beta, act, None])
