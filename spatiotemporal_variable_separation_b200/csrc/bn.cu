@@ -301,6 +301,7 @@ static bool col_plan(long long rows, int C, int G, ColPlan& pl, int blocks_per_s
 // Optional fused vs_bn_finalize: with fin.stats != nullptr every thread derives mean / invstd of its channels from the fp64
 // sums itself (the arithmetic of bn_finalize_kernel), the chunk-0 block of every group publishes them for the backward
 // pass, and the (group 0, chunk 0) block applies the running-statistics EMA group by group: one launch less per layer.
+constexpr int BN_FIN_MAX_C = 1024;
 struct BnFinArgs {
     const double* stats; double count; float eps, momentum;
     float* mean_out; float* invstd_out; float* rmean; float* rvar; long long* nbt; int G;
@@ -316,36 +317,37 @@ __global__ void __launch_bounds__(256) bn_act_fwd_col_kernel(const T* __restrict
     VS_COL_SETUP
     float mu[W], is[W], ga[W], be[W];
     if (fin.stats != nullptr) {
-#pragma unroll
-        for (int k = 0; k < W; ++k) {
-            const double s1 = fin.stats[((long long)g * C + c + k) * 2], s2 = fin.stats[((long long)g * C + c + k) * 2 + 1];
+        // one thread per CHANNEL does the fp64 division / square root (not one per channel slice and row lane: the fp64
+        // sequences are a few hundred cycles each and would dominate the short launches), the block shares the result
+        __shared__ float s_mu[BN_FIN_MAX_C], s_is[BN_FIN_MAX_C];
+        for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+            const double s1 = fin.stats[((long long)g * C + ch) * 2], s2 = fin.stats[((long long)g * C + ch) * 2 + 1];
             const double m = s1 / fin.count;
             double var = s2 / fin.count - m * m;
             if (var < 0.0) var = 0.0;
-            mu[k] = (float)m; is[k] = (float)(1.0 / sqrt(var + (double)fin.eps));
-            ga[k] = gamma[c + k]; be[k] = beta[c + k];
-        }
-        if (chunk == 0 && rl == 0) {
-#pragma unroll
-            for (int k = 0; k < W; ++k) { fin.mean_out[g * C + c + k] = mu[k]; fin.invstd_out[g * C + c + k] = is[k]; }
-            if (g == 0) {
-                if (threadIdx.x == 0 && fin.nbt != nullptr) *fin.nbt += fin.G;
-#pragma unroll
-                for (int k = 0; k < W; ++k) {
-                    float rm = fin.rmean ? fin.rmean[c + k] : 0.f, rv = fin.rvar ? fin.rvar[c + k] : 0.f;
+            const float mf = (float)m, isf = (float)(1.0 / sqrt(var + (double)fin.eps));
+            s_mu[ch] = mf; s_is[ch] = isf;
+            if (chunk == 0) {
+                fin.mean_out[g * C + ch] = mf; fin.invstd_out[g * C + ch] = isf;
+                if (g == 0) {
+                    if (ch == 0 && fin.nbt != nullptr) *fin.nbt += fin.G;
+                    float rm = fin.rmean ? fin.rmean[ch] : 0.f, rv = fin.rvar ? fin.rvar[ch] : 0.f;
                     for (int gg = 0; gg < fin.G; ++gg) {           // in the order of the reference's calls
-                        const double s1 = fin.stats[((long long)gg * C + c + k) * 2], s2 = fin.stats[((long long)gg * C + c + k) * 2 + 1];
-                        const double m = s1 / fin.count;
-                        double var = s2 / fin.count - m * m;
-                        if (var < 0.0) var = 0.0;
-                        rm = (1.f - fin.momentum) * rm + fin.momentum * (float)m;
-                        rv = (1.f - fin.momentum) * rv + fin.momentum * (float)(fin.count > 1.0 ? var * fin.count / (fin.count - 1.0) : var);
+                        const double t1 = fin.stats[((long long)gg * C + ch) * 2], t2 = fin.stats[((long long)gg * C + ch) * 2 + 1];
+                        const double mg = t1 / fin.count;
+                        double vg = t2 / fin.count - mg * mg;
+                        if (vg < 0.0) vg = 0.0;
+                        rm = (1.f - fin.momentum) * rm + fin.momentum * (float)mg;
+                        rv = (1.f - fin.momentum) * rv + fin.momentum * (float)(fin.count > 1.0 ? vg * fin.count / (fin.count - 1.0) : vg);
                     }
-                    if (fin.rmean) fin.rmean[c + k] = rm;
-                    if (fin.rvar) fin.rvar[c + k] = rv;
+                    if (fin.rmean) fin.rmean[ch] = rm;
+                    if (fin.rvar) fin.rvar[ch] = rv;
                 }
             }
         }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < W; ++k) { mu[k] = s_mu[c + k]; is[k] = s_is[c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
     } else {
 #pragma unroll
         for (int k = 0; k < W; ++k) { mu[k] = mean[g * C + c + k]; is[k] = invstd[g * C + c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
@@ -606,7 +608,7 @@ extern "C" int vs_bn_finalize_act_forward(const double* stats, int32_t G, int32_
         bool done = false;
         VS_DISPATCH_DTYPE(dtype, T, {
             ColPlan pl;
-            if (col_plan<T>(rows, C, G, pl)) {
+            if (C <= BN_FIN_MAX_C && col_plan<T>(rows, C, G, pl)) {
                 BnFinArgs fin = {stats, (double)count, eps, momentum, mean, invstd, running_mean, running_var,
                                  reinterpret_cast<long long*>(num_batches_tracked), G};
                 VS_DISPATCH_ACT(act, A, {
