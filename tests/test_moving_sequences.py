@@ -93,3 +93,21 @@ def test_generator_feeds_the_training_loop():
         assert os.path.exists(os.path.join(d, 'decoder.pt'))
     assert int(opt.step_dev) == 4 and torch.isfinite(opt.flat_p).all() and not torch.equal(before, opt.flat_p)
     assert ops.compute_dtype() == torch.float32
+
+
+@pytest.mark.gpu
+def test_main_entry_point_writes_a_reloadable_experiment(tmp_path):
+    """main.py counterpart: params.json + checkpoints of a (tiny) run, reloaded by test/utils.load_model."""
+    from spatiotemporal_variable_separation_b200 import configs, main as vs_main
+    from spatiotemporal_variable_separation_b200.test.utils import load_model
+    import shlex
+    argv = ['--xp_dir', str(tmp_path), '--data_dir', str(tmp_path), '--device', '0', '--epochs', '1', '--synthetic_batches', '3'] + \
+        shlex.split(configs.README_FLAGS['mnist']) + shlex.split(configs.SMALL_FLAGS['mnist'])
+    vs_main.main(argv)
+    assert os.path.exists(tmp_path / 'params.json') and os.path.exists(tmp_path / 'ov_Es.pt')
+    net = load_model({'xp_dir': str(tmp_path), 'device': 'cuda'})
+    ms = vs_data.MovingSequences(GLYPHS, batch_size=4, device='cuda')
+    cond, _ = ms.batch()
+    with torch.no_grad():
+        f = net.get_forecast(cond, 6)[0]
+    assert f.shape == (4, 6, 1, 64, 64) and torch.isfinite(f).all()
