@@ -486,7 +486,7 @@ def kernel_rooflines(tr, shape, dev, draws, dtype):
     bn_bytes = [0.0]
     orig = _lib.call
     lib = _lib.load()
-    BN = ('vs_bn_act_forward', 'vs_bn_act_backward_reduce', 'vs_bn_act_backward_apply')
+    BN = ('vs_bn_act_forward', 'vs_bn_finalize_act_forward', 'vs_bn_act_backward_reduce', 'vs_bn_act_backward_apply')
 
     def timed_call(name, *a):
         is_conv = name == 'vs_conv_forward' and lib.vs_conv_forward_path(a[0], a[1]) == 1
@@ -505,7 +505,7 @@ def kernel_rooflines(tr, shape, dev, draws, dtype):
             g = a[0]
             conv_rec.append((e0, e1, 2.0 * g.N * g.P * g.Q * g.K * g.C * g.R * g.S))
         else:
-            if name == 'vs_bn_act_forward':
+            if name == 'vs_bn_act_backward_reduce':          # one per BatchNorm layer and step (dout, y, dtype, rows, C, ...)
                 rows, C, dt = a[3], a[4], a[2]
                 bn_layers[0] += 1
                 bn_bytes[0] += 2.0 * rows * C * (4 if dt == _lib.VS_F32 else 2)
@@ -543,7 +543,8 @@ def kernel_rooflines(tr, shape, dev, draws, dtype):
                     'ms_per_step': bn_ms / n_steps, 'algorithmic_bytes_per_step': bn_bytes[0] / n_steps,
                     'traffic': None,
                     'note': 'algorithmic bytes = 2 tensor passes per BatchNorm layer and step (the fused ideal) over the '
-                            'summed duration of every BatchNorm launch'}
+                            'summed duration of every BatchNorm launch (the last decoder BatchNorm is applied on the operand '
+                            'path of the fused tail kernel: its forward pass costs no launch here)'}
     return roof, roof_hbm
 
 
