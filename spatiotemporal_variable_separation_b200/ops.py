@@ -165,6 +165,69 @@ def set_grad_ready_hook(on_use, on_ready):
     _grad_hooks[0], _grad_hooks[1] = on_use, on_ready
 
 
+# ------------------------------------------------------------------------------------------------
+# weight gradients off the critical path.  The backward chain of a layer is  BatchNorm backward -> input gradient
+# (needed by the layer below) -> weight gradient (needed only by the optimizer).  When the gradient goes straight into
+# the optimizer's arena, the weight-gradient kernels are enqueued on a per-device side stream: they then run next to the
+# BatchNorm backward (HBM bound) and input-gradient kernels of the layers below instead of in front of them.  The stream
+# that called ``backward()`` waits for the side stream when the pass ends (engine callback); consumers that run INSIDE the
+# pass (the early gradient-exchange buckets) call ``join_wgrad`` themselves.
+# ------------------------------------------------------------------------------------------------
+_wgrad_streams = {}
+_wgrad_dirty = set()
+_wgrad_overlap = [True]
+
+
+def set_wgrad_overlap(flag):
+    _wgrad_overlap[0] = bool(flag)
+
+
+class _OnWgradStream:
+    """``with _OnWgradStream(buffer, *operands):`` — launches inside go to the side stream when ``buffer`` is an arena view
+    (``_grad_buffer`` returned no autograd tensor) on a CUDA device; the operands are kept alive for that stream."""
+
+    def __init__(self, gbuf, *operands):
+        dev = operands[0].device
+        self.on = _wgrad_overlap[0] and gbuf[1] is None and dev.type == 'cuda'
+        self.dev, self.operands = dev, operands
+
+    def __enter__(self):
+        if not self.on:
+            return self
+        ws = _wgrad_streams.get(self.dev)
+        if ws is None:
+            ws = _wgrad_streams[self.dev] = torch.cuda.Stream(device=self.dev)
+        ws.wait_stream(torch.cuda.current_stream(self.dev))
+        self.ctx = torch.cuda.stream(ws)
+        self.ctx.__enter__()
+        for t in self.operands:
+            t.record_stream(ws)
+        if self.dev not in _wgrad_dirty:
+            _wgrad_dirty.add(self.dev)
+            # when this backward pass ends, the stream it was called on waits for the side stream: `loss.backward()` keeps
+            # its meaning (gradients complete in stream order) for every consumer, not only for FusedAdam / GradReducer
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(join_wgrad)
+            except RuntimeError:
+                pass                                     # not inside a backward pass (direct call of a backward helper)
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join_wgrad(device=None, stream=None):
+    """Make ``stream`` (default: the current one) wait for the weight gradients enqueued on the side stream."""
+    for dev in list(_wgrad_dirty):
+        if device is not None and torch.device(device) != dev:
+            continue
+        (stream or torch.cuda.current_stream(dev)).wait_stream(_wgrad_streams[dev])
+        if stream is None:
+            _wgrad_dirty.discard(dev)
+
+
 ConvCfg = namedtuple('ConvCfg', 'kind K C R S stride pad act groups training has_bn eps momentum flags')
 
 
@@ -236,12 +299,14 @@ def _conv_backward(ctx, x, weight, dy, p_weight, p_bias, need_dx, need_dw, need_
             L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dwp), L.stream())
             dw[0].add_(dwp[:cfg0.K].view_as(dw[0]))
         else:
-            L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dw[0]), L.stream())
+            with _OnWgradStream(dw, small, big):
+                L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(dw[0]), L.stream())
     if p_bias is not None and need_db:
         db = _grad_buffer(p_bias)
         if not bias_is_dead:
             # (eval-mode BatchNorm is an affine map: the bias gradient is the plain column sum of dy)
-            L.call('vs_colsum', ptr(dy), L.dtype_code(dy), rows, OC, ptr(db[0]), L.stream())
+            with _OnWgradStream(db, dy):
+                L.call('vs_colsum', ptr(dy), L.dtype_code(dy), rows, OC, ptr(db[0]), L.stream())
         # else: BatchNorm's backward returns a dy whose per-(group, channel) sum is exactly zero, so the
         # bias gradient is mathematically 0 (the reference computes rounding noise there);
         # the (zero-initialised) buffer is left untouched instead of streaming dy once more.
@@ -390,11 +455,13 @@ class DecoderTailFn(torch.autograd.Function):
         dw3 = db3 = None
         if p_b3 is not None and ctx.needs_input_grad[9]:
             db3 = _grad_buffer(p_b3)
-            L.call('vs_colsum', ptr(dz3), L.dtype_code(dz3), dz3.numel() // cfg3.C, cfg3.C, ptr(db3[0]), L.stream())
+            with _OnWgradStream(db3, dz3):
+                L.call('vs_colsum', ptr(dz3), L.dtype_code(dz3), dz3.numel() // cfg3.C, cfg3.C, ptr(db3[0]), L.stream())
         if ctx.needs_input_grad[8]:
             dw3 = _grad_buffer(p_w3)
-            L.call('vs_tail_wgrad', g3, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), G, act2, ptr(dz3), ptr(dw3[0]),
-                   L.stream())
+            with _OnWgradStream(dw3, y, dz3, mean, invstd):
+                L.call('vs_tail_wgrad', g3, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), G, act2, ptr(dz3),
+                       ptr(dw3[0]), L.stream())
         # ---- BatchNorm backward.  Default: the thin layer's input gradient is materialised once (bf16) and the two column
         # kernels stream it.  ``VARSEP_TAIL_FUSED_BACKWARD=1`` recomputes it inside both passes instead
         # (vs_tail_bn_backward: correct, less HBM traffic, but its one-row-per-thread epilogue costs more issue slots than
@@ -952,8 +1019,9 @@ class LatentRolloutFn(torch.autograd.Function):
             gw, gb = _grad_buffer(p_w), _grad_buffer(p_b)
             if rows > 0:
                 g = L.Geom(L.VS_F32, rows, 1, 1, Cc, 1, 1, K, 1, 1, 1, 0, 1, 0, 0)
-                L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(gw[0]), L.stream())
-                L.call('vs_colsum', ptr(small), L.VS_F32, rows, K, ptr(gb[0]), L.stream())
+                with _OnWgradStream(gw if gb[1] is None else gb, small, big):
+                    L.call('vs_conv_wgrad', g, ptr(small), ptr(big), ptr(gw[0]), L.stream())
+                    L.call('vs_colsum', ptr(small), L.VS_F32, rows, K, ptr(gb[0]), L.stream())
             return gw[1], gb[1]
 
         for j in range(nb):

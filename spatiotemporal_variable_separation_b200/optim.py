@@ -74,6 +74,7 @@ class FusedAdam:
         return self._groups[0]['eps']
 
     def zero_grad(self, set_to_none=False):
+        ops.join_wgrad(self.flat_p.device)
         self.flat_g.zero_()
 
     def sync_lr(self):
@@ -84,6 +85,7 @@ class FusedAdam:
             self._lr_uploaded = self.lr
 
     def step(self):
+        ops.join_wgrad(self.flat_p.device)             # weight gradients enqueued on the side stream (ops._OnWgradStream)
         if not (self.flat_p.is_cuda and torch.cuda.is_current_stream_capturing()):
             self.sync_lr()
         self.step_dev += 1

@@ -277,6 +277,7 @@ class GradReducer:
             streams.setdefault(cur.cuda_stream, cur)
             for s in streams.values():
                 self.comm_stream.wait_stream(s)
+            ops.join_wgrad(bucket.device, self.comm_stream)      # the weight gradients themselves run on a side stream
             with torch.cuda.stream(self.comm_stream):
                 if self.peer is not None:
                     # a few CTAs only: the exchange runs next to the rest of backward and must not push the persistent
@@ -298,6 +299,7 @@ class GradReducer:
         bucket waiting) and make the compute stream wait for all buckets."""
         ops.set_grad_ready_hook(None, None)
         self._armed = False
+        ops.join_wgrad(self.opt.flat_g.device)
         if self.peer is not None and self.comm_stream is not None:
             # the early partial exchanges share the flags / epoch with the final one: strictly one after the other
             torch.cuda.current_stream(self.opt.flat_g.device).wait_stream(self.comm_stream)
