@@ -511,8 +511,10 @@ def kernel_rooflines(tr, shape, dev, draws, dtype):
                 bn_bytes[0] += 2.0 * rows * C * (4 if dt == _lib.VS_F32 else 2)
             bn_rec.append((e0, e1))
 
+    from spatiotemporal_variable_separation_b200 import ops
     graph, tr.graph = tr.graph, False
     _lib.call = timed_call
+    ops.set_wgrad_overlap(False)         # kernels are timed one by one: nothing may run next to them on another stream
     n_steps = 2
     try:
         for i in range(n_steps):
@@ -522,6 +524,7 @@ def kernel_rooflines(tr, shape, dev, draws, dtype):
     finally:
         _lib.call = orig
         tr.graph = graph
+        ops.set_wgrad_overlap(True)
     tot_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in conv_rec)
     tot_flop = sum(f for _, _, f in conv_rec)
     traffic = None

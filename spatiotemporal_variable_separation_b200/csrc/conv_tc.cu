@@ -31,6 +31,7 @@ struct TcParams {
     int IC, kchunks, ntaps;
     int in_sh, in_sw;         // class-grid -> input coordinate multiplier
     int act, has_bias, partial, n_per_group;
+    int res_taps;             // resident-weight pair kernel: filter taps R*S (slabs = res_taps * kchunks)
     signed char dh[TC_TABLE], dw[TC_TABLE];          // [class * ntaps + tap]: input offset of the tap on the class grid
     unsigned char wtap[TC_TABLE];                    // ... and its index r*S + s in the packed weights
     unsigned char ca[TC_MAX_CLASSES], cb[TC_MAX_CLASSES];
@@ -586,30 +587,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_convT4_kernel(const __grid_c
 // 16 + BN/4 KB for the same 128 x BN x 64 MACs: the L2 -> shared-memory fill that bounds the single-CTA kernel drops by
 // 25 % (BN = 128) to 33 % (BN = 256, which one CTA cannot hold with double-buffered accumulators).
 // One CTA per SM (both TMEM accumulator stages of BN = 256 take all 512 columns), deeper smem ring instead.
-template <int BN, int STAGES>
+// RESB: the weight slabs of ALL (tap, 64-channel chunk) steps stay resident in shared memory for the whole kernel (each CTA
+// of the pair holds its half: R*S*kchunks slabs of BN/2 rows x 128 B, at most 128 KB) and the ring stages carry only the
+// input boxes.  The narrow layers are bound by what an SM can ingest from L2: this removes the weight
+// bytes from every step — 16 KB instead of 24 KB (BN = 64) / 24 KB (BN = 128, already halved by the pair) per 128 x BN x 64 block.
+constexpr int TC_RES_BYTES = 128 * 1024;
+template <int BN, int STAGES, bool RESB = false>
 struct TcPairSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = (BN / 2) * TC_BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
+    static constexpr int RES_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = RES_OFF + (RESB ? TC_RES_BYTES : 0);
     static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 2 * 4 /*tile statistics*/;
-    static_assert((2 * STAGES + 5) * 8 <= 256, "barrier area");
+    static_assert((2 * STAGES + 6) * 8 <= 256, "barrier area");
+    static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RESB = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b,
                                                                      const __grid_constant__ TcParams p,
                                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                                      double* __restrict__ stats) {
-    using S = TcPairSmem<BN, STAGES>;
+    using S = TcPairSmem<BN, STAGES, RESB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* bres = smem + S::RES_OFF;              // RESB: resident weight slabs [R*S*kchunks][BN/2 rows][128 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* full = bars;                          // leader's: both CTAs' TMA bytes of a stage have landed
     uint64_t* empty = bars + STAGES;                // each CTA's: the MMAs that read this stage have completed
     uint64_t* tmem_full = bars + 2 * STAGES;        // [2] each CTA's: accumulator stage complete
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2] leader's: both CTAs' epilogues have drained the stage
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* bres_full = bars + 2 * STAGES + 5;    // leader's: both CTAs' resident slabs have landed
     float* sstat = reinterpret_cast<float*>(smem + S::BAR_OFF + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -626,6 +636,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
         prefetch_tmap(&map_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * TC_EPI_WARPS); }
+        mbar_init(bres_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.f;
@@ -651,6 +662,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own A box + own half of the weight slab, completion on the LEADER's barrier =====
         if (lane == 0) {
+            if (RESB) {
+                // all weight slabs of the layer, once: slab (filter tap, channel chunk) -> this CTA's BN/2 rows of it
+                const int nslab = p.res_taps * p.kchunks;
+                if (leader) mbar_expect_tx(bres_full, (uint32_t)(2 * nslab * S::B_BYTES));
+                const uint32_t rbar = cl_map(bres_full, 0);
+                for (int sl = 0; sl < nslab; ++sl)
+                    tma_load_2d_pair(bres + sl * S::B_BYTES, &map_b, rbar, (sl / p.kchunks) * p.IC + (sl % p.kchunks) * TC_BK, rank * (BN / 2));
+            }
             int it = 0;
             for (int idx = t_begin; idx < t_end; ++idx) {
                 VS_TCP_DECODE(idx)
@@ -665,7 +684,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
                     const uint32_t bar = cl_map(&full[s], 0);
                     tma_load_4d_pair(a_dst, &map_a, bar, kc * TC_BK, j0 * p.in_sw + p.dw[cls * p.ntaps + tap],
                                      i0 * p.in_sh + p.dh[cls * p.ntaps + tap], b0);
-                    tma_load_2d_pair(b_dst, &map_b, bar, p.wtap[cls * p.ntaps + tap] * p.IC + kc * TC_BK, n0 + rank * (BN / 2));
+                    if (!RESB)
+                        tma_load_2d_pair(b_dst, &map_b, bar, p.wtap[cls * p.ntaps + tap] * p.IC + kc * TC_BK, n0 + rank * (BN / 2));
                 }
             }
         }
@@ -673,9 +693,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
         // ===== MMA issuer: one thread of the leader CTA =====
         if (leader && lane == 0) {
             constexpr uint32_t idesc = idesc_bf16_f32_pair(BN);
+            if (RESB) mbar_wait(bres_full, 0);
             int it = 0, lt = 0;
             for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
                 const int acc = lt & 1;
+                const int cls_m = idx % p.classes;
                 mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -685,7 +707,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + S::A_BYTES;
+                    const int tap_m = kb / p.kchunks;
+                    const uint32_t b_addr = RESB ? smem_u32(bres + (p.wtap[cls_m * p.ntaps + tap_m] * p.kchunks + (kb - tap_m * p.kchunks)) * S::B_BYTES)
+                                                 : a_addr + S::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k)
                         umma_bf16_pair(tmem_d, kmajor_sw128_desc(a_addr + k * 32), kmajor_sw128_desc(b_addr + k * 32), idesc,
@@ -704,7 +728,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
         const int w = m % p.WT, h = (m / p.WT) % p.HT, n = m / (p.WT * p.HT);
         int lt = 0;
         int stat_key = -1;
-        double stat_acc[2 * BN / (32 * TC_EPI_WARPS)] = {};
+        constexpr int NE = (2 * BN + 32 * TC_EPI_WARPS - 1) / (32 * TC_EPI_WARPS);      // statistics entries per epilogue thread
+        double stat_acc[NE] = {};
         for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
             VS_TCP_DECODE(idx)
             const int acc = lt & 1;
@@ -764,19 +789,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
                 if (key != stat_key) {
                     if (stat_key >= 0) {
 #pragma unroll
-                        for (int e = 0; e < 2 * BN / (32 * TC_EPI_WARPS); ++e) {
+                        for (int e = 0; e < NE; ++e) {
                             const int ii = t + e * 32 * TC_EPI_WARPS, col = (stat_key % p.n_tiles) * BN + (ii >> 1);
-                            atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (ii & 1)], stat_acc[e]);
+                            if (ii < 2 * BN) atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (ii & 1)], stat_acc[e]);
                             stat_acc[e] = 0.0;
                         }
                     }
                     stat_key = key;
                 }
 #pragma unroll
-                for (int e = 0; e < 2 * BN / (32 * TC_EPI_WARPS); ++e) {
+                for (int e = 0; e < NE; ++e) {
                     const int ii = t + e * 32 * TC_EPI_WARPS;
-                    stat_acc[e] += (double)sstat[ii];
-                    sstat[ii] = 0.f;
+                    if (ii < 2 * BN) { stat_acc[e] += (double)sstat[ii]; sstat[ii] = 0.f; }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
             }
@@ -784,9 +808,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
         if (stats != nullptr && stat_key >= 0) {
             const int t = threadIdx.x - 64;
 #pragma unroll
-            for (int e = 0; e < 2 * BN / (32 * TC_EPI_WARPS); ++e) {
+            for (int e = 0; e < NE; ++e) {
                 const int ii = t + e * 32 * TC_EPI_WARPS, col = (stat_key % p.n_tiles) * BN + (ii >> 1);
-                atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (ii & 1)], stat_acc[e]);
+                if (ii < 2 * BN) atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (ii & 1)], stat_acc[e]);
             }
         }
     }
@@ -828,13 +852,13 @@ static bool pair_disabled() {
     return v == 1;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RESB = false>
 static int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const float* bias, void* out, int classes,
                           double* stats, cudaStream_t stream) {
-    using S = TcPairSmem<BN, STAGES>;
+    using S = TcPairSmem<BN, STAGES, RESB>;
     static DeviceOnce configured;
     if (!configured.flag()) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_pair_kernel<BN, STAGES, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return fail("tc_conv_pair_kernel smem attribute: %s", cudaGetErrorString(e));
         configured.flag() = true;
     }
@@ -855,7 +879,7 @@ static int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb, const Tc
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_pair_kernel<BN, STAGES>, ma, mb, q, bias, (__nv_bfloat16*)out, stats);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_pair_kernel<BN, STAGES, RESB>, ma, mb, q, bias, (__nv_bfloat16*)out, stats);
     if (e != cudaSuccess) return fail("tc_conv_pair_kernel launch: %s", cudaGetErrorString(e));
     return launched("tc_conv_pair_kernel");
 }
@@ -1055,10 +1079,22 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     static int pair128_min = -1;       // (tap, 64-channel chunk) steps from which 128-column layers use CTA pairs
     if (pair128_min < 0) { const char* e = getenv("VARSEP_PAIR128_MIN_STEPS"); pair128_min = e ? atoi(e) : 64; }
     const bool pair = OC % 128 == 0 && IC >= 64 && !p.partial && !pair_disabled() && (PBN == 256 || p.ntaps * p.kchunks >= pair128_min);
+    // narrow layers with little weight data: CTA pairs with ALL weight slabs resident in shared memory (see TcPairSmem)
+    static long long res_min_items = -1;      // work items (pixel tiles x parity classes) from which it pays: 8 per SM
+    // OPT-IN (VARSEP_RESIDENT_OC: bit 0 = 64-channel layers, bit 1 = 128-channel layers).  Measured on the mnist step
+    // (bf16, batch 128): 3.76 ms without, 3.80 ms with the 128-channel layers, 3.99 ms with the 64-channel layers resident —
+    // one pair tile per SM with 64-column MMAs loses more tensor-pipe rate than the removed weight traffic gives back.
+    static int res_oc = -1;
+    if (res_oc < 0) { const char* e = getenv("VARSEP_RESIDENT_OC"); res_oc = e ? atoi(e) : 0; }
+    if (res_min_items < 0) { const char* e = getenv("VARSEP_RESIDENT_MIN_ITEMS"); res_min_items = e ? atoll(e) : 8LL * num_sms(); }
+    const long long work_items = (long long)p.tiles_w * p.tiles_h * p.tiles_n * classes;
+    const bool resb = !pair_disabled() && ((OC == 64 && (res_oc & 1)) || (OC == 128 && (res_oc & 2))) && IC % 64 == 0 && !p.partial && !one_px &&
+                      (long long)g->R * g->S * p.kchunks * (OC / 2) * 128 <= TC_RES_BYTES && work_items >= res_min_items;
+    p.res_taps = g->R * g->S;
     {
         cuuint64_t dims[2] = {(cuuint64_t)g->R * g->S * IC, (cuuint64_t)OC};
         cuuint64_t strides[1] = {(cuuint64_t)g->R * g->S * IC * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)(pair ? PBN / 2 : BN)};
+        cuuint32_t box[2] = {64, (cuuint32_t)(resb ? OC / 2 : pair ? PBN / 2 : BN)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1089,6 +1125,13 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
         }
     }
     double* stp = fuse_stats ? stats : nullptr;
+    if (resb) {
+        int rc = OC == 64 ? launch_tc_pair<64, 5, true>(ma, mb, p, bias, out, classes, stp, stream)
+                          : launch_tc_pair<128, 5, true>(ma, mb, p, bias, out, classes, stp, stream);
+        if (rc) return rc;
+        if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
+        return rc;
+    }
     TcFusedTab ftab;
     if (tr && staged && BN == 64 && !pair && (stp == nullptr || p.act == VS_ACT_NONE) && !fused_classes_disabled() && build_fused_tab(p, classes, ftab)) {
         int rc = launch_tc_fused<3>(ma, mb, om, p, ftab, bias, stp, stream);

@@ -6,6 +6,7 @@ the two Et calls and the 1 + nt_pred + offset decoder calls are each ONE grouped
 (BatchNorm statistics per call), and all loss terms are reduced by fused kernels.
 """
 import contextlib
+import os
 
 import numpy as np
 import torch
@@ -156,6 +157,7 @@ class GraphedStep:
         self.nt_cond, self.nt_pred, self.offset = nt_cond, nt_pred, offset
         self.graph, self.overlap_encoders = bool(graph), overlap_encoders
         self.inputs, self.terms, self.graphs, self.pool = {}, {}, {}, None
+        self._capture_stream = None
         self.dtype = ops.compute_dtype()                         # the graphs bake the compute dtype in
 
     # ---- static buffers ------------------------------------------------------------------------------------
@@ -194,14 +196,19 @@ class GraphedStep:
                 return self.terms[key]
             g = self.graphs.get((key, t_random))
             if g is None:
-                # warm up on a side stream (lazy allocations, packed-weight caches), then capture
-                s = torch.cuda.Stream()
+                # warm up on a side stream (lazy allocations, packed-weight caches), then capture.  The step's own chain
+                # is captured on a HIGH-priority stream: the weight-gradient side stream (ops._OnWgradStream) and the
+                # content encoder's stream then fill the SMs the critical chain leaves free instead of competing with it
+                if self._capture_stream is None:
+                    prio = int(os.environ.get('VARSEP_STEP_STREAM_PRIORITY', '-1'))
+                    self._capture_stream = torch.cuda.Stream(priority=prio)
+                s = self._capture_stream
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
                     self._body(key, t_random)
                 torch.cuda.current_stream().wait_stream(s)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=self.pool):
+                with torch.cuda.graph(g, pool=self.pool, stream=s):
                     self._body(key, t_random)
                 if self.pool is None:
                     self.pool = g.pool()

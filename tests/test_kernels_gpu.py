@@ -177,6 +177,26 @@ def test_conv_forward_tensor_core(case, mode):
     close(o_tc.cpu(), o_simt.cpu(), dtype, 'tc vs simt', outliers=1e-4)
 
 
+def test_conv_forward_many_tiles():
+    """More than 8 pixel tiles per SM (several work items per persistent CTA): the decoder's 128 -> 64 transposed
+    layer, 160 images, two BatchNorm groups."""
+    test_conv_forward_tensor_core((160, 32, 32, 64, 128, 4, 2, 1, 2), L.TRANSPOSED)
+
+
+@pytest.mark.timeout(1200)
+def test_conv_forward_resident_weights_all_geometries():
+    """Every tensor-core case again in a fresh process with the opt-in resident-weight CTA-pair kernel switched on for
+    all eligible layers (64 / 128 output channels, whole 64-channel chunks, weight slabs <= 128 KB), whatever their size."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, VARSEP_RESIDENT_OC='3', VARSEP_RESIDENT_MIN_ITEMS='1')
+    r = subprocess.run([sys.executable, '-m', 'pytest', __file__, '-x', '-q', '-m', 'gpu', '-k', 'test_conv_forward_tensor_core or test_conv_forward_many_tiles',
+                        '-p', 'no:cacheprovider'], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize('dt', ['f32', 'bf16'])
 @pytest.mark.parametrize('case', CONV_CASES + TC_CASES)
 def test_conv_wgrad_and_pack(case, dt):
