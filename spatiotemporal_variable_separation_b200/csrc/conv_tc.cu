@@ -597,7 +597,9 @@ struct TcPairSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = (BN / 2) * TC_BK * 2;
     static constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
     static constexpr int RES_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = RES_OFF + (RESB ? TC_RES_BYTES : 0);
+    static constexpr int OUT_OFF = RES_OFF + (RESB ? TC_RES_BYTES : 0);      // RESB: one staged bf16 output tile (TMA store)
+    static constexpr int OUT_BYTES = RESB ? (BN / 64) * TC_BM * 128 : 0;
+    static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
     static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 2 * 4 /*tile statistics*/;
     static_assert((2 * STAGES + 6) * 8 <= 256, "barrier area");
     static_assert(TOTAL <= 227 * 1024, "shared memory");
@@ -606,6 +608,7 @@ struct TcPairSmem {
 template <int BN, int STAGES, bool RESB = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b,
+                                                                     const __grid_constant__ TcOutMaps omaps,
                                                                      const __grid_constant__ TcParams p,
                                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                                      double* __restrict__ stats) {
@@ -613,6 +616,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* bres = smem + S::RES_OFF;              // RESB: resident weight slabs [R*S*kchunks][BN/2 rows][128 B]
+    uint8_t* obuf = smem + S::OUT_OFF;              // RESB: BN/64 half-tiles of [128 pixels][128 bytes]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* full = bars;                          // leader's: both CTAs' TMA bytes of a stage have landed
     uint64_t* empty = bars + STAGES;                // each CTA's: the MMAs that read this stage have completed
@@ -728,6 +732,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
         const int w = m % p.WT, h = (m / p.WT) % p.HT, n = m / (p.WT * p.HT);
         int lt = 0;
         int stat_key = -1;
+        if constexpr (RESB) {
+            // staged epilogue (as tc_conv_kernel<.., TS, SS>): the tile goes to shared memory as bf16, one thread writes it
+            // with TMA stores, and the BatchNorm sums are read back from the staged tile.  One staging tile: the previous
+            // item's store must have read it (and everybody's statistics reads be done) before it is refilled.
+            constexpr int HALVES = BN / 64;
+            const int t = threadIdx.x - 64, cp = t & 31, rg = t >> 5;
+            float ss[HALVES][4] = {};
+            auto ss_flush = [&](int key) {
+#pragma unroll
+                for (int hf = 0; hf < HALVES; ++hf) {
+                    const int c = hf * 64 + 2 * cp;
+                    atomicAdd(&sstat[c * 2], ss[hf][0]);       atomicAdd(&sstat[c * 2 + 1], ss[hf][1]);
+                    atomicAdd(&sstat[(c + 1) * 2], ss[hf][2]); atomicAdd(&sstat[(c + 1) * 2 + 1], ss[hf][3]);
+                    ss[hf][0] = ss[hf][1] = ss[hf][2] = ss[hf][3] = 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+                if (t < 2 * BN) {
+                    atomicAdd(&stats[((long long)key * p.OC + (t >> 1)) * 2 + (t & 1)], (double)sstat[t]);      // OC == BN
+                    sstat[t] = 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            };
+            for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
+                VS_TCP_DECODE(idx)
+                const int acc = lt & 1;
+                const int i = i0 + h, j = j0 + w, nn = b0 + n;
+                const bool ok = i < p.OHc && j < p.OWc && nn < p.N;
+                const bool full_tile = i0 + p.HT <= p.OHc && j0 + p.WT <= p.OWc && b0 + p.NT <= p.N;
+                if (stats != nullptr && b0 < p.N) {
+                    const int key = b0 / p.n_per_group;
+                    if (key != stat_key) {
+                        if (stat_key >= 0) ss_flush(stat_key);
+                        stat_key = key;
+                    }
+                }
+                mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+                tc_fence_after();
+                if (threadIdx.x == 64) tma_store_wait_read();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+#pragma unroll 1
+                for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                    float xs[32];
+                    if (p.has_bias) {
+                        const float bias_l = __ldg(bias + n0 + c0 + lane);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]);
+                    }
+                    if (!full_tile && !ok) {          // rows beyond the tensor edge: clipped by the TMA store, must not count
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) xs[c] = 0.f;
+                    }
+                    stage_row32(obuf + (c0 >> 6) * (TC_BM * 128), m, c0 & 63, xs, p.act);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(cl_map(&tmem_empty[acc], 0));
+                fence_proxy_async();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+                if (threadIdx.x == 64 && b0 < p.N) {
+#pragma unroll
+                    for (int hf = 0; hf < HALVES; ++hf) tma_store_4d(&omaps.m[cls], obuf + hf * (TC_BM * 128), n0 + hf * 64, j0, i0, b0);
+                    tma_store_commit();
+                }
+                if (stats != nullptr && b0 < p.N) {
+#pragma unroll
+                    for (int hf = 0; hf < HALVES; ++hf) {
+                        const uint8_t* tile = obuf + hf * (TC_BM * 128) + (cp & 3) * 4;
+#pragma unroll
+                        for (int rr = 0; rr < TC_BM / TC_EPI_WARPS; ++rr) {
+                            const int row = rg * (TC_BM / TC_EPI_WARPS) + rr;
+                            const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + row * 128 + (((cp >> 2) ^ (row & 7)) << 4));
+                            const float a = __uint_as_float(v << 16), b = __uint_as_float(v & 0xffff0000u);
+                            ss[hf][0] += a; ss[hf][1] = fmaf(a, a, ss[hf][1]);
+                            ss[hf][2] += b; ss[hf][3] = fmaf(b, b, ss[hf][3]);
+                        }
+                    }
+                }
+            }
+            if (stats != nullptr && stat_key >= 0) ss_flush(stat_key);
+            if (threadIdx.x == 64) tma_store_wait_all();
+        } else {
         constexpr int NE = (2 * BN + 32 * TC_EPI_WARPS - 1) / (32 * TC_EPI_WARPS);      // statistics entries per epilogue thread
         double stat_acc[NE] = {};
         for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
@@ -813,6 +903,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
                 if (ii < 2 * BN) atomicAdd(&stats[((long long)(stat_key / p.n_tiles) * p.OC + col) * 2 + (ii & 1)], stat_acc[e]);
             }
         }
+        }
     }
     // the leader's MMAs read the peer's shared memory and write its tensor memory: nobody leaves before everybody is done
     tc_fence_before();
@@ -822,6 +913,270 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
         tmem_dealloc_pair<2 * BN>(tmem_base);
     }
 #undef VS_TCP_DECODE
+}
+
+// ------------------------------------------------------------------------------------------ shifted windows
+// The 64/128-channel k4 s2 p1 layers at 16x16 / 32x32 (decoder 128->64 and its input gradient, encoder 64->128 and its
+// input gradient) are bound by what the tensor core's operands cost on the way in: per 128 x 64 x 64 block the per-class
+// kernels above stage 16 KB of input + 8 KB of weights from L2, 125-190 B/clk/SM at the tensor pipe's rate, and the L2
+// sits at 62 % of its throughput (profiles/r02_ncu_per_launch_tc_conv.txt).  This kernel removes most of those bytes:
+//   * CTA pairs (cta_group::2, M = 256) with ALL weight slabs resident in shared memory (each CTA its half, 128 KB),
+//   * a pixel tile of 16 rows x 8 columns of ONE image, so that a pixel row of the tile is exactly one 1024-byte swizzle
+//     atom: an input box of 17-18 rows is loaded once and the taps that differ only by a row shift read it through
+//     descriptors offset by 1024 bytes per row (no re-load),
+//   * transposed mode: the four output-parity classes of the tile are accumulated together (4 x 64 TMEM columns) and a
+//     shift shared by 2 or 4 classes is ONE N = 128 / 256 instruction (schedule of the fused-class kernel above).
+// Input bytes per work item: 3 column shifts x 18 KB per 64-channel chunk (transposed) or 8 x 17 KB (direct, stride 2:
+// two row parities x four filter columns) instead of 16 x 16 KB, no weight bytes: 26-33 B/clk/SM at full tensor rate.
+// The MMA schedule comes from the host as a flat table (box -> groups of {row shift, resident offset, descriptor,
+// accumulator column}); the issuer does four loads from the constant bank per group of four MMAs.
+constexpr int TCS_MAX_BOX = 8, TCS_MAX_GRP = 24, TCS_PIECES = 32, TCS_HT = 16, TCS_WT = 8, TCS_ACC = 256;
+struct TcShiftTab {
+    int nbox, ngrp, nblk, hb;                  // boxes / MMA groups per work item, 64-column accumulator blocks, rows per box
+    int npieces;                               // resident 32-row weight pieces per CTA (4 KB each)
+    short box_dx[TCS_MAX_BOX], box_dy[TCS_MAX_BOX], box_c0[TCS_MAX_BOX];     // input offset of the box, first channel
+    unsigned char box_g0[TCS_MAX_BOX + 1];     // groups [g0[b], g0[b+1]) read box b
+    // per group: x = offset of its first pixel row inside the box (1024 bytes x row shift), y = offset of its weight rows in
+    // the resident area, both in 16-byte descriptor units; z = instruction descriptor (N = 64 x merged classes, or OC);
+    // w = first accumulator column
+    uint4 grp[TCS_MAX_GRP];
+    int piece_x[2][TCS_PIECES], piece_y[2][TCS_PIECES];      // [CTA rank][piece]: coordinates in the packed weights
+    unsigned char blk_cls[4], blk_ch0[4];      // accumulator block -> output map (parity class), first output channel
+};
+
+template <int STAGES>
+struct TcShiftSmem {
+    static constexpr int STAGE_BYTES = 18 * 1024;
+    static constexpr int RES_OFF = STAGES * STAGE_BYTES;
+    static constexpr int OUT_OFF = RES_OFF + TC_RES_BYTES;
+    static constexpr int BAR_OFF = OUT_OFF + 2 * TC_BM * 128;      // two staged 128-pixel x 64-channel bf16 tiles
+    static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/ + 128 * 2 * 4 /*column sums*/;
+    static_assert((2 * STAGES + 6) * 8 <= 256, "barrier area");
+    static_assert(TOTAL <= 227 * 1024, "shared memory");
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_shift_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                      const __grid_constant__ CUtensorMap map_b,
+                                                                      const __grid_constant__ TcOutMaps omaps,
+                                                                      const __grid_constant__ TcParams p,
+                                                                      const __grid_constant__ TcShiftTab tab,
+                                                                      const float* __restrict__ bias, double* __restrict__ stats) {
+    using S = TcShiftSmem<STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* bres = smem + S::RES_OFF;
+    uint8_t* obuf = smem + S::OUT_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* full = bars;                          // leader's: both CTAs' box of a stage has landed
+    uint64_t* empty = bars + STAGES;                // each CTA's: the MMAs that read this stage have completed
+    uint64_t* tmem_full = bars + 2 * STAGES;        // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2] leader's
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* bres_full = bars + 2 * STAGES + 5;    // leader's: both CTAs' resident weights have landed
+    float* sstat = reinterpret_cast<float*>(smem + S::BAR_OFF + 256);      // [OC][2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cl_rank();
+    const bool leader = rank == 0;
+    const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+    const int t_begin = (int)((long long)pair * p.total_tiles / npairs);
+    const int t_end = (int)((long long)(pair + 1) * p.total_tiles / npairs);
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // accumulator hand-back: one arrival per epilogue group that owns blocks, of both CTAs
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], tab.nblk > 1 ? 4 : 2); }
+        mbar_init(bres_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * 128; i += blockDim.x) sstat[i] = 0.f;
+    __syncthreads();
+    if (warp == 1) tmem_alloc_pair<2 * TCS_ACC>(tmem_slot);
+    tc_fence_before();
+    cl_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item of the pair -> this CTA's tile (16 rows x 8 columns of one image's class grid); an odd tile count leaves
+    // the last rank-1 tile beyond the batch: its boxes are zero-filled, its stores and statistics skipped
+#define VS_TCS_DECODE(idx)                                                  \
+    int t_ = (idx) * 2 + rank;                                              \
+    const int j0 = (t_ % p.tiles_w) * TCS_WT; t_ /= p.tiles_w;              \
+    const int i0 = (t_ % p.tiles_h) * TCS_HT;                               \
+    const int nn = t_ / p.tiles_h;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): the resident weight pieces once, then one input box per stage =====
+        if (lane == 0) {
+            if (leader) mbar_expect_tx(bres_full, (uint32_t)(2 * tab.npieces * 4096));
+            const uint32_t rbar = cl_map(bres_full, 0);
+            for (int i = 0; i < tab.npieces; ++i)
+                tma_load_2d_pair(bres + i * 4096, &map_b, rbar, tab.piece_x[rank][i], tab.piece_y[rank][i]);
+            int it = 0;
+            for (int idx = t_begin; idx < t_end; ++idx) {
+                // the ring holds three boxes (~54 KB in flight per SM, too little to cover DRAM latency at full bandwidth):
+                // the NEXT item's boxes are requested into L2 now, one whole item ahead of their shared-memory loads
+                if (idx + 1 < t_end) {
+                    int t2 = (idx + 1) * 2 + rank;
+                    const int pj0 = (t2 % p.tiles_w) * TCS_WT; t2 /= p.tiles_w;
+                    const int pi0 = (t2 % p.tiles_h) * TCS_HT, pn = t2 / p.tiles_h;
+                    if (pn < p.N)
+                        for (int b = 0; b < tab.nbox; ++b)
+                            tma_prefetch_4d(&map_a, tab.box_c0[b], pj0 * p.in_sw + tab.box_dx[b], pi0 * p.in_sh + tab.box_dy[b], pn);
+                }
+                VS_TCS_DECODE(idx)
+                for (int b = 0; b < tab.nbox; ++b, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * tab.hb * 1024));
+                    tma_load_4d_pair(smem + s * S::STAGE_BYTES, &map_a, cl_map(&full[s], 0), tab.box_c0[b],
+                                     j0 * p.in_sw + tab.box_dx[b], i0 * p.in_sh + tab.box_dy[b], nn);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader CTA's warp 1, converged; one elected lane issues =====
+        if (leader) {
+            const bool elected = elect_one();
+            mbar_wait(bres_full, 0);
+            const uint32_t b_lo0 = kmajor_sw128_desc_lo(smem_u32(bres));
+            int s = 0, lt = 0;
+            uint32_t ph = 0;
+            for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TCS_ACC);
+                for (int b = 0; b < tab.nbox; ++b) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_lo0 = kmajor_sw128_desc_lo(smem_u32(smem + s * S::STAGE_BYTES));
+                    const int g1 = tab.box_g0[b + 1];
+                    for (int g = tab.box_g0[b]; g < g1; ++g) {
+                        const uint4 e = tab.grp[g];
+                        const uint32_t a_lo = a_lo0 + e.x, b_lo = b_lo0 + e.y, d = tmem_d + e.w;
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k) {      // the first group of an item covers every accumulator column
+                            const uint64_t ad = kmajor_sw128_desc_from_lo(a_lo + 2 * k), bd = kmajor_sw128_desc_from_lo(b_lo + 2 * k);
+                            const uint32_t accum = (g | k) != 0 ? 1u : 0u;
+                            if (elected) umma_bf16_pair(d, ad, bd, e.z, accum);
+                        }
+                    }
+                    if (elected) umma_commit_pair(&empty[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                if (elected) umma_commit_pair(&tmem_full[acc]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 pixels.  Two groups of four warps (one warp per TMEM lane quarter), each with
+        // its own staging tile, named barrier and store-issuing thread; group gi takes the 64-column accumulator blocks
+        // gi, gi + 2: TMEM load -> bf16 tile in shared memory -> one TMA store, sums read back from the staged tile.
+        // The two groups' barrier / TMEM-load / store latencies overlap =====
+        const int q = warp & 3;
+        const int gi = (warp - 2) >> 2;
+        const int m = q * 32 + lane;                  // pixel (m / 8, m % 8) of the tile
+        const int T = threadIdx.x - 64, t = T & 127, cp = t & 31, rg = t >> 5;
+        uint8_t* tile_w = obuf + gi * (TC_BM * 128);
+        int lt = 0;
+        int stat_key = -1;
+        float ss0[4] = {0.f, 0.f, 0.f, 0.f}, ss1[4] = {0.f, 0.f, 0.f, 0.f};      // channels 2cp, 2cp+1 of [0,64) / [64,128)
+        auto group_sync = [&]() {
+            if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else         asm volatile("bar.sync 2, 128;" ::: "memory");
+        };
+        auto ss_flush = [&](int key) {
+            atomicAdd(&sstat[(2 * cp) * 2], ss0[0]);     atomicAdd(&sstat[(2 * cp) * 2 + 1], ss0[1]);
+            atomicAdd(&sstat[(2 * cp + 1) * 2], ss0[2]); atomicAdd(&sstat[(2 * cp + 1) * 2 + 1], ss0[3]);
+            if (p.OC > 64) {
+                atomicAdd(&sstat[(64 + 2 * cp) * 2], ss1[0]);     atomicAdd(&sstat[(64 + 2 * cp) * 2 + 1], ss1[1]);
+                atomicAdd(&sstat[(64 + 2 * cp + 1) * 2], ss1[2]); atomicAdd(&sstat[(64 + 2 * cp + 1) * 2 + 1], ss1[3]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ss0[e] = ss1[e] = 0.f;
+            asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            if (T < 2 * p.OC) {
+                atomicAdd(&stats[((long long)key * p.OC + (T >> 1)) * 2 + (T & 1)], (double)sstat[T]);
+                sstat[T] = 0.f;
+            }
+            asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        };
+        for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
+            VS_TCS_DECODE(idx)
+            const int acc = lt & 1;
+            const bool live = nn < p.N;
+            if (stats != nullptr && live) {
+                const int key = nn / p.n_per_group;
+                if (key != stat_key) {                       // uniform over the CTA's epilogue warps
+                    if (stat_key >= 0) ss_flush(stat_key);
+                    stat_key = key;
+                }
+            }
+            mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int blk = gi; blk < tab.nblk; blk += 2) {
+                const int ch0 = tab.blk_ch0[blk];
+                // the group's previous store has read the staging tile, and the group's statistics reads of it are done
+                if (t == 0) tma_store_wait_read();
+                group_sync();
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TCS_ACC + blk * 64 + half * 32), r);
+                    float xs[32];
+                    if (p.has_bias) {
+                        const float bias_l = __ldg(bias + ch0 + half * 32 + lane);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]) + __shfl_sync(0xffffffffu, bias_l, c);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) xs[c] = __uint_as_float(r[c]);
+                    }
+                    stage_row32(tile_w, m, half * 32, xs, p.act);
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                group_sync();
+                if (t == 0) {
+                    if (live) {
+                        tma_store_4d(&omaps.m[tab.blk_cls[blk]], tile_w, ch0, j0, i0, nn);
+                        tma_store_commit();
+                    }
+                    // the group's warps have read its last block of the accumulator stage (barrier above): one arrival per
+                    // group on the leader's barrier; no memory ordering needed, the tcgen05 fences order the TMEM accesses
+                    if (blk + 2 >= tab.nblk) { tc_fence_after(); mbar_arrive_cluster_relaxed(cl_map(&tmem_empty[acc], 0)); }
+                }
+                if (stats != nullptr && live) {
+                    const uint8_t* tile = tile_w + (cp & 3) * 4;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+                    for (int rr = 0; rr < TC_BM / 4; ++rr) {
+                        const int row = rg * (TC_BM / 4) + rr;
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + row * 128 + (((cp >> 2) ^ (row & 7)) << 4));
+                        const float a = __uint_as_float(v << 16), b = __uint_as_float(v & 0xffff0000u);
+                        a0 += a; a1 = fmaf(a, a, a1);
+                        a2 += b; a3 = fmaf(b, b, a3);
+                    }
+                    if (ch0 == 0) { ss0[0] += a0; ss0[1] += a1; ss0[2] += a2; ss0[3] += a3; }
+                    else          { ss1[0] += a0; ss1[1] += a1; ss1[2] += a2; ss1[3] += a3; }
+                }
+            }
+        }
+        if (stats != nullptr && stat_key >= 0) ss_flush(stat_key);
+        if (t == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    cl_sync();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair<2 * TCS_ACC>(tmem_base);
+    }
+#undef VS_TCS_DECODE
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -846,6 +1201,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMa
     return launched("tc_conv_kernel");
 }
 
+static bool staged_epilogue_disabled();
 static bool pair_disabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("VARSEP_DISABLE_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -853,8 +1209,8 @@ static bool pair_disabled() {
 }
 
 template <int BN, int STAGES, bool RESB = false>
-static int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const float* bias, void* out, int classes,
-                          double* stats, cudaStream_t stream) {
+static int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb, const TcOutMaps& om, const TcParams& p, const float* bias, void* out,
+                          int classes, double* stats, cudaStream_t stream) {
     using S = TcPairSmem<BN, STAGES, RESB>;
     static DeviceOnce configured;
     if (!configured.flag()) {
@@ -879,7 +1235,7 @@ static int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb, const Tc
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_pair_kernel<BN, STAGES, RESB>, ma, mb, q, bias, (__nv_bfloat16*)out, stats);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_pair_kernel<BN, STAGES, RESB>, ma, mb, om, q, bias, (__nv_bfloat16*)out, stats);
     if (e != cudaSuccess) return fail("tc_conv_pair_kernel launch: %s", cudaGetErrorString(e));
     return launched("tc_conv_pair_kernel");
 }
@@ -985,6 +1341,154 @@ static bool staged_epilogue_disabled() {
     return v == 1;
 }
 
+// VARSEP_DISABLE_SHIFT=1 switches the shifted-window kernel off; VARSEP_SHIFT_MIN_ITEMS overrides the number of pair work
+// items from which it is used (default: four per CTA pair, below that the 128 KB weight preload per CTA does not pay)
+static bool shift_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VARSEP_DISABLE_SHIFT"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+// k4 s2 p1 layers with 64 / 128 output channels on 16-row x 8-column tiles (see tc_conv_shift_kernel).
+// returns 0 = launched, -1 = not this kernel's geometry, >0 = error
+static int conv_forward_shift(EncodeTiledFn enc, const vs_conv_geom* g, bool tr, const TcParams& p0, int classes, const void* in,
+                              const void* wp, const float* bias, void* out, double* stats, cudaStream_t stream, int IH, int IW, int IC,
+                              int OH, int OW, int OC) {
+    constexpr int STAGES = 3;
+    using S = TcShiftSmem<STAGES>;
+    if (shift_disabled() || pair_disabled() || staged_epilogue_disabled()) return -1;
+    if (g->R != 4 || g->S != 4 || g->stride != 2 || g->pad != 1) return -1;
+    if ((OC != 64 && OC != 128) || IC % 64 != 0 || p0.partial) return -1;
+    if (p0.OHc % TCS_HT != 0 || p0.OWc % TCS_WT != 0) return -1;
+    if (stats != nullptr && p0.act != VS_ACT_NONE) return -1;          // the sums are taken from the staged (activated) tile
+    const int kchunks = IC / 64;
+    if (16 * kchunks * (OC / 64) > TCS_PIECES) return -1;              // resident weights: 128 KB per CTA
+    TcParams p = p0;
+    p.WT = TCS_WT; p.HT = TCS_HT; p.NT = 1;
+    p.tiles_w = p.OWc / TCS_WT; p.tiles_h = p.OHc / TCS_HT; p.tiles_n = g->N;
+    p.classes = classes; p.n_tiles = 1;
+    const long long ptiles = (long long)p.tiles_w * p.tiles_h * g->N;
+    p.total_tiles = (int)((ptiles + 1) / 2);
+    int pairs = num_sms() / 2;
+    static long long min_items = -1;
+    if (min_items < 0) { const char* e = getenv("VARSEP_SHIFT_MIN_ITEMS"); min_items = e ? atoll(e) : -2; }
+    if (p.total_tiles < (min_items >= 0 ? min_items : 4LL * pairs)) return -1;
+    if (pairs > p.total_tiles) pairs = p.total_tiles;
+    p.n_per_group = g->N / g->groups;
+
+    TcShiftTab tab;
+    memset(&tab, 0, sizeof(tab));
+    int ng = 0, nb = 0, pieces = 0;
+    if (tr) {
+        TcFusedTab ft;
+        if (OC != 64 || 3 * kchunks > TCS_MAX_BOX || !build_fused_tab(p, classes, ft)) return -1;
+        tab.hb = TCS_HT + 2;
+        static const int dw_order[3] = {0, 1, -1};          // the centre shift (all four classes, N = 256) comes first
+        for (int wi = 0; wi < 3; ++wi)
+            for (int kc = 0; kc < kchunks; ++kc, ++nb) {
+                tab.box_dx[nb] = (short)dw_order[wi]; tab.box_dy[nb] = -1; tab.box_c0[nb] = (short)(kc * 64);
+                tab.box_g0[nb] = (unsigned char)ng;
+                for (int o = 0; o < ft.nshift; ++o) {
+                    if (ft.dw[o] != dw_order[wi]) continue;
+                    for (int gi = 0; gi < ft.ngrp[o]; ++gi, ++ng) {
+                        if (ng >= TCS_MAX_GRP) return -1;
+                        const int n = ft.grp_n[o][gi];
+                        tab.grp[ng] = make_uint4((unsigned)((ft.dh[o] + 1) * 1024 / 16), (unsigned)(pieces * 4096 / 16),
+                                                 idesc_bf16_f32_pair(64 * n), (unsigned)(ft.grp_pos[o][gi] * 64));
+                        // the n class slabs side by side are the N = 64n weight rows of the instruction; CTA r stages rows
+                        // [32n r, 32n (r+1)) of them as 32-row pieces
+                        for (int r = 0; r < 2; ++r)
+                            for (int i = 0; i < n; ++i) {
+                                const int pi = r * n + i, slab = ft.grp_slab[o][gi] + pi / 2;
+                                tab.piece_x[r][pieces + i] = ft.slab_wtap[o][slab] * IC + kc * 64;
+                                tab.piece_y[r][pieces + i] = (pi % 2) * 32;
+                            }
+                        pieces += n;
+                    }
+                }
+            }
+        tab.nblk = 4;
+        for (int b = 0; b < 4; ++b) { tab.blk_cls[b] = ft.pos_cls[b]; tab.blk_ch0[b] = 0; }
+    } else {
+        if (classes != 1 || kchunks != 1) return -1;
+        tab.hb = TCS_HT + 1;
+        for (int dyb = -1; dyb <= 0; ++dyb)                 // odd input rows (filter rows 0, 2), even input rows (1, 3)
+            for (int sx = 0; sx < 4; ++sx, ++nb) {
+                tab.box_dx[nb] = (short)(sx - 1); tab.box_dy[nb] = (short)dyb; tab.box_c0[nb] = 0;
+                tab.box_g0[nb] = (unsigned char)ng;
+                for (int r = dyb + 1; r < 4; r += 2, ++ng) {
+                    tab.grp[ng] = make_uint4((unsigned)(((r - 1 - dyb) / 2) * 1024 / 16), (unsigned)(pieces * 4096 / 16),
+                                             idesc_bf16_f32_pair(OC), 0u);
+                    for (int rk = 0; rk < 2; ++rk)
+                        for (int i = 0; i < OC / 64; ++i) {
+                            tab.piece_x[rk][pieces + i] = (r * 4 + sx) * IC;
+                            tab.piece_y[rk][pieces + i] = rk * (OC / 2) + 32 * i;
+                        }
+                    pieces += OC / 64;
+                }
+            }
+        tab.nblk = OC / 64;
+        for (int b = 0; b < tab.nblk; ++b) { tab.blk_cls[b] = 0; tab.blk_ch0[b] = (unsigned char)(64 * b); }
+    }
+    tab.nbox = nb; tab.ngrp = ng; tab.npieces = pieces; tab.box_g0[nb] = (unsigned char)ng;
+    if (pieces > TCS_PIECES || nb > TCS_MAX_BOX) return -1;
+
+    CUtensorMap ma, mb;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)IC, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)IC * 2, (cuuint64_t)IC * IW * 2, (cuuint64_t)IC * IW * IH * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(TCS_WT * p.in_sw), (cuuint32_t)(tab.hb * p.in_sh), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)p.in_sw, (cuuint32_t)p.in_sh, 1};
+        CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(shift A) failed: %d", (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)g->R * g->S * IC, (cuuint64_t)OC};
+        cuuint64_t strides[1] = {(cuuint64_t)g->R * g->S * IC * 2};
+        cuuint32_t box[2] = {64, 32};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(shift B) failed: %d", (int)r);
+    }
+    TcOutMaps om;
+    memset(&om, 0, sizeof(om));
+    const int ost = p.ost;
+    for (int cls = 0; cls < classes; ++cls) {
+        const char* base = reinterpret_cast<const char*>(out) + ((size_t)p.ca[cls] * OW + p.cb[cls]) * OC * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)OC, (cuuint64_t)p.OWc, (cuuint64_t)p.OHc, (cuuint64_t)g->N};
+        cuuint64_t strides[3] = {(cuuint64_t)ost * OC * 2, (cuuint64_t)ost * OW * OC * 2, (cuuint64_t)OH * OW * OC * 2};
+        cuuint32_t box[4] = {64, TCS_WT, TCS_HT, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&om.m[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(shift out) failed: %d", (int)r);
+    }
+    static DeviceOnce configured;
+    if (!configured.flag()) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_shift_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return fail("tc_conv_shift_kernel smem attribute: %s", cudaGetErrorString(e));
+        configured.flag() = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_shift_kernel<STAGES>, ma, mb, om, p, tab, bias, stats);
+    if (e != cudaSuccess) return fail("tc_conv_shift_kernel launch: %s", cudaGetErrorString(e));
+    return launched("tc_conv_shift_kernel");
+}
+
 int conv_forward_tc_eligible(const vs_conv_geom* g, int mode) {
     if (g->dtype != VS_BF16 || (g->flags & VS_FLAG_FORCE_SIMT) || tc_disabled()) return 0;
     const bool tr = mode == VS_CONV_TRANSPOSED;
@@ -1072,6 +1576,10 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     }
     const int BN = (OC % 128 == 0 || OC >= 512) ? 128 : 64;
     p.partial = (OC % 8 != 0) || (reinterpret_cast<uintptr_t>(out) & 15) ? 1 : 0;      // rows not 16-byte aligned
+    if (!one_px) {
+        const int rc = conv_forward_shift(enc, g, tr, p, classes, in, wp, bias, out, stats, stream, IH, IW, IC, OH, OW, OC);
+        if (rc >= 0) return rc;
+    }
     // wide layers: CTA pairs (cta_group::2), BN = 256 when OC allows.  A property of the layer, never of the batch size.
     // (measured: 256-column pair tiles reach 1.2-1.4 PFLOP/s on the decoder layers; 128-column pair tiles lose to two
     // single CTAs per SM except for long reduction loops, where the deeper ring of the pair kernel hides the latency)
@@ -1089,6 +1597,7 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     if (res_min_items < 0) { const char* e = getenv("VARSEP_RESIDENT_MIN_ITEMS"); res_min_items = e ? atoll(e) : 8LL * num_sms(); }
     const long long work_items = (long long)p.tiles_w * p.tiles_h * p.tiles_n * classes;
     const bool resb = !pair_disabled() && ((OC == 64 && (res_oc & 1)) || (OC == 128 && (res_oc & 2))) && IC % 64 == 0 && !p.partial && !one_px &&
+                      classes <= TC_MAX_OUT_MAPS && !staged_epilogue_disabled() && (stats == nullptr || p.act == VS_ACT_NONE) &&
                       (long long)g->R * g->S * p.kchunks * (OC / 2) * 128 <= TC_RES_BYTES && work_items >= res_min_items;
     p.res_taps = g->R * g->S;
     {
@@ -1110,7 +1619,7 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     memset(&om, 0, sizeof(om));
     // (BN = 128: only the statistics-carrying forward launches, see below; one CTA per SM with a five-stage ring)
     const bool staged128 = BN == 128 && OC % 128 == 0 && fuse_stats && p.act == VS_ACT_NONE && !staged_stats_disabled();
-    const bool staged = (BN == 64 || staged128) && !p.partial && classes <= TC_MAX_OUT_MAPS && !staged_epilogue_disabled();
+    const bool staged = (resb || BN == 64 || staged128) && !p.partial && classes <= TC_MAX_OUT_MAPS && !staged_epilogue_disabled();
     if (staged) {
         for (int cls = 0; cls < classes; ++cls) {
             const char* base = reinterpret_cast<const char*>(out) + ((size_t)p.ca[cls] * OW + p.cb[cls]) * OC * 2;
@@ -1126,8 +1635,8 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
     }
     double* stp = fuse_stats ? stats : nullptr;
     if (resb) {
-        int rc = OC == 64 ? launch_tc_pair<64, 5, true>(ma, mb, p, bias, out, classes, stp, stream)
-                          : launch_tc_pair<128, 5, true>(ma, mb, p, bias, out, classes, stp, stream);
+        int rc = OC == 64 ? launch_tc_pair<64, 5, true>(ma, mb, om, p, bias, out, classes, stp, stream)
+                          : launch_tc_pair<128, 4, true>(ma, mb, om, p, bias, out, classes, stp, stream);
         if (rc) return rc;
         if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
         return rc;
@@ -1139,8 +1648,8 @@ int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void*
         if (stats != nullptr && !fuse_stats) return stats_of_output(g, g->dtype, out, (long long)g->N * OH * OW, OC, stats, stream);
         return rc;
     }
-    int rc = pair ? (PBN == 256 ? launch_tc_pair<256, 6>(ma, mb, p, bias, out, classes, stp, stream)
-                                : launch_tc_pair<128, 8>(ma, mb, p, bias, out, classes, stp, stream))
+    int rc = pair ? (PBN == 256 ? launch_tc_pair<256, 6>(ma, mb, om, p, bias, out, classes, stp, stream)
+                                : launch_tc_pair<128, 8>(ma, mb, om, p, bias, out, classes, stp, stream))
              : BN == 128 ? (staged ? launch_tc<128, 5, true, true>(ma, mb, om, p, bias, out, classes, stp, stream)
                                    : launch_tc<128, 3, false>(ma, mb, om, p, bias, out, classes, stp, stream))
              : staged && stp != nullptr && p.act == VS_ACT_NONE && !staged_stats_disabled()

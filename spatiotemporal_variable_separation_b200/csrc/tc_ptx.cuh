@@ -34,6 +34,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// bring a box into L2 only (no shared-memory destination, no completion): run-ahead for boxes whose ring stage is not free yet
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -94,6 +99,17 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// the same descriptor from its low word ((address >> 4) | 1 << 16): offsets inside a tile are added to the low word in
+// 16-byte units (shared-memory addresses stay below 2^18, so the 14-bit address field never carries)
+__device__ __forceinline__ uint32_t kmajor_sw128_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ uint64_t kmajor_sw128_desc_from_lo(uint32_t lo) { return ((uint64_t)0x40004040u << 32) | lo; }
+// one lane of a converged warp (the MMA issuer keeps the whole warp in its loop so that addresses and descriptors are
+// computed on the uniform datapath; only the tcgen05 instructions themselves are predicated on the elected lane)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int bn) {
@@ -172,6 +188,11 @@ __device__ __forceinline__ uint32_t cl_map(const void* p, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// the same without memory ordering: for hand-backs that only order tcgen05 operations (TMEM reads before the next MMAs
+// into the same columns), which the tcgen05.fence pair around the barrier covers; a cluster-scope release costs a MEMBAR
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot) {

@@ -137,6 +137,11 @@ TC_CASES = [
     (10, 4, 4, 512, 256, 4, 2, 1, 1),
     # partial pixel tiles (12 of 16 columns, 4 of 8 rows) with BatchNorm statistics fused in the staged epilogue
     (6, 12, 12, 64, 64, 3, 1, 1, 1),
+    # shifted-window CTA-pair kernel (k4 s2 p1, 64 / 128 output channels, class grid of 16-row x 8-column tiles): the
+    # decoder's 128 -> 64 layer and its input gradient, an odd tile count with one image per BatchNorm group, two tile rows
+    (5, 32, 32, 64, 128, 4, 2, 1, 1),
+    (3, 32, 16, 64, 128, 4, 2, 1, 3),
+    (4, 64, 32, 64, 128, 4, 2, 1, 2),
 ]
 
 
@@ -177,22 +182,25 @@ def test_conv_forward_tensor_core(case, mode):
     close(o_tc.cpu(), o_simt.cpu(), dtype, 'tc vs simt', outliers=1e-4)
 
 
-def test_conv_forward_many_tiles():
-    """More than 8 pixel tiles per SM (several work items per persistent CTA): the decoder's 128 -> 64 transposed
-    layer, 160 images, two BatchNorm groups."""
-    test_conv_forward_tensor_core((160, 32, 32, 64, 128, 4, 2, 1, 2), L.TRANSPOSED)
+@pytest.mark.parametrize('mode', [L.DIRECT, L.TRANSPOSED])
+def test_conv_forward_many_tiles(mode):
+    """More than four work items per CTA pair (the default threshold of the shifted-window kernel): the decoder's
+    128 -> 64 layer / its input gradient on 300 images, two BatchNorm groups."""
+    test_conv_forward_tensor_core((300, 32, 32, 64, 128, 4, 2, 1, 2), mode)
 
 
-@pytest.mark.timeout(1200)
-def test_conv_forward_resident_weights_all_geometries():
-    """Every tensor-core case again in a fresh process with the opt-in resident-weight CTA-pair kernel switched on for
-    all eligible layers (64 / 128 output channels, whole 64-channel chunks, weight slabs <= 128 KB), whatever their size."""
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize('env', [{'VARSEP_SHIFT_MIN_ITEMS': '1'},
+                                 {'VARSEP_DISABLE_SHIFT': '1', 'VARSEP_RESIDENT_OC': '3', 'VARSEP_RESIDENT_MIN_ITEMS': '1'}],
+                         ids=['shift', 'resident'])
+def test_conv_forward_size_gated_kernels(env):
+    """Every tensor-core case again in a fresh process with the size-gated kernels forced on for all eligible layers
+    whatever their size: the shifted-window kernel, and the opt-in resident-weight variant of the CTA-pair kernel."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, VARSEP_RESIDENT_OC='3', VARSEP_RESIDENT_MIN_ITEMS='1')
-    r = subprocess.run([sys.executable, '-m', 'pytest', __file__, '-x', '-q', '-m', 'gpu', '-k', 'test_conv_forward_tensor_core or test_conv_forward_many_tiles',
-                        '-p', 'no:cacheprovider'], env=env, capture_output=True, text=True,
+    r = subprocess.run([sys.executable, '-m', 'pytest', __file__, '-x', '-q', '-m', 'gpu', '-k', 'test_conv_forward_tensor_core',
+                        '-p', 'no:cacheprovider'], env=dict(os.environ, **env), capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
