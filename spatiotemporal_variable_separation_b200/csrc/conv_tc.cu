@@ -138,31 +138,36 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_conv_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp stays converged in the loop, so that barrier addresses and descriptors are
+        // computed on the uniform datapath (a lane-0-only loop re-derived them per instruction through R2UR/ELECT
+        // sequences, ~17 instructions per MMA: more than a 64-column MMA lasts); one elected lane issues =====
+        {
             constexpr uint32_t idesc = idesc_bf16_f32(BN);
-            int it = 0, lt = 0;
+            const bool elected = elect_one();
+            int s = 0, lt = 0;
+            uint32_t ph = 0;
             for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
                 const int acc = lt & 1;
                 mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + S::A_BYTES;
+                    const uint32_t a_lo = kmajor_sw128_desc_lo(smem_u32(smem + s * S::STAGE_BYTES));
+                    const uint32_t b_lo = a_lo + S::A_BYTES / 16;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
-                        umma_bf16(tmem_d, kmajor_sw128_desc(a_addr + k * 32), kmajor_sw128_desc(b_addr + k * 32), idesc,
-                                  (kb | k) != 0 ? 1u : 0u);
+                        const uint64_t ad = kmajor_sw128_desc_from_lo(a_lo + 2 * k), bd = kmajor_sw128_desc_from_lo(b_lo + 2 * k);
+                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        if (elected) umma_bf16(tmem_d, ad, bd, idesc, accum);
                     }
-                    umma_commit(&empty[s]);          // smem slot reusable once these MMAs have read it
+                    if (elected) umma_commit(&empty[s]);          // smem slot reusable once these MMAs have read it
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);        // accumulator of this tile complete
+                if (elected) umma_commit(&tmem_full[acc]);        // accumulator of this tile complete
             }
+            __syncwarp();
         }
     } else {
         // ===== epilogue: warps 2..9.  A warp may only touch the TMEM lane quarter (warp % 4); the two warps that share a
@@ -694,34 +699,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_pair_kernel(const __gri
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread of the leader CTA =====
-        if (leader && lane == 0) {
+        // ===== MMA issuer: the leader CTA's warp 1, converged (see tc_conv_kernel); one elected lane issues =====
+        if (leader) {
             constexpr uint32_t idesc = idesc_bf16_f32_pair(BN);
+            const bool elected = elect_one();
             if (RESB) mbar_wait(bres_full, 0);
-            int it = 0, lt = 0;
+            const uint32_t bres_lo = kmajor_sw128_desc_lo(smem_u32(bres));
+            int s = 0, lt = 0;
+            uint32_t ph = 0;
             for (int idx = t_begin; idx < t_end; ++idx, ++lt) {
                 const int acc = lt & 1;
                 const int cls_m = idx % p.classes;
                 mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t a_lo = kmajor_sw128_desc_lo(smem_u32(smem + s * S::STAGE_BYTES));
                     const int tap_m = kb / p.kchunks;
-                    const uint32_t b_addr = RESB ? smem_u32(bres + (p.wtap[cls_m * p.ntaps + tap_m] * p.kchunks + (kb - tap_m * p.kchunks)) * S::B_BYTES)
-                                                 : a_addr + S::A_BYTES;
+                    const uint32_t b_lo = RESB ? bres_lo + (uint32_t)((p.wtap[cls_m * p.ntaps + tap_m] * p.kchunks + (kb - tap_m * p.kchunks)) * (S::B_BYTES / 16))
+                                               : a_lo + S::A_BYTES / 16;
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k)
-                        umma_bf16_pair(tmem_d, kmajor_sw128_desc(a_addr + k * 32), kmajor_sw128_desc(b_addr + k * 32), idesc,
-                                       (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_pair(&empty[s]);
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint64_t ad = kmajor_sw128_desc_from_lo(a_lo + 2 * k), bd = kmajor_sw128_desc_from_lo(b_lo + 2 * k);
+                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        if (elected) umma_bf16_pair(tmem_d, ad, bd, idesc, accum);
+                    }
+                    if (elected) umma_commit_pair(&empty[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                umma_commit_pair(&tmem_full[acc]);
+                if (elected) umma_commit_pair(&tmem_full[acc]);
             }
+            __syncwarp();
         }
     } else {
         // ===== epilogue (both CTAs): own 128 pixel rows of the pair tile =====
@@ -1745,25 +1755,29 @@ __global__ void __launch_bounds__(192, 2) tc_wgrad_kernel(const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // converged warp, one elected lane issues (see tc_conv_kernel)
             // D=f32, A=B=bf16, both MN-major (bits 15, 16), M=128, N=BN
             constexpr uint32_t idesc = idesc_bf16_f32(BN) | (1u << 15) | (1u << 16);
+            const bool elected = elect_one();
+            int st = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&full[st], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + st * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + A_BYTES;
+                const uint32_t a_lo = mnmajor_sw128_desc_lo(smem_u32(smem + st * STAGE_BYTES), CHUNK);
+                const uint32_t b_lo = a_lo + A_BYTES / 16;
 #pragma unroll
                 for (int k = 0; k < PIX / 16; ++k) {
                     // 16 pixels = two 8-pixel swizzle groups = 2048 bytes along K
-                    umma_bf16(tmem_base, mnmajor_sw128_desc(a_addr + k * 2048, CHUNK), mnmajor_sw128_desc(b_addr + k * 2048, CHUNK),
-                              idesc, (kb | k) != 0 ? 1u : 0u);
+                    const uint64_t ad = kmajor_sw128_desc_from_lo(a_lo + k * 128), bd = kmajor_sw128_desc_from_lo(b_lo + k * 128);
+                    const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                    if (elected) umma_bf16(tmem_base, ad, bd, idesc, accum);
                 }
-                umma_commit(&empty[st]);
+                if (elected) umma_commit(&empty[st]);
+                if (++st == STAGES) { st = 0; ph ^= 1; }
             }
-            umma_commit(tmem_full);
+            if (elected) umma_commit(tmem_full);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -1866,22 +1880,27 @@ __global__ void __launch_bounds__(192, 2) tc_wgrad_taps_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // converged warp, one elected lane issues (see tc_conv_kernel)
             constexpr uint32_t idesc = idesc_bf16_f32(BN) | (1u << 15) | (1u << 16);      // both operands MN-major
+            const bool elected = elect_one();
+            int st = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&full[st], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + st * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + A_BYTES;
+                const uint32_t a_lo = mnmajor_sw128_desc_lo(smem_u32(smem + st * STAGE_BYTES), CHUNK);
+                const uint32_t b_lo = a_lo + A_BYTES / 16;
 #pragma unroll
-                for (int k = 0; k < PIX / 16; ++k)
-                    umma_bf16(tmem_base, mnmajor_sw128_desc(a_addr + k * 2048, CHUNK), mnmajor_sw128_desc(b_addr + k * 2048, CHUNK),
-                              idesc, (kb | k) != 0 ? 1u : 0u);
-                umma_commit(&empty[st]);
+                for (int k = 0; k < PIX / 16; ++k) {
+                    const uint64_t ad = kmajor_sw128_desc_from_lo(a_lo + k * 128), bd = kmajor_sw128_desc_from_lo(b_lo + k * 128);
+                    const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                    if (elected) umma_bf16(tmem_base, ad, bd, idesc, accum);
+                }
+                if (elected) umma_commit(&empty[st]);
+                if (++st == STAGES) { st = 0; ph ^= 1; }
             }
-            umma_commit(tmem_full);
+            if (elected) umma_commit(tmem_full);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -1992,21 +2011,27 @@ __global__ void __launch_bounds__(192, 2) tc_wgrad_pair_kernel(const __grid_cons
                 }
             }
         } else if (warp == 1) {
-            if (leader && lane == 0) {
+            if (leader) {   // converged warp, one elected lane issues (see tc_conv_kernel)
                 constexpr uint32_t idesc = idesc_bf16_f32_pair(BN) | (1u << 15) | (1u << 16);      // both operands MN-major
+                const bool elected = elect_one();
+                int st = 0;
+                uint32_t ph = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    const int st = kb % STAGES;
-                    mbar_wait(&full[st], (kb / STAGES) & 1);
+                    mbar_wait(&full[st], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + st * STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + A_BYTES;
+                    const uint32_t a_lo = mnmajor_sw128_desc_lo(smem_u32(smem + st * STAGE_BYTES), CHUNK);
+                    const uint32_t b_lo = a_lo + A_BYTES / 16;
 #pragma unroll
-                    for (int k = 0; k < PIX / 16; ++k)
-                        umma_bf16_pair(tmem_base, mnmajor_sw128_desc(a_addr + k * 2048, CHUNK), mnmajor_sw128_desc(b_addr + k * 2048, CHUNK),
-                                       idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_pair(&empty[st]);
+                    for (int k = 0; k < PIX / 16; ++k) {
+                        const uint64_t ad = kmajor_sw128_desc_from_lo(a_lo + k * 128), bd = kmajor_sw128_desc_from_lo(b_lo + k * 128);
+                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        if (elected) umma_bf16_pair(tmem_base, ad, bd, idesc, accum);
+                    }
+                    if (elected) umma_commit_pair(&empty[st]);
+                    if (++st == STAGES) { st = 0; ph ^= 1; }
                 }
-                umma_commit_pair(tmem_full);
+                if (elected) umma_commit_pair(tmem_full);
+                __syncwarp();
             }
         } else {
             const int q = warp & 3;

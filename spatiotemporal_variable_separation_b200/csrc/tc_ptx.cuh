@@ -146,6 +146,10 @@ __device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t saddr, uint32_t 
            (2ull << 61);
 }
 
+__device__ __forceinline__ uint32_t mnmajor_sw128_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+
 // TMA store of a shared-memory box (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
