@@ -469,8 +469,8 @@ def _shutdown(tr, world):
 
 
 def kernel_rooflines(tr, shape, dev, draws, dtype):
-    """(1) Roofline of the dominant kernel family, the tcgen05 tap GEMM (tc_conv_kernel and its CTA-pair variant
-    tc_conv_pair_kernel: fprop and dgrad of every eligible conv layer).  CUDA events on the launching stream around each
+    """(1) Roofline of the dominant kernel family, the tcgen05 tap GEMM (tc_conv_kernel, its CTA-pair variant
+    tc_conv_pair_kernel and the shifted-window variant tc_conv_shift_kernel: fprop and dgrad of every eligible conv layer).  CUDA events on the launching stream around each
     vs_conv_forward call of two extra eager steps (each pair enqueued behind a short spin kernel, so that the interval
     is the kernel's duration and not its launch latency); only the calls that the library routes to the tensor-core
     kernel (vs_conv_forward_path == 1) are counted.  Algorithmic FLOPs per launch = 2*N*P*Q*K*C*R*S (for a stride-2
@@ -531,7 +531,7 @@ def kernel_rooflines(tr, shape, dev, draws, dtype):
     tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get('tc_conv_kernel', {}).get('dram_bytes_per_launch')
-    roof = {'bound': 'tensor', 'kernel': 'tc_conv_kernel + tc_conv_pair_kernel (tcgen05 tap GEMM: every fprop / dgrad launch of the eligible conv layers)',
+    roof = {'bound': 'tensor', 'kernel': 'tc_conv_kernel + tc_conv_pair_kernel + tc_conv_shift_kernel (tcgen05 tap GEMM: every fprop / dgrad launch of the eligible conv layers)',
             'achieved': tot_flop / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0, 'unit': 'TFLOP/s',
             'launches': len(conv_rec) // n_steps, 'avg_launch_ms': tot_ms / max(len(conv_rec), 1),
             'flop_per_launch': tot_flop / max(len(conv_rec), 1), 'traffic': traffic,

@@ -12,7 +12,7 @@ echo "== launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches_mnist_bf16.csv python scripts/profile_step.py > $O/prof.log 2>&1
 python scripts/summarize_launches.py $O/launches_mnist_bf16.csv > $O/launch_summary_mnist_bf16.txt; head -12 $O/launch_summary_mnist_bf16.txt
 echo "== ncu full: tensor-core convolution launches"
-timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:tc_conv_(pair_)?kernel" -c 40 -o /tmp/r02_tc_conv -f python scripts/profile_step.py > $O/ncu_tc_conv.log 2>&1; tail -1 $O/ncu_tc_conv.log
+timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:tc_conv_(pair_|shift_)?kernel" -c 40 -o /tmp/r02_tc_conv -f python scripts/profile_step.py > $O/ncu_tc_conv.log 2>&1; tail -1 $O/ncu_tc_conv.log
 ncu -i /tmp/r02_tc_conv.ncu-rep --page raw --csv > /tmp/r02_tc_conv_raw.csv 2>/dev/null
 python scripts/summarize_ncu_raw.py /tmp/r02_tc_conv_raw.csv > $O/ncu_per_launch_tc_conv.txt; head -30 $O/ncu_per_launch_tc_conv.txt
 python - <<'PY'
@@ -26,7 +26,7 @@ def val(r, name):
 rd = sum(val(r, 'dram__bytes_read.sum') for r in rows[2:]); wr = sum(val(r, 'dram__bytes_write.sum') for r in rows[2:])
 n = len(rows) - 2
 out = {'tc_conv_kernel': {'launches': n, 'dram_bytes_per_launch': (rd + wr) / max(n, 1), 'dram_read_bytes_total': rd, 'dram_write_bytes_total': wr},
-       'how': 'ncu --set full -k regex:tc_conv_(pair_)?kernel over one eager training step (mnist DCGAN, batch 128, bf16), round 2'}
+       'how': 'ncu --set full -k regex:tc_conv_(pair_|shift_)?kernel over one eager training step (mnist DCGAN, batch 128, bf16), round 2'}
 json.dump(out, open('gpurun_out/r02/roofline_traffic.json', 'w'), indent=1); print(out)
 PY
 for spec in "bn_apply_dec2:bn_bwd_apply_col_kernel:0" "tail_col2im_xf:convT_col2im_kernel:0" "wgrad_taps_dec1:tc_wgrad_taps_kernel:1" "peerless_pack:pack_multi_kernel:0" "rollout_fwd:rollout_cluster_kernel:0"; do

@@ -184,18 +184,19 @@ def test_conv_forward_tensor_core(case, mode):
 
 @pytest.mark.parametrize('mode', [L.DIRECT, L.TRANSPOSED])
 def test_conv_forward_many_tiles(mode):
-    """More than four work items per CTA pair (the default threshold of the shifted-window kernel): the decoder's
-    128 -> 64 layer / its input gradient on 300 images, two BatchNorm groups."""
+    """Several work items per CTA pair of the shifted-window kernel (ring and accumulator stages wrap, statistics
+    flushed between BatchNorm groups): the decoder's 128 -> 64 layer / its input gradient on 300 images."""
     test_conv_forward_tensor_core((300, 32, 32, 64, 128, 4, 2, 1, 2), mode)
 
 
 @pytest.mark.timeout(1800)
-@pytest.mark.parametrize('env', [{'VARSEP_SHIFT_MIN_ITEMS': '1'},
+@pytest.mark.parametrize('env', [{'VARSEP_DISABLE_SHIFT': '1'},
                                  {'VARSEP_DISABLE_SHIFT': '1', 'VARSEP_RESIDENT_OC': '3', 'VARSEP_RESIDENT_MIN_ITEMS': '1'}],
-                         ids=['shift', 'resident'])
-def test_conv_forward_size_gated_kernels(env):
-    """Every tensor-core case again in a fresh process with the size-gated kernels forced on for all eligible layers
-    whatever their size: the shifted-window kernel, and the opt-in resident-weight variant of the CTA-pair kernel."""
+                         ids=['per_class', 'resident'])
+def test_conv_forward_alternative_kernels(env):
+    """Every tensor-core case again in a fresh process with the kernels the default selection no longer reaches: the
+    per-class kernels on the layers the shifted-window kernel takes, and the opt-in resident-weight variant of the
+    CTA-pair kernel on every eligible layer whatever its size."""
     import os
     import subprocess
     import sys
