@@ -310,6 +310,26 @@ def test_long_horizon_rollout_95_frames_bf16():
     assert torch.equal(f100[:, :10].contiguous(), f10.contiguous())
 
 
+def test_eval_forecast_is_batch_invariant_bf16():
+    """SURVEY H6 on the tensor-core path: full-size DCGAN, bf16, eval mode — a sequence's forecast does not depend on what
+    else is in the batch (kernel selection is a property of the layer, never of the batch size: per-class, CTA-pair and
+    shifted-window kernels give the same bits for a sample whatever the number of images in the launch)."""
+    cfg = configs.preset('mnist', extra='--batch_size 8')
+    from spatiotemporal_variable_separation_b200.networks.factory import build_model
+    from spatiotemporal_variable_separation_b200.data import synthetic_batch
+    ops.set_compute_dtype(torch.bfloat16)
+    torch.manual_seed(0)
+    net = build_model(cfg, 'cuda').eval()
+    cond = synthetic_batch(cfg, device='cuda')[:, :cfg['nt_cond']].contiguous()
+    with torch.no_grad():
+        f8, t8, _, _ = net.get_forecast(cond, 10)
+        f3, t3, _, _ = net.get_forecast(cond[:3].contiguous(), 10)
+        f1, t1, _, _ = net.get_forecast(cond[2:3].contiguous(), 10)
+    assert torch.equal(t8[:3].contiguous(), t3.contiguous()) and torch.equal(t8[2:3].contiguous(), t1.contiguous())
+    assert torch.equal(f8[:3].contiguous(), f3.contiguous())
+    assert torch.equal(f8[2:3].contiguous(), f1.contiguous())
+
+
 def test_checkpoint_resume_on_the_gpu(tmp_path):
     """SURVEY 8f N3 on the device: save (reference-format module pickles + training state) after two graphed steps,
     reload into a fresh model / optimizer / stepper and continue: identical arenas as the uninterrupted run up to the
