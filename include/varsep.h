@@ -89,6 +89,12 @@ int vs_conv_forward(const vs_conv_geom* g, int32_t mode, const void* in, const v
  * the measured launch times to the tensor-core kernel for the roofline. */
 int vs_conv_forward_path(const vs_conv_geom* g, int32_t mode);
 
+/* For a geometry on path 1: which tap-GEMM kernel is launched (default switches, 16-byte aligned tensors): 1 = per-class
+ * single-CTA kernel, 2 = CTA-pair kernel (cta_group::2), 3 = shifted-window CTA-pair kernel with resident weights; 0 on
+ * every other path.  A function of the layer geometry and dtype only — never of the batch size g->N (a sample's result
+ * must not depend on what else is in the launch).  Host-only (no launch). */
+int vs_conv_forward_variant(const vs_conv_geom* g, int32_t mode);
+
 /* replaces: aten::convolution_backward, weight part.  dw[K][C][R][S] (fp32, torch layout) +=
  * sum over pixels of small[n,p,q,k] * big[n, p*stride-pad+r, q*stride-pad+s, c].
  * For nn.Conv2d small = dy, big = x; for nn.ConvTranspose2d small = x, big = dy. */

@@ -39,6 +39,7 @@ SIGNATURES = {
     'vs_pack_weights_multi': [_p, _i32, _i32, _p],
     'vs_conv_forward': [_PG, _i32, _p, _p, _p, _p, _p, _p],
     'vs_conv_forward_path': [_PG, _i32],
+    'vs_conv_forward_variant': [_PG, _i32],
     'vs_conv_wgrad': [_PG, _p, _p, _p, _p],
     'vs_colsum': [_p, _i32, _i64, _i32, _p, _p],
     'vs_bn_finalize': [_p, _i32, _i32, _i64, _f, _f, _p, _p, _p, _p, _p, _p],

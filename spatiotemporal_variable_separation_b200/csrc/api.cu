@@ -118,6 +118,7 @@ int conv_forward_col2im_eligible(const vs_conv_geom* g, int mode);
 int conv_forward_im2col_eligible(const vs_conv_geom* g, int mode);
 int conv_forward_tc_eligible(const vs_conv_geom* g, int mode);
 int conv_forward_thin_eligible(const vs_conv_geom* g, int mode);
+int conv_forward_tc_variant(const vs_conv_geom* g, int mode);
 }
 extern "C" int vs_conv_forward_path(const vs_conv_geom* g, int32_t mode) {
     if (check_geom(g)) return -1;
@@ -127,6 +128,11 @@ extern "C" int vs_conv_forward_path(const vs_conv_geom* g, int32_t mode) {
     if (conv_forward_tc_eligible(g, mode)) return 1;
     if (conv_forward_thin_eligible(g, mode)) return 2;
     return 0;
+}
+
+extern "C" int vs_conv_forward_variant(const vs_conv_geom* g, int32_t mode) {
+    if (vs_conv_forward_path(g, mode) != 1) return 0;
+    return conv_forward_tc_variant(g, mode);
 }
 
 extern "C" int vs_conv_wgrad(const vs_conv_geom* g, const void* small_, const void* big, float* dw, void* stream) {

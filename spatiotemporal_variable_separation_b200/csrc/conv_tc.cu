@@ -1512,6 +1512,29 @@ int conv_forward_tc_eligible(const vs_conv_geom* g, int mode) {
     return 1;
 }
 
+// Which of the tap-GEMM kernels conv_forward_tc launches for a geometry it accepts, from the geometry alone (default
+// switches, 16-byte aligned tensors): 1 = per-class single-CTA kernel, 2 = CTA-pair kernel, 3 = shifted-window kernel.
+// Host-only mirror of the selection below for vs_conv_forward_variant; the batch size g->N does not enter.
+int conv_forward_tc_variant(const vs_conv_geom* g, int mode) {
+    if (!conv_forward_tc_eligible(g, mode)) return 0;
+    const bool tr = mode == VS_CONV_TRANSPOSED;
+    const int IC = tr ? g->K : g->C, OC = tr ? g->C : g->K;
+    const int OH = tr ? g->H : g->P, OW = tr ? g->W : g->Q;
+    const int st = g->stride;
+    const bool one_px = tr && g->P == 1 && g->Q == 1 && g->pad == 0 && st == 1 && g->R == g->S && g->R * g->S <= TC_MAX_CLASSES;
+    const int cst = one_px ? g->R : st, ost = tr ? cst : 1;
+    const int kchunks = (IC + 63) / 64;
+    const bool aligned_rows = OC % 8 == 0;
+    if (!one_px && g->R == 4 && g->S == 4 && st == 2 && g->pad == 1 && (OC == 64 || OC == 128) && IC % 64 == 0 &&
+        (OH / ost) % TCS_HT == 0 && (OW / ost) % TCS_WT == 0 && 16 * kchunks * (OC / 64) <= TCS_PIECES &&
+        (tr ? (OC == 64 && 3 * kchunks <= TCS_MAX_BOX) : kchunks == 1))
+        return 3;
+    const int ntaps = !tr ? g->R * g->S : one_px ? 1 : (g->R / cst) * (g->S / cst);
+    const int PBN = OC % 256 == 0 ? 256 : 128;
+    if (OC % 128 == 0 && IC >= 64 && aligned_rows && (PBN == 256 || ntaps * kchunks >= 64)) return 2;
+    return 1;
+}
+
 // returns 0 = done, -1 = geometry not eligible (caller falls back), >0 = error
 int conv_forward_tc(const vs_conv_geom* g, int mode, const void* in, const void* wp, const float* bias, void* out,
                     double* stats, cudaStream_t stream) {
